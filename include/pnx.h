@@ -1,0 +1,136 @@
+/* pnx.h -- C-ABI of libpnx.so, the B200 (sm_100a) hot path of PillarNeXt-B.
+ *
+ * Boundary rules: extern "C", plain pointers and sizes, no torch types.
+ * The caller owns every buffer (device memory unless stated), kernels never allocate and never
+ * synchronise, everything is enqueued on the `stream` argument (the caller passes its current
+ * stream; the reference's only native extension, iou3d_nms, uses the legacy default stream and
+ * exit()s on error -- /root/reference/det3d/core/iou3d_nms/src/iou3d_nms.cpp:14-38 -- neither is
+ * copied).  Every entry point returns 0 on success or a negative PNX_ERR_* code;
+ * pnx_last_error() returns the thread-local message.  Variable-size results (pillars, sites)
+ * are written into fixed-capacity buffers with the true count in device memory (`counts`).
+ *
+ * The reference reaches this path through Python modules, not an FFI (its third-party CUDA ops
+ * are torch_scatter / spconv / cuDNN); each entry point cites the reference lines it replaces.
+ */
+#ifndef PNX_H_
+#define PNX_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define PNX_OK 0
+#define PNX_ERR_ARG (-1)
+#define PNX_ERR_CUDA (-2)
+#define PNX_ERR_CAPACITY (-3)
+
+const char* pnx_last_error(void);
+int pnx_abi_version(void);
+int pnx_sm_count(void);
+
+/* ---------------------------------------------------------------- generic device scan
+ * out[i] = sum_{j<i} f(in[j]), i in [0,n]; f = popcount (popc=1) or identity on int32 (popc=0).
+ * block_sums: scratch of (n+1)/2048 + 2 ints; total_out (optional) receives out[n]. */
+int pnx_scan_u32(const uint32_t* in, int n, int popc, int* out, int* block_sums, int* total_out,
+                 cudaStream_t stream);
+
+/* ---------------------------------------------------------------- V1-V3 voxelizer
+ * Replaces PillarNet.forward index generation, det3d/models/readers/pillar_encoder.py:86-111
+ * (range mask, trunc, torch.unique(dim=0, return_inverse=True)) bit-exactly, without a sort.
+ *   points        [n_points, 6] fp32 (batch_idx, x, y, z, intensity, time), 16-byte aligned
+ *   bitmap        pnx_voxelize_bitmap_words() u32, occupancy in (b, xi, yi) order (zeroed here)
+ *   word_prefix   [words+1]  exclusive popcount prefix (rank of a bit = pillar id)
+ *   scan_scratch  [max(words, cap_pillars)/2048 + 2]
+ *   cell_of_point [n_points] scratch
+ *   pillar_of_point [n_points] OUT: pillar id (== reference `unq_inv`) or -1 for dropped points
+ *   coords        [cap_pillars, 3] OUT int32 (b, yi, xi), rows in the reference's sorted-unique order
+ *   bucket_cnt    [2*(cap_pillars+1)] scratch;  bucket_off [cap_pillars+1] OUT CSR offsets
+ *   bucket_tmp    [n_points] scratch;           bucket_pts [n_points] OUT point ids grouped by pillar,
+ *                                                ascending inside a pillar
+ *   counts        [2] OUT device ints: {#pillars P, #kept points Nv}
+ * cap_pillars must be >= min(n_points, batch*gx*gy). */
+size_t pnx_voxelize_bitmap_words(int batch, int gx, int gy);
+int pnx_voxelize(const float* points, int n_points, int batch, float min_x, float min_y, float vs_x,
+                 float vs_y, int gx, int gy, uint32_t* bitmap, int* word_prefix, int* scan_scratch,
+                 int* cell_of_point, int* pillar_of_point, int* coords, int cap_pillars,
+                 uint32_t* bucket_cnt, int* bucket_off, int* bucket_tmp, int* bucket_pts, int* counts,
+                 cudaStream_t stream);
+
+/* ---------------------------------------------------------------- BatchNorm statistics
+ * stats = [2*C] fp64 (sum, sum of squares) accumulated by the producing kernel.
+ * count = (*count_ptr if non-NULL else 1) * count_mult.  Writes scale/shift (y = x*scale+shift),
+ * optional mean/invstd (for backward) and updates running_mean/var like torch
+ * (nn.BatchNorm1d/2d training forward; pillar_encoder.py:33, sparse_conv.py:31,52, conv.py:27). */
+int pnx_bn_finalize(const double* stats, int channels, const int* count_ptr, long long count_mult,
+                    const float* gamma, const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var, float* scale, float* shift,
+                    float* mean_out, float* invstd_out, cudaStream_t stream);
+int pnx_bn_eval_affine(int channels, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift,
+                       cudaStream_t stream);
+
+/* ---------------------------------------------------------------- P1-P3 PillarFeatureNet (forward)
+ * Replaces pillar_encoder.py:113-123 (scatter_mean + decoration), :35-50 (PFNLayer x2), :180.
+ * counts = the voxelizer's device counts.  y0 [cap_points,32], y1 [cap_points,64] fp32 (rows in
+ * bucket order), x0max [cap_pillars,32], mean [cap_pillars,3], stats fp64 accumulated in place. */
+int pnx_pfn_mean(const float* points, const int* bucket_off, const int* bucket_pts, const int* counts,
+                 int cap_pillars, float* mean, cudaStream_t stream);
+int pnx_pfn_lin0(const float* points, const int* bucket_pts, const int* pillar_of_point,
+                 const int* coords, const float* mean, const int* counts, int cap_points, float min_x,
+                 float min_y, float vs_x, float vs_y, const float* w0, float* y0, double* stats,
+                 int training, cudaStream_t stream);
+int pnx_pfn_max0(const float* y0, const int* bucket_off, const int* counts, int cap_pillars,
+                 const float* scale, const float* shift, float* x0max, cudaStream_t stream);
+int pnx_pfn_lin1(const float* y0, const float* x0max, const int* bucket_pts, const int* pillar_of_point,
+                 const int* counts, int cap_points, const float* scale0, const float* shift0,
+                 const float* w1, float* y1, double* stats, int training, cudaStream_t stream);
+int pnx_pfn_max1(const float* y1, const int* bucket_off, const int* counts, int cap_pillars,
+                 const float* scale, const float* shift, float* feat_f32, void* feat_bf16,
+                 cudaStream_t stream);
+
+/* ---------------------------------------------------------------- B1-B4 active sites / rulebook
+ * Replaces spconv index-pair generation (sparse_conv.py:25-29,50-51; sparse_resnet.py:43-48,63-64).
+ * Bitmaps are in (b, u=x, v=y) order, v padded to 32 bits; coords are (b, u, v) int32. */
+int pnx_sites_out_dim(int in_dim, int stride);
+int pnx_sites_dilate(const uint32_t* bm_in, int batch, int u_in, int v_in, int stride, uint32_t* bm_out,
+                     cudaStream_t stream);
+int pnx_sites_coords(const uint32_t* bm, const int* prefix, int batch, int u, int v, int* coords, int cap,
+                     cudaStream_t stream);
+/* nbr [cap, 9] int32: row index in the source level feeding site i through tap t = ku*3+kv, -1 = absent.
+ * transposed=1 builds the data-gradient table of a (strided) SparseConv2d. */
+int pnx_nbr_table(const int* dst_coords, const int* n_dst_ptr, int cap, const uint32_t* src_bm,
+                  const int* src_prefix, int batch, int src_u, int src_v, int stride, int transposed,
+                  int* nbr, cudaStream_t stream);
+/* x.dense() (sparse_resnet.py:68): feat [n, C] bf16 -> zeroed channels-last canvas [B, V, U, C]
+ * (gather=0) or the reverse (gather=1, used by backward). */
+int pnx_scatter_dense(const void* feat, const int* coords, const int* n_ptr, int cap, int channels,
+                      int batch, int u, int v, void* canvas, int gather, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- tcgen05 gather implicit GEMM
+ * out[m, n] = sum_{t<taps} sum_{c<Cin} A[nbr(m,t), c] * W[t, n, c]  (+ bias[n]) (relu)
+ *   A       [rows, lda] bf16        W  [taps, Cout, Cin] bf16 (packed, K-major)
+ *   nbr(m,t): nbr[m*taps+t] if nbr != NULL; computed from the dense geometry if dense != 0
+ *             (m -> (b, y, x) over Hout x Wout; source pixel (y*mul + r*dil - pad, x*mul + s*dil - pad)
+ *             in an Hin x Win image, t = r*kw + s; out of range = zero);  m itself otherwise (taps==1).
+ *   out     bf16 (out_fp32=0) or fp32, row stride ldc elements; shuffle=1: ConvTranspose2d k2 s2
+ *           pixel-shuffle store (column n = q*64 + co -> pixel (2y + q/2, 2x + q%2), channel co)
+ *   stats   optional fp64 [2*stats_C]: per-channel sum / sum of squares of the stored values
+ *           (channel = n % stats_mod), for the BatchNorm that follows the convolution.
+ * Replaces spconv SparseConv2d/SubMConv2d (sparse_conv.py:25-29,50-51), F.conv2d/nn.Conv2d
+ * (aspp.py:19-32, conv.py:9-10, centerhead.py:35-46,108-114), nn.ConvTranspose2d (centerhead.py:26-27). */
+int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void* Wpacked, int Cout,
+              int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
+              int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
+              double* stats, int stats_C, int stats_mod, int shuffle, int relu, int sm_count,
+              cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNX_H_ */

@@ -1,0 +1,91 @@
+"""ctypes binding of libpnx.so (C-ABI declared in include/pnx.h).
+
+The library is the product; there is NO fallback: if it is missing (and cannot be built) or an entry
+point fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpnx.so")
+_lib = None
+
+P = ctypes.c_void_p
+I = ctypes.c_int
+L = ctypes.c_longlong
+F = ctypes.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPE)
+_SIGS = {
+    "pnx_last_error": [],
+    "pnx_abi_version": [],
+    "pnx_sm_count": [],
+    "pnx_scan_u32": [P, I, I, P, P, P, P],
+    "pnx_voxelize_bitmap_words": [I, I, I],
+    "pnx_voxelize": [P, I, I, F, F, F, F, I, I, P, P, P, P, P, P, I, P, P, P, P, P, P],
+    "pnx_bn_finalize": [P, I, P, L, P, P, F, F, P, P, P, P, P, P, P],
+    "pnx_bn_eval_affine": [I, P, P, P, P, F, P, P, P],
+    "pnx_pfn_mean": [P, P, P, P, I, P, P],
+    "pnx_pfn_lin0": [P, P, P, P, P, P, I, F, F, F, F, P, P, P, I, P],
+    "pnx_pfn_max0": [P, P, P, I, P, P, P, P],
+    "pnx_pfn_lin1": [P, P, P, P, P, I, P, P, P, P, P, I, P],
+    "pnx_pfn_max1": [P, P, P, I, P, P, P, P, P],
+    "pnx_sites_out_dim": [I, I],
+    "pnx_sites_dilate": [P, I, I, I, I, P, P],
+    "pnx_sites_coords": [P, P, I, I, I, P, I, P],
+    "pnx_nbr_table": [P, P, I, P, P, I, I, I, I, I, P, P],
+    "pnx_scatter_dense": [P, P, P, I, I, I, I, I, P, I, P],
+    "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, I, P],
+}
+_RESTYPE = {"pnx_last_error": ctypes.c_char_p, "pnx_voxelize_bitmap_words": ctypes.c_size_t}
+
+
+def exported_symbols():
+    """Every symbol include/pnx.h declares (used by the CPU-side load test)."""
+    return sorted(_SIGS)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        from . import build as _build  # compiles with nvcc; raises if impossible
+        _build.build()
+    if not os.path.exists(_SO):
+        raise RuntimeError("pillarnext_b200: libpnx.so is missing and could not be built -- no fallback path exists")
+    l = ctypes.CDLL(_SO)
+    for name, argtypes in _SIGS.items():
+        fn = getattr(l, name)  # AttributeError if the .so does not export what the header declares
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, ctypes.c_int)
+    _lib = l
+    return l
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libpnx error %d: %s" % (rc, lib().pnx_last_error().decode()))
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "libpnx kernels take device pointers"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_sm = None
+
+
+def sm_count():
+    global _sm
+    if _sm is None:
+        _sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _sm

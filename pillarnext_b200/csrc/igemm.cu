@@ -1,0 +1,381 @@
+// igemm.cu -- gather implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// One engine for every convolution on the path (rows B1-B3, N1, H1 of SURVEY.md section 8a; their
+// data-gradients too):   out[m, n] = sum_t sum_c  A[nbr(m,t), c] * W[t, n, c]   (+bias)(relu)
+//   * sparse BEV backbone (spconv SparseConv2d / SubMConv2d, reference sparse_conv.py:25-29,50-51,
+//     sparse_resnet.py:43-48): rows = active sites, nbr = neighbour table from rulebook.cu
+//   * dense neck/head (F.conv2d 3x3 / dilated 3x3 / 1x1, reference aspp.py:19-32, conv.py:9-10,
+//     centerhead.py:35-46,108-114): rows = pixels of a channels-last image, nbr computed from geometry
+//     (zero padding = absent neighbour), ConvTranspose2d k2 s2 (centerhead.py:26-27) = one GEMM with
+//     N = 4*Cout and a pixel-shuffle store.
+// Pipeline per CTA (persistent over 128-row tiles, one CTA per SM):
+//   warp 0      : TMA (cp.async.bulk.tensor) producer of the weight tile  B[BN x 64]  (SWIZZLE_128B)
+//   warps 2..5  : gather producers: cp.async 16 B row chunks of A into the same 128B-swizzled K-major
+//                 layout (zero-fill for absent neighbours), generic->async proxy fence, mbarrier arrive
+//   warp 1      : single-thread tcgen05.mma issue, fp32 accumulators in TMEM (2 stages x BN columns)
+//   warps 6..9  : epilogue: tcgen05.ld -> bias/relu -> bf16|fp32 store, fused BatchNorm statistics
+//                 (per-channel sum / sum of squares, butterfly column reduce, fp64 accumulate)
+#include "pnx_common.cuh"
+
+namespace {
+
+struct IgemmParams {
+  const __nv_bfloat16* A;
+  long long lda;
+  int M, T, Cin, w_rows_per_tap;
+  const int* nbr;
+  int dense, Hout, Wout, Hin, Win, kw, mul, dil, pad;
+  void* out;
+  long long ldc;
+  int out_fp32;
+  const float* bias;
+  double* stats;
+  int stats_C, stats_mod;
+  int shuffle, relu;
+};
+
+constexpr int kThreads = 320;
+constexpr uint32_t kABytes = 128 * 128;
+constexpr int kLag = 2;
+
+template <int BN>
+struct Cfg {
+  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr int kStagesRaw = (196 * 1024) / (int)(kABytes + kBBytes);
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + 128 * 9 * 4 + 256;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+__device__ __forceinline__ float colsum32(float (&v)[32]) {
+  const uint32_t lane = pnx::lane_id();
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      float send = upper ? v[k] : v[k + off];
+      float keep = upper ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, IgemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int kStages = C::kStages;
+  constexpr uint32_t kBBytes = C::kBBytes;
+  constexpr int kColBlk = BN >= 32 ? 32 : 16;
+  constexpr int kNumCB = BN / kColBlk;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)kStages * kABytes;
+  int* s_idx = reinterpret_cast<int*>(sB + (size_t)kStages * kBBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_idx + 128 * 9);
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && pnx::elect_one()) {
+    pnx::tma_prefetch_desc(&wmap);
+    for (int s = 0; s < kStages; ++s) {
+      pnx::mbar_init(&full[s], 1 + 4);
+      pnx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      pnx::mbar_init(&tfull[a], 1);
+      pnx::mbar_init(&tempty[a], 4);
+    }
+    pnx::fence_barrier_init();
+  }
+  if (warp == 1) pnx::tmem_alloc<512>(tmem_slot);
+  pnx::tc_fence_before();
+  __syncthreads();
+  pnx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = (p.M + 127) >> 7;
+  const int n0 = blockIdx.y * BN;
+  const int kpt = p.Cin >> 6;
+  const int num_k = p.T * kpt;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA weight producer
+    if (pnx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < num_k; ++kc) {
+          const int t = kc / kpt, cc = kc - t * kpt;
+          pnx::mbar_wait(&empty[stage], phase ^ 1);
+          pnx::mbar_arrive_expect_tx(&full[stage], kBBytes);
+          pnx::tma_load_2d(&wmap, &full[stage], sB + (size_t)stage * kBBytes, cc * 64, t * p.w_rows_per_tap + n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (pnx::elect_one()) {
+      constexpr uint32_t idesc = pnx::make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        pnx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        pnx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < num_k; ++kc) {
+          pnx::mbar_wait(&full[stage], phase);
+          pnx::tc_fence_after();
+          const uint32_t a_base = pnx::smem_u32(sA + (size_t)stage * kABytes);
+          const uint32_t b_base = pnx::smem_u32(sB + (size_t)stage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = pnx::make_smem_desc_sw128(a_base + k * 32, 0, 1024);
+            const uint64_t db = pnx::make_smem_desc_sw128(b_base + k * 32, 0, 1024);
+            pnx::umma_f16(d_tmem, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+          }
+          pnx::umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        pnx::umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- A gather producers (128 threads)
+    const int ptid = threadIdx.x - 64;
+    const int sub_row = ptid >> 3, chunk = ptid & 7;
+    int stage = 0, arr_stage = 0, pending = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      named_bar_sync(1, 128);
+      {
+        const int m = tile * 128 + ptid;
+        int* row = s_idx + ptid * 9;
+        if (m >= p.M) {
+          for (int t = 0; t < p.T; ++t) row[t] = -1;
+        } else if (p.nbr) {
+          for (int t = 0; t < p.T; ++t) row[t] = p.nbr[(size_t)m * p.T + t];
+        } else if (p.dense) {
+          const int hw = p.Hout * p.Wout;
+          const int b = m / hw, rem = m - b * hw;
+          const int y = rem / p.Wout, x = rem - y * p.Wout;
+          for (int t = 0; t < p.T; ++t) {
+            const int r = t / p.kw, s = t - r * p.kw;
+            const int yi = y * p.mul + r * p.dil - p.pad, xi = x * p.mul + s * p.dil - p.pad;
+            row[t] = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
+          }
+        } else {
+          row[0] = m;
+        }
+      }
+      named_bar_sync(1, 128);
+      for (int kc = 0; kc < num_k; ++kc) {
+        const int t = kc / kpt, cc = kc - t * kpt;
+        pnx::mbar_wait(&empty[stage], phase ^ 1);
+        const uint32_t dst = pnx::smem_u32(sA + (size_t)stage * kABytes);
+        const __nv_bfloat16* col = p.A + cc * 64 + chunk * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = j * 16 + sub_row;
+          const int idx = s_idx[r * 9 + t];
+          const __nv_bfloat16* src = col + (size_t)(idx < 0 ? 0 : idx) * p.lda;
+          pnx::cp_async16(dst + r * 128 + ((chunk ^ (r & 7)) << 4), src, idx < 0 ? 0u : 16u);
+        }
+        pnx::cp_async_commit();
+        if (pending == kLag) {
+          pnx::cp_async_wait<kLag>();
+          pnx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
+          if (++arr_stage == kStages) arr_stage = 0;
+        } else {
+          ++pending;
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    pnx::cp_async_wait<0>();
+    pnx::fence_proxy_async_smem();
+    __syncwarp();
+    for (; pending > 0; --pending) {
+      if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
+      if (++arr_stage == kStages) arr_stage = 0;
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (4 warps = 128 TMEM lanes)
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    double ssum[kNumCB], ssq[kNumCB];
+#pragma unroll
+    for (int i = 0; i < kNumCB; ++i) ssum[i] = ssq[i] = 0.0;
+    const int hw = p.Hout * p.Wout;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      pnx::mbar_wait(&tfull[acc], acc_phase);
+      pnx::tc_fence_after();
+      const int m = tile * 128 + quarter * 32 + lane;
+      const bool active = m < p.M;
+      long long out_row = m;
+      int sh_b = 0, sh_y = 0, sh_x = 0;
+      if (p.shuffle && active) {
+        sh_b = m / hw;
+        const int rem = m - sh_b * hw;
+        sh_y = rem / p.Wout;
+        sh_x = rem - sh_y * p.Wout;
+      }
+#pragma unroll
+      for (int cb = 0; cb < kNumCB; ++cb) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb * kColBlk;
+        if (kColBlk == 32) pnx::tmem_ld_32x32b_x32(taddr, r);
+        else pnx::tmem_ld_32x32b_x16(taddr, r);
+        pnx::tmem_ld_wait();
+        const int ncol0 = n0 + cb * kColBlk;
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < kColBlk; ++k) {
+          float x = __uint_as_float(r[k]);
+          if (p.bias) x += __ldg(p.bias + ncol0 + k);
+          if (p.relu) x = fmaxf(x, 0.f);
+          if (!p.out_fp32) x = pnx::bf16_round(x);
+          v[k] = x;
+        }
+#pragma unroll
+        for (int k = kColBlk; k < 32; ++k) v[k] = 0.f;
+        if (active) {
+          int col = ncol0;
+          if (p.shuffle) {
+            const int q = ncol0 >> 6;
+            out_row = ((long long)(sh_b * 2 * p.Hout + 2 * sh_y + (q >> 1))) * (2 * p.Wout) + 2 * sh_x + (q & 1);
+            col = ncol0 & 63;
+          }
+          if (p.out_fp32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldc + col);
+#pragma unroll
+            for (int k = 0; k < kColBlk / 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + col);
+#pragma unroll
+            for (int k = 0; k < kColBlk / 8; ++k)
+              dst[k] = make_uint4(pnx::pack_bf16x2(v[8 * k], v[8 * k + 1]), pnx::pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                  pnx::pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pnx::pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+          }
+        }
+        if (p.stats) {
+          float a[32], b2[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = active ? v[k] : 0.f;
+            a[k] = x;
+            b2[k] = x * x;
+          }
+          ssum[cb] += (double)colsum32(a);
+          ssq[cb] += (double)colsum32(b2);
+        }
+      }
+      pnx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) pnx::mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.stats) {
+#pragma unroll
+      for (int cb = 0; cb < kNumCB; ++cb) {
+        if (lane < kColBlk) {
+          const int ch = (n0 + cb * kColBlk + lane) % p.stats_mod;
+          atomicAdd(&p.stats[ch], ssum[cb]);
+          atomicAdd(&p.stats[p.stats_C + ch], ssq[cb]);
+        }
+      }
+    }
+  }
+
+  pnx::tc_fence_before();
+  __syncthreads();
+  pnx::tc_fence_after();
+  if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
+}
+
+template <int BN>
+int launch_igemm(const CUtensorMap& wmap, const IgemmParams& p, int n_blocks, int sm_count, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmem));
+    attr_set = true;
+  }
+  const int num_tiles = (p.M + 127) / 128;
+  int gx = sm_count / n_blocks;
+  if (gx < 1) gx = 1;
+  if (gx > num_tiles) gx = num_tiles;
+  dim3 grid(gx, n_blocks);
+  igemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, stream>>>(wmap, p);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
+}  // namespace
+
+// Contract: include/pnx.h (pnx_igemm).
+extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void* Wpacked, int Cout,
+                         int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
+                         int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
+                         double* stats, int stats_C, int stats_mod, int shuffle, int relu, int sm_count,
+                         cudaStream_t stream) {
+  PNX_CHECK_ARG(M >= 0, "M");
+  if (M == 0) return PNX_OK;
+  PNX_CHECK_ARG(taps >= 1 && taps <= 9, "taps in [1,9]");
+  PNX_CHECK_ARG(Cin > 0 && Cin % 64 == 0, "Cin must be a multiple of 64");
+  PNX_CHECK_ARG(Cout % block_n == 0, "Cout % block_n");
+  PNX_CHECK_ARG(lda % 8 == 0 && ldc % 8 == 0, "lda/ldc must be multiples of 8 elements");
+  PNX_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(Wpacked) & 15) == 0,
+                "A/out/W must be 16-byte aligned");
+  PNX_CHECK_ARG(!(nbr && dense), "nbr table and dense geometry are exclusive");
+  PNX_CHECK_ARG(nbr || dense || taps == 1, "taps > 1 needs a neighbour table or dense geometry");
+  PNX_CHECK_ARG(!shuffle || (block_n % 64 == 0 || 64 % block_n == 0), "shuffle store needs 64-channel groups");
+  if (stats) PNX_CHECK_ARG(stats_C > 0 && stats_mod > 0, "stats_C/stats_mod");
+  if (sm_count <= 0) sm_count = 148;
+  IgemmParams p;
+  p.A = (const __nv_bfloat16*)A;
+  p.lda = lda;
+  p.M = M; p.T = taps; p.Cin = Cin; p.w_rows_per_tap = Cout;
+  p.nbr = nbr; p.dense = dense;
+  p.Hout = Hout > 0 ? Hout : 1; p.Wout = Wout > 0 ? Wout : 1; p.Hin = Hin; p.Win = Win;
+  p.kw = kw > 0 ? kw : 1; p.mul = mul; p.dil = dil; p.pad = pad;
+  p.out = out; p.ldc = ldc; p.out_fp32 = out_fp32; p.bias = bias;
+  p.stats = stats; p.stats_C = stats_C; p.stats_mod = stats_mod > 0 ? stats_mod : 1 << 30;
+  p.shuffle = shuffle; p.relu = relu;
+  CUtensorMap wmap;
+  int rc = pnx_encode_tmap_2d_bf16(&wmap, Wpacked, (uint64_t)taps * Cout, (uint64_t)Cin, (uint64_t)Cin * 2,
+                                   (uint32_t)block_n, 64);
+  if (rc) return rc;
+  const int n_blocks = Cout / block_n;
+  switch (block_n) {
+    case 16: return launch_igemm<16>(wmap, p, n_blocks, sm_count, stream);
+    case 32: return launch_igemm<32>(wmap, p, n_blocks, sm_count, stream);
+    case 64: return launch_igemm<64>(wmap, p, n_blocks, sm_count, stream);
+    case 128: return launch_igemm<128>(wmap, p, n_blocks, sm_count, stream);
+    case 192: return launch_igemm<192>(wmap, p, n_blocks, sm_count, stream);
+    case 256: return launch_igemm<256>(wmap, p, n_blocks, sm_count, stream);
+    default:
+      pnx_set_error("pnx_igemm: unsupported block_n %d (16/32/64/128/192/256)", block_n);
+      return PNX_ERR_ARG;
+  }
+}

@@ -1,0 +1,282 @@
+// voxelize.cu -- dynamic point->pillar voxelizer (rows V1-V3 of SURVEY.md section 8a) for sm_100a.
+//
+// Replaces, bit-exactly on the indices, reference det3d/models/readers/pillar_encoder.py:86-125:
+//   (xyz-min)/voxel (fp32 sub + IEEE fp32 divide), float-domain range test on x,y only, trunc,
+//   torch.unique(dim=0, return_inverse=True) over (b, xi, yi)   [lexicographically sorted]
+// WITHOUT a sort: the BEV grid is bounded (B*Gx*Gy cells), so occupancy is a direct-address bitmap
+// laid out in the reference's sort order (bit index = (b*Gx + xi)*GyPad + yi); the rank of a set
+// bit (popcount prefix) IS the sorted-unique pillar id, i.e. `unq_inv`.
+// Points are then bucketed by pillar (CSR, ascending point id inside a bucket) so every later
+// per-pillar reduction (mean, max) is a plain in-order loop -- no atomics on any reduction.
+//
+// HBM traffic (algorithmic): 24 B/point read + 4 B/point pillar id + 12 B/pillar coords.
+#include "pnx_common.cuh"
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((int)pnx::lane_id() >= o) v += t;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix, total in *total
+__device__ __forceinline__ int block_excl_scan(int v, int* total) {
+  __shared__ int wsum[kScanThreads / 32];
+  __shared__ int wtot;
+  int incl = warp_incl_scan(v);
+  int w = threadIdx.x >> 5;
+  if (pnx::lane_id() == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int s = (pnx::lane_id() < kScanThreads / 32) ? wsum[pnx::lane_id()] : 0;
+    int si = warp_incl_scan(s);
+    if (pnx::lane_id() < kScanThreads / 32) wsum[pnx::lane_id()] = si - s;
+    if (pnx::lane_id() == kScanThreads / 32 - 1) wtot = si;
+  }
+  __syncthreads();
+  int r = incl - v + wsum[w];
+  *total = wtot;
+  __syncthreads();
+  return r;
+}
+
+template <bool kPopc>
+__device__ __forceinline__ int scan_val(const uint32_t* in, int i, int n) {
+  if (i >= n) return 0;
+  return kPopc ? __popc(in[i]) : (int)in[i];
+}
+
+template <bool kPopc>
+__global__ void scan_reduce_kernel(const uint32_t* __restrict__ in, int n, int* __restrict__ block_sums) {
+  int base = blockIdx.x * kScanTile;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) s += scan_val<kPopc>(in, base + k * kScanThreads + threadIdx.x, n);
+  int tot;
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void scan_top_kernel(int* __restrict__ block_sums, int n_blocks, int* __restrict__ total_out) {
+  int carry = 0;
+  for (int base = 0; base < n_blocks; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    int v = i < n_blocks ? block_sums[i] : 0;
+    int tot;
+    int ex = block_excl_scan(v, &tot);
+    if (i < n_blocks) block_sums[i] = ex + carry;
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+template <bool kPopc>
+__global__ void scan_apply_kernel(const uint32_t* __restrict__ in, int n, const int* __restrict__ block_sums,
+                                  int* __restrict__ out) {
+  // items are distributed so that thread t owns kScanItems CONSECUTIVE elements
+  int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = scan_val<kPopc>(in, base + k, n);
+    s += v[k];
+  }
+  int tot;
+  int ex = block_excl_scan(s, &tot) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+  if (base <= n && n < base + kScanItems) out[n] = ex - 0;  // total (exclusive prefix at n)
+}
+
+}  // namespace
+
+// Exclusive prefix sum of popcounts (popc=1) or raw int32 values (popc=0).
+// out has n+1 entries (out[n] = total); block_sums scratch needs ceil(n/2048)+1 ints.
+extern "C" int pnx_scan_u32(const uint32_t* in, int n, int popc, int* out, int* block_sums, int* total_out,
+                            cudaStream_t stream) {
+  PNX_CHECK_ARG(n >= 0, "n < 0");
+  int nb = pnx_cdiv(n + 1, kScanTile);  // +1 so the thread owning index n exists
+  if (popc) {
+    scan_reduce_kernel<true><<<nb, kScanThreads, 0, stream>>>(in, n, block_sums);
+    scan_top_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nb, total_out);
+    scan_apply_kernel<true><<<nb, kScanThreads, 0, stream>>>(in, n, block_sums, out);
+  } else {
+    scan_reduce_kernel<false><<<nb, kScanThreads, 0, stream>>>(in, n, block_sums);
+    scan_top_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nb, total_out);
+    scan_apply_kernel<false><<<nb, kScanThreads, 0, stream>>>(in, n, block_sums, out);
+  }
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
+namespace {
+
+struct VoxGeom {
+  float min_x, min_y, vs_x, vs_y;
+  int gx, gy, vwords, batch;
+};
+
+// V1: cell index per point + occupancy bitmap.  One thread per point; the block stages its
+// 256 points (6 KB) through shared memory with 128-bit coalesced loads.
+__global__ void __launch_bounds__(256) vox_mark_kernel(const float* __restrict__ points, int n, VoxGeom g,
+                                                       uint32_t* __restrict__ bitmap,
+                                                       int* __restrict__ cell_of_point) {
+  __shared__ float4 stage[256 * 6 / 4];
+  const long long first = (long long)blockIdx.x * 256;
+  const int n_here = (int)min((long long)256, (long long)n - first);
+  const float4* src = reinterpret_cast<const float4*>(points + first * 6);  // 256*24 B blocks stay 16B aligned
+  const int n_vec = (n_here * 6 + 3) / 4;
+  const long long total_floats = (long long)n * 6;
+  for (int v = threadIdx.x; v < n_vec; v += 256) {
+    long long f0 = first * 6 + (long long)v * 4;
+    if (f0 + 4 <= total_floats) {
+      stage[v] = __ldg(src + v);
+    } else {  // ragged tail of the whole array
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < 4 && f0 + k < total_floats; ++k) t[k] = points[f0 + k];
+      stage[v] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= n_here) return;
+  const float* p = reinterpret_cast<const float*>(stage) + threadIdx.x * 6;
+  const float bf = p[0], x = p[1], y = p[2];
+  // pillar_encoder.py:95-96 -- fp32 subtract then true fp32 division (no reciprocal, no FMA)
+  const float cx = __fdiv_rn(__fsub_rn(x, g.min_x), g.vs_x);
+  const float cy = __fdiv_rn(__fsub_rn(y, g.min_y), g.vs_y);
+  // :98-101 -- range test in the float domain, x/y only (NaN fails every comparison)
+  bool keep = (cx >= 0.f) && (cx < (float)g.gx) && (cy >= 0.f) && (cy < (float)g.gy);
+  const int b = (int)bf;  // :107 .long() truncation
+  keep = keep && (b >= 0) && (b < g.batch);
+  int cell = -1;
+  if (keep) {
+    const int xi = (int)cx, yi = (int)cy;  // :106 trunc
+    const int word = (b * g.gx + xi) * g.vwords + (yi >> 5);
+    atomicOr(&bitmap[word], 1u << (yi & 31));
+    cell = word * 32 + (yi & 31);
+  }
+  cell_of_point[first + threadIdx.x] = cell;
+}
+
+// V2b: pillar id per point (= rank of its bit) and per-pillar point counts.
+__global__ void vox_rank_kernel(const int* __restrict__ cell_of_point, int n, const uint32_t* __restrict__ bitmap,
+                                const int* __restrict__ word_prefix, int* __restrict__ pillar_of_point,
+                                uint32_t* __restrict__ bucket_cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cell = cell_of_point[i];
+  int pid = -1;
+  if (cell >= 0) {
+    int word = cell >> 5, bit = cell & 31;
+    pid = word_prefix[word] + __popc(bitmap[word] & ((1u << bit) - 1u));
+    atomicAdd(&bucket_cnt[pid], 1u);  // integer count: order-independent
+  }
+  pillar_of_point[i] = pid;
+}
+
+// V2c: coords (b, yi, xi) of every pillar in sorted-unique order. One thread per bitmap word.
+__global__ void vox_coords_kernel(const uint32_t* __restrict__ bitmap, const int* __restrict__ word_prefix,
+                                  int n_words, VoxGeom g, int* __restrict__ coords, int cap) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t bits = bitmap[w];
+  if (!bits) return;
+  int idx = word_prefix[w];
+  int row = w / g.vwords, vw = w - row * g.vwords;
+  int b = row / g.gx, xi = row - b * g.gx;
+  while (bits) {
+    int bit = __ffs(bits) - 1;
+    bits &= bits - 1;
+    if (idx < cap) {
+      coords[idx * 3 + 0] = b;
+      coords[idx * 3 + 1] = vw * 32 + bit;  // yi
+      coords[idx * 3 + 2] = xi;
+    }
+    ++idx;
+  }
+}
+
+// V3a: place points into their pillar's bucket (slot order is arbitrary here ...)
+__global__ void vox_fill_kernel(const int* __restrict__ pillar_of_point, int n, const int* __restrict__ bucket_off,
+                                uint32_t* __restrict__ cursor, int* __restrict__ bucket_tmp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int pid = pillar_of_point[i];
+  if (pid < 0) return;
+  uint32_t slot = atomicAdd(&cursor[pid], 1u);
+  bucket_tmp[bucket_off[pid] + slot] = i;
+}
+// V3b: ... and made deterministic: each entry is moved to its rank (ascending point id) in the bucket.
+__global__ void vox_sort_kernel(const int* __restrict__ bucket_tmp, const int* __restrict__ pillar_of_point,
+                                const int* __restrict__ bucket_off, int nv_cap, const int* __restrict__ nv_ptr,
+                                int* __restrict__ bucket_pts) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= *nv_ptr || q >= nv_cap) return;
+  int i = bucket_tmp[q];
+  int pid = pillar_of_point[i];
+  int lo = bucket_off[pid], hi = bucket_off[pid + 1];
+  int rank = 0;
+  for (int k = lo; k < hi; ++k) rank += (bucket_tmp[k] < i);
+  bucket_pts[lo + rank] = i;
+}
+
+}  // namespace
+
+extern "C" size_t pnx_voxelize_bitmap_words(int batch, int gx, int gy) {
+  return (size_t)batch * gx * ((gy + 31) / 32);
+}
+
+// See include/pnx.h for the contract.  All buffers are caller-owned device memory.
+extern "C" int pnx_voxelize(const float* points, int n_points, int batch, float min_x, float min_y, float vs_x,
+                            float vs_y, int gx, int gy, uint32_t* bitmap, int* word_prefix, int* scan_scratch,
+                            int* cell_of_point, int* pillar_of_point, int* coords, int cap_pillars,
+                            uint32_t* bucket_cnt, int* bucket_off, int* bucket_tmp, int* bucket_pts,
+                            int* counts /* [0]=P, [1]=Nv */, cudaStream_t stream) {
+  PNX_CHECK_ARG(n_points >= 0 && batch > 0 && gx > 0 && gy > 0, "bad sizes");
+  PNX_CHECK_ARG(vs_x > 0.f && vs_y > 0.f, "voxel size must be positive");
+  PNX_CHECK_ARG((long long)batch * gx * ((gy + 31) / 32) * 32 < 2147483647LL, "grid too large for int32 cell ids");
+  PNX_CHECK_ARG(cap_pillars >= 0, "cap_pillars");
+  VoxGeom g{min_x, min_y, vs_x, vs_y, gx, gy, (gy + 31) / 32, batch};
+  const int n_words = batch * gx * g.vwords;
+  PNX_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)n_words * 4, stream));
+  PNX_CUDA(cudaMemsetAsync(bucket_cnt, 0, (size_t)(cap_pillars + 1) * 4 * 2, stream));  // counts + cursors
+  PNX_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int), stream));
+  if (n_points > 0) {
+    vox_mark_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(points, n_points, g, bitmap, cell_of_point);
+    PNX_CHECK_LAUNCH();
+  }
+  int rc = pnx_scan_u32(bitmap, n_words, 1, word_prefix, scan_scratch, counts + 0, stream);
+  if (rc) return rc;
+  vox_coords_kernel<<<pnx_cdiv(n_words, 256), 256, 0, stream>>>(bitmap, word_prefix, n_words, g, coords,
+                                                                cap_pillars);
+  PNX_CHECK_LAUNCH();
+  if (n_points > 0) {
+    vox_rank_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(cell_of_point, n_points, bitmap, word_prefix,
+                                                                 pillar_of_point, bucket_cnt);
+    PNX_CHECK_LAUNCH();
+  }
+  // bucket offsets = exclusive scan of per-pillar counts over the pillar CAPACITY (device-side P unknown to host)
+  rc = pnx_scan_u32(bucket_cnt, cap_pillars, 0, bucket_off, scan_scratch, counts + 1, stream);
+  if (rc) return rc;
+  if (n_points > 0) {
+    uint32_t* cursor = bucket_cnt + cap_pillars + 1;
+    vox_fill_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(pillar_of_point, n_points, bucket_off, cursor,
+                                                                 bucket_tmp);
+    vox_sort_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(bucket_tmp, pillar_of_point, bucket_off,
+                                                                 n_points, counts + 1, bucket_pts);
+    PNX_CHECK_LAUNCH();
+  }
+  return PNX_OK;
+}

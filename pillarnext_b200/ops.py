@@ -1,0 +1,226 @@
+"""Thin host wrappers: torch device buffers + current stream -> libpnx C-ABI calls.
+
+torch is used here for device memory, streams and dtype plumbing only; all compute is in libpnx.
+"""
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, sm_count, stream
+
+
+# --------------------------------------------------------------------------------- geometry
+def grid_size_xy(voxel_size, pc_range):
+    """Same float64 arithmetic as the reference (pillar_encoder.py:87-89)."""
+    vs = np.array(voxel_size, dtype=np.float64)
+    pr = np.array(pc_range, dtype=np.float64)
+    g = (pr[3:] - pr[:3]) / vs
+    return np.round(g).astype(np.int64)
+
+
+def _f32(x):
+    return float(np.float32(x))
+
+
+class Voxels:
+    """Result of the voxelizer: fixed-capacity device buffers + device counts {P, Nv}."""
+
+    def __init__(self):
+        self.P = None
+        self.Nv = None
+
+    def sync_counts(self):
+        if self.P is None:
+            c = self.counts.cpu()
+            self.P, self.Nv = int(c[0]), int(c[1])
+        return self.P, self.Nv
+
+
+def voxelize(points, batch, voxel_size, pc_range):
+    """V1-V3 index generation (pnx_voxelize). points [N,6] fp32 cuda (b,x,y,z,i,t)."""
+    assert points.is_cuda and points.dtype == torch.float32 and points.dim() == 2 and points.shape[1] == 6, \
+        "points must be a CUDA float32 [N, 6] tensor (batch_idx, x, y, z, intensity, time)"
+    points = points.contiguous()
+    if points.data_ptr() % 16:
+        points = points.clone()
+    n = points.shape[0]
+    g = grid_size_xy(voxel_size, pc_range)
+    gx, gy = int(g[0]), int(g[1])
+    dev = points.device
+    L = lib()
+    words = L.pnx_voxelize_bitmap_words(batch, gx, gy)
+    cap_p = min(n, batch * gx * gy)
+    v = Voxels()
+    v.points, v.n, v.batch, v.gx, v.gy, v.cap_p = points, n, batch, gx, gy, cap_p
+    v.min_x, v.min_y = _f32(pc_range[0]), _f32(pc_range[1])
+    v.vs_x, v.vs_y = _f32(voxel_size[0]), _f32(voxel_size[1])
+    i32 = dict(dtype=torch.int32, device=dev)
+    v.bitmap = torch.empty(words, **i32)
+    v.word_prefix = torch.empty(words + 1, **i32)
+    scratch = torch.empty(max(words, cap_p) // 2048 + 4, **i32)
+    cell = torch.empty(max(n, 1), **i32)
+    v.pillar_of_point = torch.empty(max(n, 1), **i32)
+    v.coords = torch.empty(max(cap_p, 1), 3, **i32)
+    bucket_cnt = torch.empty(2 * (cap_p + 1), **i32)
+    v.bucket_off = torch.empty(cap_p + 1, **i32)
+    bucket_tmp = torch.empty(max(n, 1), **i32)
+    v.bucket_pts = torch.empty(max(n, 1), **i32)
+    v.counts = torch.empty(2, **i32)
+    check(L.pnx_voxelize(ptr(points), n, batch, v.min_x, v.min_y, v.vs_x, v.vs_y, gx, gy, ptr(v.bitmap),
+                         ptr(v.word_prefix), ptr(scratch), ptr(cell), ptr(v.pillar_of_point), ptr(v.coords), cap_p,
+                         ptr(bucket_cnt), ptr(v.bucket_off), ptr(bucket_tmp), ptr(v.bucket_pts), ptr(v.counts),
+                         stream()))
+    return v
+
+
+# --------------------------------------------------------------------------------- BatchNorm stats
+def bn_finalize(stats, channels, count_ptr, count_mult, gamma, beta, eps, momentum, running_mean, running_var,
+                want_saved=True):
+    dev = stats.device
+    scale = torch.empty(channels, dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale) if want_saved else None
+    invstd = torch.empty_like(scale) if want_saved else None
+    check(lib().pnx_bn_finalize(ptr(stats), channels, ptr(count_ptr) if count_ptr is not None else None,
+                                int(count_mult), ptr(gamma), ptr(beta), float(eps), float(momentum),
+                                ptr(running_mean) if running_mean is not None else None,
+                                ptr(running_var) if running_var is not None else None,
+                                ptr(scale), ptr(shift), ptr(mean) if want_saved else None,
+                                ptr(invstd) if want_saved else None, stream()))
+    return scale, shift, mean, invstd
+
+
+def bn_eval_affine(gamma, beta, rm, rv, eps):
+    c = gamma.shape[0]
+    scale = torch.empty(c, dtype=torch.float32, device=gamma.device)
+    shift = torch.empty_like(scale)
+    check(lib().pnx_bn_eval_affine(c, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), float(eps), ptr(scale), ptr(shift),
+                                   stream()))
+    return scale, shift
+
+
+# --------------------------------------------------------------------------------- PFN forward
+def pfn_forward(v, w0, bn0, w1, bn1, training, eps=1e-3, momentum=0.01, want_f32=True):
+    """P1-P3. bn0/bn1 = (gamma, beta, running_mean, running_var). Returns dict with feat (fp32 [capP,64]),
+    feat_bf16, and everything the backward needs."""
+    L = lib()
+    dev = v.points.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    n, cap_p = max(v.n, 1), max(v.cap_p, 1)
+    out = {}
+    mean = torch.empty(cap_p, 3, **f32)
+    y0 = torch.empty(n, 32, **f32)
+    y1 = torch.empty(n, 64, **f32)
+    x0max = torch.empty(cap_p, 32, **f32)
+    stats = torch.zeros(2 * 32 + 2 * 64, dtype=torch.float64, device=dev)
+    s0, s1 = stats[:64], stats[64:]
+    nv_ptr = v.counts[1:2]
+    tr = 1 if training else 0
+    check(L.pnx_pfn_mean(ptr(v.points), ptr(v.bucket_off), ptr(v.bucket_pts), ptr(v.counts), v.cap_p, ptr(mean),
+                         stream()))
+    check(L.pnx_pfn_lin0(ptr(v.points), ptr(v.bucket_pts), ptr(v.pillar_of_point), ptr(v.coords), ptr(mean),
+                         ptr(v.counts), v.n, v.min_x, v.min_y, v.vs_x, v.vs_y, ptr(w0), ptr(y0), ptr(s0), tr,
+                         stream()))
+    if training:
+        sc0, sh0, m0, i0 = bn_finalize(s0, 32, nv_ptr, 1, bn0[0], bn0[1], eps, momentum, bn0[2], bn0[3])
+    else:
+        sc0, sh0 = bn_eval_affine(bn0[0], bn0[1], bn0[2], bn0[3], eps)
+        m0 = i0 = None
+    check(L.pnx_pfn_max0(ptr(y0), ptr(v.bucket_off), ptr(v.counts), v.cap_p, ptr(sc0), ptr(sh0), ptr(x0max),
+                         stream()))
+    check(L.pnx_pfn_lin1(ptr(y0), ptr(x0max), ptr(v.bucket_pts), ptr(v.pillar_of_point), ptr(v.counts), v.n,
+                         ptr(sc0), ptr(sh0), ptr(w1), ptr(y1), ptr(s1), tr, stream()))
+    if training:
+        sc1, sh1, m1, i1 = bn_finalize(s1, 64, nv_ptr, 1, bn1[0], bn1[1], eps, momentum, bn1[2], bn1[3])
+    else:
+        sc1, sh1 = bn_eval_affine(bn1[0], bn1[1], bn1[2], bn1[3], eps)
+        m1 = i1 = None
+    feat = torch.empty(cap_p, 64, **f32) if want_f32 else None
+    feat_bf16 = torch.empty(cap_p, 64, dtype=torch.bfloat16, device=dev)
+    check(L.pnx_pfn_max1(ptr(y1), ptr(v.bucket_off), ptr(v.counts), v.cap_p, ptr(sc1), ptr(sh1),
+                         ptr(feat) if want_f32 else None, ptr(feat_bf16), stream()))
+    out.update(feat=feat, feat_bf16=feat_bf16, mean=mean, y0=y0, y1=y1, x0max=x0max, sc0=sc0, sh0=sh0, sc1=sc1,
+               sh1=sh1, mean0=m0, invstd0=i0, mean1=m1, invstd1=i1)
+    return out
+
+
+# --------------------------------------------------------------------------------- sites / rulebook
+class Level:
+    """Active-site set of one backbone level: bitmap (b,u,v), prefix, coords [n,3], count."""
+    pass
+
+
+def _scan_bitmap(bm):
+    words = bm.numel()
+    prefix = torch.empty(words + 1, dtype=torch.int32, device=bm.device)
+    scratch = torch.empty(words // 2048 + 4, dtype=torch.int32, device=bm.device)
+    count = torch.empty(1, dtype=torch.int32, device=bm.device)
+    check(lib().pnx_scan_u32(ptr(bm), words, 1, ptr(prefix), ptr(scratch), ptr(count), stream()))
+    return prefix, count
+
+
+def level_from_bitmap(bm, prefix, count, batch, U, V):
+    lv = Level()
+    lv.bm, lv.prefix, lv.count, lv.batch, lv.U, lv.V = bm, prefix, count, batch, U, V
+    lv.n = None
+    lv.coords = None
+    return lv
+
+
+def level_dilate(src, stride):
+    L = lib()
+    uo, vo = L.pnx_sites_out_dim(src.U, stride), L.pnx_sites_out_dim(src.V, stride)
+    bm = torch.empty(src.batch * uo * ((vo + 31) // 32), dtype=torch.int32, device=src.bm.device)
+    check(L.pnx_sites_dilate(ptr(src.bm), src.batch, src.U, src.V, stride, ptr(bm), stream()))
+    prefix, count = _scan_bitmap(bm)
+    return level_from_bitmap(bm, prefix, count, src.batch, uo, vo)
+
+
+def level_coords(lv, n):
+    lv.n = n
+    lv.coords = torch.empty(max(n, 1), 3, dtype=torch.int32, device=lv.bm.device)
+    check(lib().pnx_sites_coords(ptr(lv.bm), ptr(lv.prefix), lv.batch, lv.U, lv.V, ptr(lv.coords), n, stream()))
+    return lv.coords
+
+
+def nbr_table(dst, src, stride, transposed):
+    nbr = torch.empty(max(dst.n, 1), 9, dtype=torch.int32, device=dst.bm.device)
+    check(lib().pnx_nbr_table(ptr(dst.coords), ptr(dst.count), dst.n, ptr(src.bm), ptr(src.prefix), src.batch, src.U,
+                              src.V, stride, 1 if transposed else 0, ptr(nbr), stream()))
+    return nbr
+
+
+def scatter_dense(feat, lv, channels, canvas=None, gather=False):
+    """feat [n,C] bf16 <-> canvas [B, V(y), U(x), C] bf16."""
+    if canvas is None:
+        canvas = torch.zeros(lv.batch, lv.V, lv.U, channels, dtype=torch.bfloat16, device=feat.device)
+    check(lib().pnx_scatter_dense(ptr(feat), ptr(lv.coords), ptr(lv.count), lv.n, channels, lv.batch, lv.U, lv.V,
+                                  ptr(canvas), 1 if gather else 0, stream()))
+    return canvas
+
+
+# --------------------------------------------------------------------------------- implicit GEMM
+def pick_block_n(cout):
+    for bn in (256, 192, 128, 64, 32, 16):
+        if cout % bn == 0:
+            return bn
+    raise ValueError("Cout %d is not a multiple of 16" % cout)
+
+
+def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None, dense=None, bias=None, stats=None,
+          stats_mod=None, shuffle=False, relu=False, block_n=None):
+    """out[m, :cout] = sum_t A[nbr(m,t)] @ W[t]^T.  w_packed [taps, cout, cin] bf16.
+    dense = (Hout, Wout, Hin, Win, kw, mul, dil, pad) or None."""
+    assert A.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous()
+    assert tuple(w_packed.shape) == (taps, cout, cin), (tuple(w_packed.shape), (taps, cout, cin))
+    lda = A.stride(0) if lda is None else lda
+    ldc = out.stride(-2) if ldc is None else ldc
+    bn = block_n or pick_block_n(cout)
+    d = dense or (0, 0, 0, 0, 1, 1, 1, 0)
+    out_fp32 = 1 if out.dtype == torch.float32 else 0
+    assert out.dtype in (torch.float32, torch.bfloat16)
+    sC = stats.numel() // 2 if stats is not None else 0
+    check(lib().pnx_igemm(ptr(A), lda, M, taps, cin, ptr(w_packed), cout, bn, ptr(nbr) if nbr is not None else None,
+                          1 if dense else 0, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], ptr(out), ldc, out_fp32,
+                          ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None, sC,
+                          stats_mod or (sC if sC else 1), 1 if shuffle else 0, 1 if relu else 0, sm_count(), stream()))
+    return out
