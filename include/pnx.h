@@ -127,8 +127,40 @@ int pnx_scatter_dense(const void* feat, const int* coords, const int* n_ptr, int
 int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void* Wpacked, int Cout,
               int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
               int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
-              double* stats, int stats_C, int stats_mod, int shuffle, int relu, int sm_count,
+              double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
+              long long ld_add, int sm_count, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- tcgen05 weight gradient
+ * dW[t, x, y] += sum_m X[ix(m,t), x] * Y[iy(m,t), y]   (fp32, red.global.add; zero dW first)
+ * Exactly one of X / Y may be read through the neighbour map (gather_x / gather_y): the layer input is
+ * the gathered operand, the output gradient the direct one (swapped for ConvTranspose2d, shuffle=1).
+ * x_channels: 64 or a multiple of 128; y_channels: multiple of 64, <= 256.  Backward of the layers
+ * pnx_igemm replaces (autograd in the reference: trainer/trainer/trainer.py:94-108). */
+int pnx_wgrad(const void* X, long long ldx, int x_channels, int gather_x, const void* Y, long long ldy,
+              int y_channels, int gather_y, int M, int taps, const int* nbr, int dense, int Hout, int Wout,
+              int Hin, int Win, int kw, int mul, int dil, int pad, int shuffle, float* dW, int sm_count,
               cudaStream_t stream);
+
+/* ---------------------------------------------------------------- row-wise bf16 kernels
+ * y = relu?(x*scale + shift (+ res))  -- BatchNorm apply (+residual)(+ReLU): sparse_conv.py:33-39,55-63,
+ * conv.py:29-34; rows = active sites or pixels, C channels, ld* = row strides in elements. */
+int pnx_bn_apply(const void* x, long long ldx, long long M, int C, const float* scale, const float* shift,
+                 const void* res, long long ldr, int relu, void* y, long long ldy, cudaStream_t stream);
+/* BatchNorm backward: red[0:C] += sum g, red[C:2C] += sum g*xhat with g = dy*(y>0 if relu) ... */
+int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
+                      long long ldx, long long M, int C, const float* mean, const float* invstd, int relu,
+                      double* red, cudaStream_t stream);
+/* ... dx = gamma*invstd*(g - red[c]/count - xhat*red[C+c]/count); optional dres (+)= g (residual branch). */
+int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
+                     long long ldx, long long M, int C, const float* mean, const float* invstd,
+                     const float* gamma, const double* red, double count, int relu, void* dx, long long lddx,
+                     void* dres, long long lddres, int dres_accumulate, cudaStream_t stream);
+int pnx_add_rows(void* a, long long lda, const void* b, long long ldb, long long M, int C, cudaStream_t stream);
+/* y = relu(a + b) (BasicBlock tail, conv.py:48-50) and its backward g (+)= dy*(y>0). */
+int pnx_add_relu(const void* a, long long lda, const void* b, long long ldb, long long M, int C, void* y,
+                 long long ldy, cudaStream_t stream);
+int pnx_relu_bwd(const void* dy, long long lddy, const void* y, long long ldy, long long M, int C, void* g,
+                 long long ldg, int accumulate, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,14 @@ _SIGS = {
     "pnx_sites_coords": [P, P, I, I, I, P, I, P],
     "pnx_nbr_table": [P, P, I, P, P, I, I, I, I, I, P, P],
     "pnx_scatter_dense": [P, P, P, I, I, I, I, I, P, I, P],
-    "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, I, P],
+    "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, P, L, I, P],
+    "pnx_wgrad": [P, L, I, I, P, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, I, P, I, P],
+    "pnx_bn_apply": [P, L, L, I, P, P, P, L, I, P, L, P],
+    "pnx_bn_bwd_reduce": [P, L, P, L, P, L, L, I, P, P, I, P, P],
+    "pnx_bn_bwd_apply": [P, L, P, L, P, L, L, I, P, P, P, P, ctypes.c_double, I, P, L, P, L, I, P],
+    "pnx_add_rows": [P, L, P, L, L, I, P],
+    "pnx_add_relu": [P, L, P, L, L, I, P, L, P],
+    "pnx_relu_bwd": [P, L, P, L, L, I, P, L, I, P],
 }
 _RESTYPE = {"pnx_last_error": ctypes.c_char_p, "pnx_voxelize_bitmap_words": ctypes.c_size_t}
 

@@ -1,0 +1,280 @@
+// elementwise.cu -- HBM-bound row-wise kernels around the convolutions (bf16 rows x channels):
+//   BatchNorm apply (+residual)(+ReLU)                     forward of sparse_conv.py:33-39,55-63, conv.py:29-34,44-51
+//   BatchNorm backward: reduce (sum g, sum g*xhat) + apply  (autograd of the same lines in the reference)
+// 128-bit loads/stores, one thread = 8 consecutive channels of one row.
+#include "pnx_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pnx::pack_bf16x2(f[0], f[1]), pnx::pack_bf16x2(f[2], f[3]), pnx::pack_bf16x2(f[4], f[5]),
+                    pnx::pack_bf16x2(f[6], f[7]));
+}
+
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
+                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                const __nv_bfloat16* __restrict__ res, long long ldr, int relu,
+                                __nv_bfloat16* __restrict__ y, long long ldy) {
+  const int cg = C >> 3;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = M * cg;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / cg;
+    const int c0 = (int)(t - m * cg) << 3;
+    float v[8], r[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), v);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    if (res) unpack8(*reinterpret_cast<const uint4*>(res + m * ldr + c0), r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float o = fmaf(v[k], sc[k], sh[k]);
+      if (res) o += r[k];
+      if (relu) o = fmaxf(o, 0.f);
+      v[k] = o;
+    }
+    *reinterpret_cast<uint4*>(y + m * ldy + c0) = pack8(v);
+  }
+}
+
+// g = dy * (y > 0 if relu);  red[0:C] += sum g ; red[C:2C] += sum g * xhat,  xhat = (x - mean) * invstd
+template <int kThreads>
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                     const __nv_bfloat16* __restrict__ y, long long ldy,
+                                     const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                     double* __restrict__ red) {
+  extern __shared__ float sred[];  // [kThreads][16]
+  const int cg = C >> 3;
+  const int my_cg = threadIdx.x % cg;
+  const int rows_per_block = kThreads / cg;
+  const int my_row = threadIdx.x / cg;
+  const int c0 = my_cg << 3;
+  float sg[8], sgx[8], mu[8], is[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sg[k] = sgx[k] = 0.f;
+    mu[k] = mean[c0 + k];
+    is[k] = invstd[c0 + k];
+  }
+  if (my_row < rows_per_block) {
+    for (long long m = (long long)blockIdx.x * rows_per_block + my_row; m < M; m += (long long)gridDim.x * rows_per_block) {
+      float g[8], yy[8], xx[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + m * lddy + c0), g);
+      unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), xx);
+      if (relu) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
+        sg[k] += gg;
+        sgx[k] += gg * (xx[k] - mu[k]) * is[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sred[threadIdx.x * 16 + k] = sg[k];
+    sred[threadIdx.x * 16 + 8 + k] = sgx[k];
+  }
+  __syncthreads();
+  // thread j < 2*C reduces one (which, channel) over the block's rows
+  for (int j = threadIdx.x; j < 2 * C; j += kThreads) {
+    const int which = j / C, c = j - which * C;
+    const int g_ = c >> 3, k = c & 7;
+    double acc = 0.0;
+    for (int r = 0; r < rows_per_block; ++r) acc += (double)sred[(r * cg + g_) * 16 + which * 8 + k];
+    atomicAdd(&red[which * C + c], acc);
+  }
+}
+
+// dx = scale * (g - sum_g/n - xhat * sum_gx/n) ; optional dres (+)= g
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                    const __nv_bfloat16* __restrict__ y, long long ldy,
+                                    const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const double* __restrict__ red, float inv_n,
+                                    int relu, __nv_bfloat16* __restrict__ dx, long long lddx,
+                                    __nv_bfloat16* __restrict__ dres, long long lddres, int dres_accumulate) {
+  const int cg = C >> 3;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = M * cg;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / cg;
+    const int c0 = (int)(t - m * cg) << 3;
+    float g[8], yy[8], xx[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + m * lddy + c0), g);
+    unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), xx);
+    if (relu) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
+      g[k] = gg;
+      const float is = invstd[c];
+      const float xh = (xx[k] - mean[c]) * is;
+      o[k] = gamma[c] * is * (gg - (float)red[c] * inv_n - xh * (float)red[C + c] * inv_n);
+    }
+    *reinterpret_cast<uint4*>(dx + m * lddx + c0) = pack8(o);
+    if (dres) {
+      if (dres_accumulate) {
+        float a[8];
+        unpack8(*reinterpret_cast<const uint4*>(dres + m * lddres + c0), a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] += a[k];
+      }
+      *reinterpret_cast<uint4*>(dres + m * lddres + c0) = pack8(g);
+    }
+  }
+}
+
+// a[m, 0:C] += b[m, 0:C]  (bf16)
+__global__ void add_rows_kernel(__nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b,
+                                long long ldb, long long M, int C) {
+  const int cg = C >> 3;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = M * cg;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / cg;
+    const int c0 = (int)(t - m * cg) << 3;
+    float x[8], y[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + m * lda + c0), x);
+    unpack8(*reinterpret_cast<const uint4*>(b + m * ldb + c0), y);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] += y[k];
+    *reinterpret_cast<uint4*>(a + m * lda + c0) = pack8(x);
+  }
+}
+
+// y = relu(a + b)   (BasicBlock tail, reference conv.py:48-50)
+__global__ void add_relu_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b,
+                                long long ldb, long long M, int C, __nv_bfloat16* __restrict__ y, long long ldy) {
+  const int cg = C >> 3;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = M * cg;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / cg;
+    const int c0 = (int)(t - m * cg) << 3;
+    float x[8], z[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + m * lda + c0), x);
+    unpack8(*reinterpret_cast<const uint4*>(b + m * ldb + c0), z);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = fmaxf(x[k] + z[k], 0.f);
+    *reinterpret_cast<uint4*>(y + m * ldy + c0) = pack8(x);
+  }
+}
+// g (+)= dy * (y > 0)
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ y,
+                                long long ldy, long long M, int C, __nv_bfloat16* __restrict__ g, long long ldg,
+                                int accumulate) {
+  const int cg = C >> 3;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = M * cg;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / cg;
+    const int c0 = (int)(t - m * cg) << 3;
+    float d[8], yy[8], acc[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + m * lddy + c0), d);
+    unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
+    if (accumulate) unpack8(*reinterpret_cast<const uint4*>(g + m * ldg + c0), acc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = yy[k] > 0.f ? d[k] : 0.f;
+      d[k] = accumulate ? v + acc[k] : v;
+    }
+    *reinterpret_cast<uint4*>(g + m * ldg + c0) = pack8(d);
+  }
+}
+
+inline int ew_blocks(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  long long cap = 148LL * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int pnx_bn_apply(const void* x, long long ldx, long long M, int C, const float* scale, const float* shift,
+                            const void* res, long long ldr, int relu, void* y, long long ldy, cudaStream_t stream) {
+  PNX_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldr % 8 == 0, "C/ld % 8");
+  if (M == 0) return PNX_OK;
+  bn_apply_kernel<<<ew_blocks(M * (C / 8), 256), 256, 0, stream>>>((const __nv_bfloat16*)x, ldx, M, C, scale, shift,
+                                                                   (const __nv_bfloat16*)res, ldr, relu,
+                                                                   (__nv_bfloat16*)y, ldy);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
+extern "C" int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
+                                 long long ldx, long long M, int C, const float* mean, const float* invstd, int relu,
+                                 double* red, cudaStream_t stream) {
+  PNX_CHECK_ARG(C % 8 == 0 && C <= 2048, "C % 8 == 0 and C <= 2048");
+  if (M == 0) return PNX_OK;
+  constexpr int kT = 256;
+  PNX_CHECK_ARG(C / 8 <= kT, "C <= 2048");
+  const int rows_per_block = kT / (C / 8);
+  long long nb = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
+  if (nb > 148 * 4) nb = 148 * 4;
+  if (nb < 1) nb = 1;
+  bn_bwd_reduce_kernel<kT><<<(int)nb, kT, kT * 16 * sizeof(float), stream>>>(
+      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M, C, mean, invstd,
+      relu, red);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
+extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
+                                long long ldx, long long M, int C, const float* mean, const float* invstd,
+                                const float* gamma, const double* red, double count, int relu, void* dx,
+                                long long lddx, void* dres, long long lddres, int dres_accumulate,
+                                cudaStream_t stream) {
+  PNX_CHECK_ARG(C % 8 == 0, "C % 8");
+  if (M == 0) return PNX_OK;
+  bn_bwd_apply_kernel<<<ew_blocks(M * (C / 8), 256), 256, 0, stream>>>(
+      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M, C, mean, invstd,
+      gamma, red, (float)(1.0 / count), relu, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddres,
+      dres_accumulate);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
+extern "C" int pnx_add_rows(void* a, long long lda, const void* b, long long ldb, long long M, int C,
+                            cudaStream_t stream) {
+  PNX_CHECK_ARG(C % 8 == 0, "C % 8");
+  if (M == 0) return PNX_OK;
+  add_rows_kernel<<<ew_blocks(M * (C / 8), 256), 256, 0, stream>>>((__nv_bfloat16*)a, lda, (const __nv_bfloat16*)b,
+                                                                   ldb, M, C);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
+extern "C" int pnx_add_relu(const void* a, long long lda, const void* b, long long ldb, long long M, int C, void* y,
+                            long long ldy, cudaStream_t stream) {
+  PNX_CHECK_ARG(C % 8 == 0, "C % 8");
+  if (M == 0) return PNX_OK;
+  add_relu_kernel<<<ew_blocks(M * (C / 8), 256), 256, 0, stream>>>((const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b,
+                                                                   ldb, M, C, (__nv_bfloat16*)y, ldy);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
+extern "C" int pnx_relu_bwd(const void* dy, long long lddy, const void* y, long long ldy, long long M, int C, void* g,
+                            long long ldg, int accumulate, cudaStream_t stream) {
+  PNX_CHECK_ARG(C % 8 == 0, "C % 8");
+  if (M == 0) return PNX_OK;
+  relu_bwd_kernel<<<ew_blocks(M * (C / 8), 256), 256, 0, stream>>>((const __nv_bfloat16*)dy, lddy,
+                                                                   (const __nv_bfloat16*)y, ldy, M, C,
+                                                                   (__nv_bfloat16*)g, ldg, accumulate);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}

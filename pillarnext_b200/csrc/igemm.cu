@@ -32,6 +32,8 @@ struct IgemmParams {
   double* stats;
   int stats_C, stats_mod;
   int shuffle, relu;
+  const __nv_bfloat16* addend;  // optional [M, ld_add] bf16 added before the store (gradient accumulation)
+  long long ld_add;
 };
 
 constexpr int kThreads = 320;
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         for (int k = 0; k < kColBlk; ++k) {
           float x = __uint_as_float(r[k]);
           if (p.bias) x += __ldg(p.bias + ncol0 + k);
+          if (p.addend && active) x += __bfloat162float(p.addend[(long long)m * p.ld_add + ncol0 + k]);
           if (p.relu) x = fmaxf(x, 0.f);
           if (!p.out_fp32) x = pnx::bf16_round(x);
           v[k] = x;
@@ -336,8 +339,8 @@ int launch_igemm(const CUtensorMap& wmap, const IgemmParams& p, int n_blocks, in
 extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void* Wpacked, int Cout,
                          int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
                          int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
-                         double* stats, int stats_C, int stats_mod, int shuffle, int relu, int sm_count,
-                         cudaStream_t stream) {
+                         double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
+                         long long ld_add, int sm_count, cudaStream_t stream) {
   PNX_CHECK_ARG(M >= 0, "M");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(taps >= 1 && taps <= 9, "taps in [1,9]");
@@ -362,6 +365,8 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   p.out = out; p.ldc = ldc; p.out_fp32 = out_fp32; p.bias = bias;
   p.stats = stats; p.stats_C = stats_C; p.stats_mod = stats_mod > 0 ? stats_mod : 1 << 30;
   p.shuffle = shuffle; p.relu = relu;
+  p.addend = (const __nv_bfloat16*)addend; p.ld_add = ld_add;
+  PNX_CHECK_ARG(!(addend && shuffle), "addend is not supported with the pixel-shuffle store");
   CUtensorMap wmap;
   int rc = pnx_encode_tmap_2d_bf16(&wmap, Wpacked, (uint64_t)taps * Cout, (uint64_t)Cin, (uint64_t)Cin * 2,
                                    (uint32_t)block_n, 64);

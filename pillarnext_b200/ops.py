@@ -207,7 +207,7 @@ def pick_block_n(cout):
 
 
 def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None, dense=None, bias=None, stats=None,
-          stats_mod=None, shuffle=False, relu=False, block_n=None):
+          stats_mod=None, shuffle=False, relu=False, block_n=None, addend=None):
     """out[m, :cout] = sum_t A[nbr(m,t)] @ W[t]^T.  w_packed [taps, cout, cin] bf16.
     dense = (Hout, Wout, Hin, Win, kw, mul, dil, pad) or None."""
     assert A.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous()
@@ -222,5 +222,56 @@ def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None,
     check(lib().pnx_igemm(ptr(A), lda, M, taps, cin, ptr(w_packed), cout, bn, ptr(nbr) if nbr is not None else None,
                           1 if dense else 0, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], ptr(out), ldc, out_fp32,
                           ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None, sC,
-                          stats_mod or (sC if sC else 1), 1 if shuffle else 0, 1 if relu else 0, sm_count(), stream()))
+                          stats_mod or (sC if sC else 1), 1 if shuffle else 0, 1 if relu else 0,
+                          ptr(addend) if addend is not None else None, addend.stride(0) if addend is not None else 0,
+                          sm_count(), stream()))
     return out
+
+
+def wgrad(X, x_channels, gather_x, Y, y_channels, gather_y, M, taps, dW, *, nbr=None, dense=None, shuffle=False):
+    """dW[t, x, y] += sum_m X[ix(m,t), x] * Y[iy(m,t), y]; dW fp32 [taps, x_channels, y_channels]."""
+    assert X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16 and dW.dtype == torch.float32
+    assert tuple(dW.shape) == (taps, x_channels, y_channels) and dW.is_contiguous()
+    d = dense or (0, 0, 0, 0, 1, 1, 1, 0)
+    check(lib().pnx_wgrad(ptr(X), X.stride(0), x_channels, 1 if gather_x else 0, ptr(Y), Y.stride(0), y_channels,
+                          1 if gather_y else 0, M, taps, ptr(nbr) if nbr is not None else None,
+                          1 if (dense and not shuffle) else 0, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7],
+                          1 if shuffle else 0, ptr(dW), sm_count(), stream()))
+    return dW
+
+
+# --------------------------------------------------------------------------------- row-wise kernels
+def bn_apply(x, M, C, scale, shift, y, res=None, relu=True):
+    check(lib().pnx_bn_apply(ptr(x), x.stride(0), M, C, ptr(scale), ptr(shift), ptr(res) if res is not None else None,
+                             res.stride(0) if res is not None else 8, 1 if relu else 0, ptr(y), y.stride(0), stream()))
+    return y
+
+
+def bn_bwd(dy, y, x, M, C, mean, invstd, gamma, count, relu, dx, dres=None, dres_accumulate=False):
+    """Returns red (fp64 [2C]: sum g = dbeta, sum g*xhat = dgamma); writes dx (and dres)."""
+    red = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
+    L = lib()
+    yy = y if y is not None else dy
+    check(L.pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), ptr(yy), yy.stride(0), ptr(x), x.stride(0), M, C, ptr(mean),
+                              ptr(invstd), 1 if relu else 0, ptr(red), stream()))
+    check(L.pnx_bn_bwd_apply(ptr(dy), dy.stride(0), ptr(yy), yy.stride(0), ptr(x), x.stride(0), M, C, ptr(mean),
+                             ptr(invstd), ptr(gamma), ptr(red), float(max(count, 1)), 1 if relu else 0, ptr(dx),
+                             dx.stride(0), ptr(dres) if dres is not None else None,
+                             dres.stride(0) if dres is not None else 8, 1 if dres_accumulate else 0, stream()))
+    return red
+
+
+def add_rows(a, b, M, C):
+    check(lib().pnx_add_rows(ptr(a), a.stride(0), ptr(b), b.stride(0), M, C, stream()))
+    return a
+
+
+def add_relu(a, b, M, C, y):
+    check(lib().pnx_add_relu(ptr(a), a.stride(0), ptr(b), b.stride(0), M, C, ptr(y), y.stride(0), stream()))
+    return y
+
+
+def relu_bwd(dy, y, M, C, g, accumulate=False):
+    check(lib().pnx_relu_bwd(ptr(dy), dy.stride(0), ptr(y), y.stride(0), M, C, ptr(g), g.stride(0),
+                             1 if accumulate else 0, stream()))
+    return g

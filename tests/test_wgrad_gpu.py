@@ -1,0 +1,132 @@
+"""tcgen05 weight-gradient GEMM (MN-major operands) and the row-wise BatchNorm kernels vs torch fp32
+autograd on the same bf16-rounded operands.  Tolerance: 3e-3 of the result scale (fp32 accumulation
+order + fp32 atomics); BN backward additionally carries bf16 rounding of dx (2^-8 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pillarnext_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(out, ref, extra=0.0):
+    scale = ref.abs().max().item() + 1e-6
+    err = (out.float() - ref).abs().max().item()
+    assert err <= (3e-3 + extra) * scale, "max abs err %g (scale %g)" % (err, scale)
+
+
+@pytest.mark.parametrize("M,Min,Cx,Cy,gx", [(5000, 4000, 64, 64, False), (20000, 20000, 256, 256, False), (3000, 3000, 128, 64, False),
+                                            (7777, 9000, 384, 64, True), (700, 900, 256, 128, False), (100, 100, 1536, 256, True)])
+def test_wgrad_table(M, Min, Cx, Cy, gx):
+    """gx=False: X = dOut (direct, M rows), Y = In (gathered).  gx=True: X = In (gathered), Y = dOut."""
+    torch.manual_seed(M + Cx)
+    T = 9
+    nbr = torch.randint(-Min // 3, Min, (M, T), device="cuda", dtype=torch.int32).clamp(min=-1)
+    if gx:
+        X = torch.randn(Min, Cx, device="cuda").bfloat16()
+        Y = torch.randn(M, Cy, device="cuda").bfloat16()
+    else:
+        X = torch.randn(M, Cx, device="cuda").bfloat16()
+        Y = torch.randn(Min, Cy, device="cuda").bfloat16()
+    ref = torch.zeros(T, Cx, Cy, device="cuda")
+    for t in range(T):
+        idx = nbr[:, t].long()
+        ok = (idx >= 0).unsqueeze(1)
+        if gx:
+            xg = torch.where(ok, X[idx.clamp(min=0)].float(), torch.zeros(1, device="cuda"))
+            ref[t] = xg.t() @ Y.float()
+        else:
+            yg = torch.where(ok, Y[idx.clamp(min=0)].float(), torch.zeros(1, device="cuda"))
+            ref[t] = X.float().t() @ yg
+    dW = torch.zeros(T, Cx, Cy, device="cuda")
+    ops.wgrad(X, Cx, gx, Y, Cy, not gx, M, T, dW, nbr=nbr)
+    _close(dW, ref)
+
+
+@pytest.mark.parametrize("B,H,W_,Cin,Cout,k,stride,dil", [(2, 24, 24, 64, 64, 3, 1, 1), (1, 40, 36, 256, 256, 3, 1, 6), (1, 21, 33, 128, 256, 3, 2, 1), (2, 16, 16, 256, 256, 1, 1, 1)])
+def test_wgrad_dense_conv(B, H, W_, Cin, Cout, k, stride, dil):
+    torch.manual_seed(H + Cin)
+    x = torch.randn(B, Cin, H, W_, device="cuda").bfloat16()
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    pad = dil * (k // 2)
+    y = F.conv2d(x.float(), w, stride=stride, padding=pad, dilation=dil)
+    dy = torch.randn_like(y).bfloat16()
+    y.backward(dy.float())
+    Ho, Wo = y.shape[2], y.shape[3]
+    M = B * Ho * Wo
+    x_rows = x.permute(0, 2, 3, 1).contiguous().view(-1, Cin)
+    dy_rows = dy.permute(0, 2, 3, 1).contiguous().view(-1, Cout)
+    dW = torch.zeros(k * k, Cout, Cin, device="cuda")
+    ops.wgrad(dy_rows, Cout, False, x_rows, Cin, True, M, k * k, dW, dense=(Ho, Wo, H, W_, k, stride, dil, pad))
+    got = dW.view(k, k, Cout, Cin).permute(2, 3, 0, 1)
+    _close(got, w.grad)
+
+
+def test_wgrad_conv_transpose():
+    torch.manual_seed(3)
+    B, H, W_, C = 2, 12, 20, 64
+    x = torch.randn(B, C, H, W_, device="cuda").bfloat16()
+    w = torch.zeros(C, C, 2, 2, device="cuda", requires_grad=True)
+    y = F.conv_transpose2d(x.float(), w, stride=2)
+    dy = torch.randn_like(y).bfloat16()
+    y.backward(dy.float())
+    x_rows = x.permute(0, 2, 3, 1).contiguous().view(-1, C)
+    dy_rows = dy.permute(0, 2, 3, 1).contiguous().view(-1, C)
+    dW = torch.zeros(4, C, C, device="cuda")                      # [q, ci, co]
+    ops.wgrad(x_rows, C, False, dy_rows, C, True, B * H * W_, 4, dW, dense=(H, W_, 2 * H, 2 * W_, 2, 2, 1, 0), shuffle=True)
+    got = dW.view(2, 2, C, C).permute(2, 3, 0, 1)                 # [ci, co, dy, dx]
+    _close(got, w.grad)
+
+
+@pytest.mark.parametrize("M,C,relu,with_res", [(5000, 64, True, False), (3001, 256, True, True), (777, 128, False, True), (4000, 384, True, False)])
+def test_bn_rows(M, C, relu, with_res):
+    torch.manual_seed(M)
+    x = (torch.randn(M, C, device="cuda") * 2 + 0.5).bfloat16()
+    res = torch.randn(M, C, device="cuda").bfloat16() if with_res else None
+    gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_()
+    beta = (torch.randn(C, device="cuda") * 0.1).requires_grad_()
+    xf = x.float().requires_grad_()
+    rf = res.float().requires_grad_() if with_res else None
+    mean = xf.mean(0)
+    var = xf.var(0, unbiased=False)
+    yref = (xf - mean) / torch.sqrt(var + 1e-3) * gamma + beta
+    if with_res:
+        yref = yref + rf
+    if relu:
+        yref = F.relu(yref)
+    # forward through the kernels: stats (fp64) -> finalize -> apply
+    stats = torch.cat([x.double().sum(0), (x.double() ** 2).sum(0)])
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    sc, sh, mu, istd = ops.bn_finalize(stats, C, None, M, gamma.detach(), beta.detach(), 1e-3, 0.01, rm, rv)
+    y = torch.empty(M, C, dtype=torch.bfloat16, device="cuda")
+    ops.bn_apply(x, M, C, sc, sh, y, res=res, relu=relu)
+    _close(y, yref.detach(), extra=8e-3)
+    assert torch.allclose(rm, 0.01 * mean.detach(), atol=1e-5)
+    assert torch.allclose(rv, 0.99 + 0.01 * xf.detach().var(0, unbiased=True), atol=1e-4)
+    # backward; use the kernel's own y for the relu mask so both sides see the same mask
+    dy = torch.randn(M, C, device="cuda").bfloat16()
+    mask = (y.float() > 0) if relu else torch.ones_like(yref, dtype=torch.bool)
+    pre = (xf - mean) / torch.sqrt(var + 1e-3) * gamma + beta
+    pre.backward(torch.where(mask, dy.float(), torch.zeros(1, device="cuda")))
+    dx = torch.empty(M, C, dtype=torch.bfloat16, device="cuda")
+    dres = torch.empty(M, C, dtype=torch.bfloat16, device="cuda") if with_res else None
+    red = ops.bn_bwd(dy, y, x, M, C, mu, istd, gamma.detach(), M, relu, dx, dres=dres)
+    _close(dx, xf.grad, extra=8e-3)
+    _close(red[:C].float(), beta.grad)
+    _close(red[C:].float(), gamma.grad)
+    if with_res:
+        assert torch.equal(dres.float(), torch.where(mask, dy.float(), torch.zeros(1, device="cuda")))
+
+
+def test_add_relu_roundtrip():
+    a = torch.randn(1000, 256, device="cuda").bfloat16()
+    b = torch.randn(1000, 256, device="cuda").bfloat16()
+    y = torch.empty_like(a)
+    ops.add_relu(a, b, 1000, 256, y)
+    assert torch.equal(y, F.relu(a.float() + b.float()).bfloat16())
+    dy = torch.randn(1000, 256, device="cuda").bfloat16()
+    g = torch.empty_like(a)
+    ops.relu_bwd(dy, y, 1000, 256, g)
+    assert torch.equal(g.float(), torch.where(y.float() > 0, dy.float(), torch.zeros(1, device="cuda")))
+    ops.add_rows(g, b, 1000, 256)
