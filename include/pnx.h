@@ -94,6 +94,21 @@ int pnx_pfn_max1(const float* y1, const int* bucket_off, const int* counts, int 
                  const float* scale, const float* shift, float* feat_f32, void* feat_bf16,
                  cudaStream_t stream);
 
+/* PillarFeatureNet backward (autograd of pillar_encoder.py:35-50,174-182 in the reference).
+ * Inputs: the forward's saved buffers (pnx_pfn_* outputs), dfeat [cap_pillars,64] fp32.
+ * Scratch: argq1 [cap_pillars,64] int32, d_x0 / dxm_part [cap_points,32] fp32.
+ * Outputs (zero them first): red fp64 [64+128] = {dbeta0[32], dgamma0[32], dbeta1[64], dgamma1[64]},
+ * dW0 [32,10], dW1 [64,64] fp32. */
+int pnx_pfn_backward(const float* points, const int* bucket_off, const int* bucket_pts,
+                     const int* pillar_of_point, const int* coords, const int* counts, int cap_points,
+                     int cap_pillars, float min_x, float min_y, float vs_x, float vs_y, const float* pmean,
+                     const float* y0, const float* y1, const float* x0max, const float* feat,
+                     const float* dfeat, const float* w1, const float* scale0, const float* shift0,
+                     const float* mean0, const float* invstd0, const float* gamma0, const float* scale1,
+                     const float* shift1, const float* mean1, const float* invstd1, const float* gamma1,
+                     int* argq1, float* d_x0, float* dxm_part, double* red, float* dW0, float* dW1,
+                     cudaStream_t stream);
+
 /* ---------------------------------------------------------------- B1-B4 active sites / rulebook
  * Replaces spconv index-pair generation (sparse_conv.py:25-29,50-51; sparse_resnet.py:43-48,63-64).
  * Bitmaps are in (b, u=x, v=y) order, v padded to 32 bits; coords are (b, u, v) int32. */

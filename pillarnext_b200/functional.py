@@ -1,0 +1,375 @@
+"""torch.autograd glue: every differentiable op of the hot path as an autograd.Function whose forward AND
+backward call libpnx kernels (pillarnext_b200/ops.py).  Activations between ops are bf16 row matrices
+[rows, channels] (rows = active sites or channels-last pixels); parameters stay fp32 in the reference's
+own layouts (state-dict compatible) and are repacked to the kernels' bf16 [tap, Cout, Cin] layout on the fly.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------- weights
+class WLayout:
+    """Packing between a parameter's native layout and the kernels' [taps, Cout, Cin] layout.
+    kind: 'dense' nn.Conv2d [Cout,Cin,kh,kw] | 'sp' spconv [Cout,kH(y),kW(x),Cin] (tap = kx*3+ky, rulebook order)
+          | 'convT' nn.ConvTranspose2d [Cin,Cout,2,2] (n = (dy*2+dx)*Cout + co)."""
+
+    def __init__(self, kind):
+        self.kind = kind
+
+    def pack_fwd(self, w):
+        if self.kind == "dense":
+            co, ci, kh, kw = w.shape
+            p = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+        elif self.kind == "sp":
+            co, kh, kw, ci = w.shape
+            p = w.permute(2, 1, 0, 3).reshape(kh * kw, co, ci)
+        else:
+            ci, co, kh, kw = w.shape
+            p = w.permute(2, 3, 1, 0).reshape(1, kh * kw * co, ci)
+        return p.to(torch.bfloat16).contiguous()
+
+    def pack_dgrad(self, w, flip):
+        """[taps_d, Cin, Cout] bf16 for the data-gradient GEMM."""
+        if self.kind == "convT":
+            ci, co, kh, kw = w.shape
+            return w.permute(2, 3, 0, 1).reshape(kh * kw, ci, co).to(torch.bfloat16).contiguous()
+        p = self.pack_fwd(w)
+        if flip:
+            p = p.flip(0)
+        return p.transpose(1, 2).contiguous()
+
+    def unpack_grad(self, g, shape):
+        """g fp32 [taps, Cout, Cin] (convT: [4, Cin, Cout]) -> gradient in the parameter's layout."""
+        if self.kind == "dense":
+            co, ci, kh, kw = shape
+            return g.view(kh, kw, co, ci).permute(2, 3, 0, 1).contiguous()
+        if self.kind == "sp":
+            co, kh, kw, ci = shape
+            return g.view(kw, kh, co, ci).permute(2, 1, 0, 3).contiguous()
+        ci, co, kh, kw = shape
+        return g.view(kh, kw, ci, co).permute(2, 3, 0, 1).contiguous()
+
+
+_pack_cache = {}
+
+
+def packed(w, layout, which, flip=False):
+    """Cache of bf16 packed weights keyed by parameter identity + version (repacked after optimizer steps)."""
+    if not w.is_leaf:  # e.g. per-step torch.cat of sibling-head weights: nothing stable to key on
+        with torch.no_grad():
+            return layout.pack_fwd(w) if which == "fwd" else layout.pack_dgrad(w, flip)
+    key = (id(w), which, flip, layout.kind)
+    ent = _pack_cache.get(key)
+    ver = w._version
+    if ent is not None and ent[0] == ver and ent[1] == w.data_ptr():
+        return ent[2]
+    with torch.no_grad():
+        p = layout.pack_fwd(w) if which == "fwd" else layout.pack_dgrad(w, flip)
+    _pack_cache[key] = (ver, w.data_ptr(), p)
+    return p
+
+
+class ConvSpec:
+    """Row space and neighbour map of one convolution application.
+       fwd: (nbr table | dense geometry | identity) over M_out output rows, reading M_in input rows.
+       bwd: table / geometry of the data-gradient GEMM (+ whether taps are flipped)."""
+
+    def __init__(self, M_out, M_in, taps, nbr=None, dense=None, d_nbr=None, d_dense=None, d_flip=False, d_taps=None,
+                 shuffle=False):
+        self.M_out, self.M_in, self.taps = M_out, M_in, taps
+        self.nbr, self.dense = nbr, dense
+        self.d_nbr, self.d_dense, self.d_flip = d_nbr, d_dense, d_flip
+        self.d_taps = taps if d_taps is None else d_taps
+        self.shuffle = shuffle
+
+
+def dense_spec(B, H, W, k, dil=1):
+    """Stride-1 'same' convolution on a channels-last image (zero padding = absent neighbour)."""
+    pad = dil * (k // 2)
+    geo = (H, W, H, W, k, 1, dil, pad)
+    M = B * H * W
+    return ConvSpec(M, M, k * k, dense=geo if k > 1 else None, d_dense=geo if k > 1 else None, d_flip=True)
+
+
+def convT_spec(B, H, W):
+    """ConvTranspose2d k2 s2: rows = input pixels, output image 2H x 2W."""
+    return ConvSpec(B * H * W, B * H * W, 1, dense=(H, W, H, W, 1, 1, 1, 0), d_dense=(H, W, 2 * H, 2 * W, 2, 2, 1, 0),
+                    d_taps=4, shuffle=True)
+
+
+# ------------------------------------------------------------------------------------------- conv
+class ConvFn(torch.autograd.Function):
+    """out = conv(x; w) (+bias) (relu) through pnx_igemm; optional BatchNorm statistics of the output.
+    x bf16 [M_in, >=Cin]; returns (out [M_out(*4 if shuffle), Cout], stats fp64 [2*Cs] or empty)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, spec, layout, want_stats, out_fp32, relu, n_valid_out):
+        shape = tuple(w.shape)
+        if layout.kind == "dense":
+            cout, cin = shape[0], shape[1]
+        elif layout.kind == "sp":
+            cout, cin = shape[0], shape[3]
+        else:
+            cin, cout = shape[0], shape[1]
+        wp = packed(w, layout, "fwd")
+        n_cols = wp.shape[1]
+        rows = spec.M_out * (4 if spec.shuffle else 1)
+        out_c = cout
+        out = torch.empty(rows, out_c, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
+        stats = torch.zeros(2 * cout if want_stats else 0, dtype=torch.float64, device=x.device)
+        ops.igemm(x, spec.M_out, wp, wp.shape[0], cin, n_cols, out, lda=x.stride(0), ldc=out_c, nbr=spec.nbr,
+                  dense=spec.dense, bias=bias, stats=stats if want_stats else None,
+                  stats_mod=cout if want_stats else None, shuffle=spec.shuffle, relu=relu)
+        ctx.save_for_backward(x, w, out if relu else None)
+        ctx.spec, ctx.layout, ctx.dims = spec, layout, (cin, cout, shape)
+        ctx.has_bias, ctx.relu, ctx.out_fp32 = bias is not None, relu, out_fp32
+        ctx.n_valid_out = n_valid_out
+        ctx.mark_non_differentiable(stats)
+        return out, stats
+
+    @staticmethod
+    def backward(ctx, dout, _dstats):
+        x, w, out = ctx.saved_tensors
+        spec, layout = ctx.spec, ctx.layout
+        cin, cout, shape = ctx.dims
+        rows = dout.shape[0]
+        # gradient rows as bf16, channel count padded to a multiple of 64 for the tensor-core kernels
+        cpad = (cout + 63) // 64 * 64
+        if dout.dtype != torch.bfloat16 or cpad != cout or not dout.is_contiguous():
+            dy = torch.zeros(rows, cpad, dtype=torch.bfloat16, device=dout.device) if cpad != cout else \
+                torch.empty(rows, cpad, dtype=torch.bfloat16, device=dout.device)
+            dy[:, :cout] = dout
+        else:
+            dy = dout
+        if ctx.relu:
+            g = torch.empty_like(dy)
+            ops.relu_bwd(dy, out, rows, cout, g)
+            dy = g
+        dbias = dy[:, :cout].float().sum(0) if ctx.has_bias else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wd = packed(w, layout, "dgrad", spec.d_flip)            # [taps_d, Cin, Cout]
+            if cpad != cout:
+                wd = torch.nn.functional.pad(wd, (0, cpad - cout))
+            dx = torch.empty(spec.M_in, cin, dtype=torch.bfloat16, device=dy.device)
+            ops.igemm(dy, spec.M_in, wd, wd.shape[0], cpad, cin, dx, nbr=spec.d_nbr, dense=spec.d_dense)
+            if x.shape[1] != cin:                                   # x was a column slice of a wider buffer
+                full = torch.zeros(x.shape[0], x.shape[1], dtype=torch.bfloat16, device=dy.device)
+                full[:, :cin] = dx
+                dx = full
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if layout.kind == "convT":
+                g = torch.zeros(4, cin, cout, dtype=torch.float32, device=dy.device)
+                ops.wgrad(x, cin, False, dy, cout, True, spec.M_out, 4, g, dense=spec.d_dense, shuffle=True)
+                dw = layout.unpack_grad(g, shape)
+            elif cout >= cin and cin <= 256 and cpad == cout:
+                g = torch.zeros(spec.taps, cout, cin, dtype=torch.float32, device=dy.device)
+                ops.wgrad(dy, cout, False, x, cin, spec.taps > 1 or spec.nbr is not None, spec.M_out, spec.taps, g,
+                          nbr=spec.nbr, dense=spec.dense)
+                dw = layout.unpack_grad(g, shape)
+            else:
+                g = torch.zeros(spec.taps, cin, cpad, dtype=torch.float32, device=dy.device)
+                ops.wgrad(x, cin, spec.taps > 1 or spec.nbr is not None, dy, cpad, False, spec.M_out, spec.taps, g,
+                          nbr=spec.nbr, dense=spec.dense)
+                dw = layout.unpack_grad(g[:, :, :cout].transpose(1, 2).contiguous(), shape)
+        return dx, dw, dbias, None, None, None, None, None, None
+
+
+def conv(x, w, bias, spec, layout, want_stats=False, out_fp32=False, relu=False):
+    return ConvFn.apply(x, w, bias, spec, layout, want_stats, out_fp32, relu, None)
+
+
+# ------------------------------------------------------------------------------------------- batch norm
+def _sync_enabled(bn):
+    return getattr(bn, "pnx_sync", False) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class BNActFn(torch.autograd.Function):
+    """y = relu?(BatchNorm(x_raw) (+ residual)), batch statistics taken from the conv epilogue (`stats`).
+    Training: biased batch variance, running stats updated in place (momentum/eps of `bn`).
+    pnx_sync (SyncBatchNorm semantics, reference tools/train.py:55-56): statistics all-reduced over ranks."""
+
+    @staticmethod
+    def forward(ctx, x_raw, stats, gamma, beta, residual, bn, relu, count):
+        M, C = x_raw.shape
+        if bn.training:
+            if _sync_enabled(bn):
+                pack = torch.cat([stats, torch.tensor([float(count)], dtype=torch.float64, device=stats.device)])
+                dist.all_reduce(pack)
+                stats, count = pack[:-1], float(pack[-1].item())
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            scale, shift, mean, invstd = ops.bn_finalize(stats, C, None, int(count), gamma, beta, bn.eps, mom,
+                                                         bn.running_mean, bn.running_var)
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        else:
+            scale, shift = ops.bn_eval_affine(gamma, beta, bn.running_mean, bn.running_var, bn.eps)
+            mean = invstd = None
+        y = torch.empty(M, C, dtype=torch.bfloat16, device=x_raw.device)
+        ops.bn_apply(x_raw, M, C, scale, shift, y, res=residual, relu=relu)
+        ctx.save_for_backward(x_raw, y, gamma, mean, invstd, scale)
+        ctx.relu, ctx.count, ctx.has_res, ctx.sync, ctx.training = relu, count, residual is not None, _sync_enabled(bn), bn.training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_raw, y, gamma, mean, invstd, scale = ctx.saved_tensors
+        M, C = x_raw.shape
+        dy = dy.contiguous()
+        dx = torch.empty(M, C, dtype=torch.bfloat16, device=dy.device)
+        dres = torch.empty(M, C, dtype=torch.bfloat16, device=dy.device) if ctx.has_res else None
+        if not ctx.training:
+            raise RuntimeError("pillarnext_b200: backward through eval-mode BatchNorm is not supported")
+        if ctx.sync:
+            red = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
+            from ._lib import check, lib, ptr, stream
+            check(lib().pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), ptr(y), y.stride(0), ptr(x_raw), x_raw.stride(0), M, C,
+                                          ptr(mean), ptr(invstd), 1 if ctx.relu else 0, ptr(red), stream()))
+            local = red.clone()
+            dist.all_reduce(red)
+            check(lib().pnx_bn_bwd_apply(ptr(dy), dy.stride(0), ptr(y), y.stride(0), ptr(x_raw), x_raw.stride(0), M, C,
+                                         ptr(mean), ptr(invstd), ptr(gamma), ptr(red), float(max(ctx.count, 1)),
+                                         1 if ctx.relu else 0, ptr(dx), dx.stride(0), ptr(dres) if dres is not None else None,
+                                         dres.stride(0) if dres is not None else 8, 0, stream()))
+            red = local
+        else:
+            red = ops.bn_bwd(dy, y, x_raw, M, C, mean, invstd, gamma, ctx.count, ctx.relu, dx, dres=dres)
+        r = red.float()
+        return dx, None, r[C:], r[:C], dres, None, None, None
+
+
+def bn_act(x_raw, stats, bn, relu=True, residual=None, count=None):
+    return BNActFn.apply(x_raw, stats, bn.weight, bn.bias, residual, bn, relu, x_raw.shape[0] if count is None else count)
+
+
+class AddReluIntoFn(torch.autograd.Function):
+    """cat_buf[:, :C] = relu(a + b) (BasicBlock tail, conv.py:48-50) written straight into slot 0 of the
+    ASPP concat buffer; returns the buffer."""
+
+    @staticmethod
+    def forward(ctx, a, b, cat_buf):
+        M, C = a.shape
+        ops.add_relu(a, b, M, C, cat_buf[:, :C])
+        ctx.save_for_backward(cat_buf)
+        ctx.C = C
+        ctx.mark_dirty(cat_buf)
+        return cat_buf
+
+    @staticmethod
+    def backward(ctx, dcat):
+        (cat_buf,) = ctx.saved_tensors
+        M, C = cat_buf.shape[0], ctx.C
+        g = torch.empty(M, C, dtype=torch.bfloat16, device=dcat.device)
+        ops.relu_bwd(dcat[:, :C], cat_buf[:, :C], M, C, g)
+        return g, g, None
+
+
+# ------------------------------------------------------------------------------------------- dense()
+class DensifyFn(torch.autograd.Function):
+    """SparseConvTensor.dense() (sparse_resnet.py:68) into channels-last rows [B*H*W, C]; backward gathers."""
+
+    @staticmethod
+    def forward(ctx, feat, level):
+        C = feat.shape[1]
+        canvas = ops.scatter_dense(feat, level, C)
+        ctx.level, ctx.C = level, C
+        return canvas.view(-1, C)
+
+    @staticmethod
+    def backward(ctx, dcanvas):
+        lv, C = ctx.level, ctx.C
+        d = torch.empty(max(lv.n, 1), C, dtype=torch.bfloat16, device=dcanvas.device)[:lv.n]
+        g = dcanvas.contiguous().view(lv.batch, lv.V, lv.U, C)
+        if lv.n:
+            ops.scatter_dense(d, lv, C, canvas=g, gather=True)
+        return d, None
+
+
+# ------------------------------------------------------------------------------------------- ASPP branches
+class ASPPBranchesFn(torch.autograd.Function):
+    """cat(x, conv1x1(x), W(*)x d=1, d=6, d=12, d=18) (aspp.py:21-31): five GEMMs writing the column slots of one
+    [M, 6C] buffer whose slot 0 already holds x.  Backward: five data-gradient GEMMs chained through the
+    epilogue addend, weight gradients of the four dilations accumulated into the one shared tensor."""
+    DILS = (1, 6, 12, 18)
+
+    @staticmethod
+    def forward(ctx, cat_buf, w1x1, wshared, B, H, W):
+        M, C6 = cat_buf.shape
+        C = C6 // 6
+        l = WLayout("dense")
+        x = cat_buf[:, :C]
+        ops.igemm(x, M, packed(w1x1, l, "fwd"), 1, C, C, cat_buf[:, C:2 * C], lda=C6, ldc=C6)
+        wp = packed(wshared, l, "fwd")
+        for j, d in enumerate(ASPPBranchesFn.DILS):
+            ops.igemm(x, M, wp, 9, C, C, cat_buf[:, (2 + j) * C:(3 + j) * C], lda=C6, ldc=C6, dense=(H, W, H, W, 3, 1, d, d))
+        ctx.save_for_backward(cat_buf, w1x1, wshared)
+        ctx.geo = (B, H, W, C)
+        ctx.mark_dirty(cat_buf)
+        return cat_buf
+
+    @staticmethod
+    def backward(ctx, dcat):
+        cat_buf, w1x1, wshared = ctx.saved_tensors
+        B, H, W, C = ctx.geo
+        M, C6 = cat_buf.shape
+        l = WLayout("dense")
+        dcat = dcat.contiguous()
+        x = cat_buf[:, :C]
+        # dx = dcat[:, 0:C] + dgrad_1x1(dcat[:, C:2C]) + sum_d dgrad_d(dcat[:, slot d])
+        dx = torch.empty(M, C, dtype=torch.bfloat16, device=dcat.device)
+        ops.igemm(dcat[:, C:2 * C], M, packed(w1x1, l, "dgrad", True), 1, C, C, dx, lda=C6, addend=dcat[:, :C])
+        wd = packed(wshared, l, "dgrad", True)
+        for j, d in enumerate(ASPPBranchesFn.DILS):
+            nxt = torch.empty_like(dx)
+            ops.igemm(dcat[:, (2 + j) * C:(3 + j) * C], M, wd, 9, C, C, nxt, lda=C6, dense=(H, W, H, W, 3, 1, d, d), addend=dx)
+            dx = nxt
+        g1 = torch.zeros(1, C, C, dtype=torch.float32, device=dcat.device)
+        ops.wgrad(dcat[:, C:2 * C], C, False, x, C, False, M, 1, g1)
+        gs = torch.zeros(9, C, C, dtype=torch.float32, device=dcat.device)
+        for j, d in enumerate(ASPPBranchesFn.DILS):
+            ops.wgrad(dcat[:, (2 + j) * C:(3 + j) * C], C, False, x, C, True, M, 9, gs, dense=(H, W, H, W, 3, 1, d, d))
+        dbuf = torch.empty_like(dcat)          # only slot 0 is consumed upstream (AddReluIntoFn.backward)
+        dbuf[:, :C] = dx
+        return dbuf, l.unpack_grad(g1, tuple(w1x1.shape)), l.unpack_grad(gs, tuple(wshared.shape)), None, None, None
+
+
+# ------------------------------------------------------------------------------------------- reader
+class PFNFn(torch.autograd.Function):
+    """PillarFeatureNet on pre-voxelized points: returns feat fp32 [P, 64] (pillar_encoder.py:174-182)."""
+
+    @staticmethod
+    def forward(ctx, w0, g0, b0, w1, g1, b1, voxels, bn0, bn1, training):
+        P, _ = voxels.sync_counts()
+        fwd = ops.pfn_forward(voxels, w0, (g0, b0, bn0.running_mean, bn0.running_var), w1,
+                              (g1, b1, bn1.running_mean, bn1.running_var), training, eps=bn0.eps, momentum=bn0.momentum)
+        if training:
+            for bn in (bn0, bn1):
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+        ctx.voxels, ctx.fwd, ctx.training = voxels, fwd, training
+        ctx.save_for_backward(w1, g0, g1)
+        voxels.feat_bf16 = fwd["feat_bf16"]
+        return fwd["feat"][:P]
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        if not ctx.training:
+            raise RuntimeError("pillarnext_b200: backward through an eval-mode reader is not supported")
+        w1, g0, g1 = ctx.saved_tensors
+        dW0, dW1, dg0, db0, dg1, db1 = ops.pfn_backward(ctx.voxels, ctx.fwd, dfeat.contiguous().float(), w1, g0, g1)
+        return dW0, dg0, db0, dW1, dg1, db1, None, None, None, None
+
+
+class ToBF16RowsFn(torch.autograd.Function):
+    """fp32 [P,64] reader output -> the bf16 copy the PFN kernel already wrote (identity for autograd)."""
+
+    @staticmethod
+    def forward(ctx, feat, feat_bf16):
+        return feat_bf16[:feat.shape[0]]
+
+    @staticmethod
+    def backward(ctx, d):
+        return d.float(), None

@@ -1,0 +1,518 @@
+"""Host-side mirror of the reference's model classes for the PillarNeXt-B hot path.
+
+Same class names, constructor kwargs, forward signatures and state-dict keys as the reference
+ so hydra's `_target_` strings, `load_checkpoint(strict=True)`, DDP and
+`tools/train.py` / `tools/test.py` work unchanged -- but every forward/backward runs in libpnx (sm_100a).
+The drop-in module paths live in the top-level `det3d/` package, which re-exports these classes.
+
+  PillarFeatureNet  <- det3d/models/readers/pillar_encoder.py:128-182
+  SparseResNet      <- det3d/models/backbones/sparse_resnet.py:10-68 (+ utils/sparse_conv.py:16-63)
+  ASPPNeck          <- det3d/models/necks/aspp.py:8-40 (+ utils/conv.py)
+  CenterHead        <- det3d/models/heads/centerhead.py:62-136 (forward), :142-229 (loss)
+  SingleStageDetector <- det3d/models/detectors/single_stage.py:5-59
+"""
+import copy
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import functional as Fn
+from . import loss as L
+from . import ops
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("pillarnext_b200.%s runs on CUDA (sm_100a) only -- there is no CPU path" % what)
+
+
+# =========================================================================================== reader
+class PFNLayer(nn.Module):
+    """Parameter container with the reference's names (pillar_encoder.py:15-33): linear.weight, norm.*"""
+
+    def __init__(self, in_channels, out_channels, norm_cfg=None, last_layer=False):
+        super().__init__()
+        self.last_vfe = last_layer
+        if not self.last_vfe:
+            out_channels = out_channels // 2
+        self.units = out_channels
+        self.linear = nn.Linear(in_channels, out_channels, bias=False)
+        self.norm = nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01)
+
+
+class PillarNet(nn.Module):
+    """Dynamic voxelizer (pillar_encoder.py:53-125). forward(points) -> (features[Nv,10] are NOT materialised
+    here; use PillarFeatureNet) -- kept for API completeness: returns the voxelizer result object."""
+
+    def __init__(self, num_input_features, voxel_size, pc_range):
+        super().__init__()
+        self.voxel_size = np.array(voxel_size)
+        self.pc_range = np.array(pc_range)
+
+    def forward(self, points, batch_size=None):
+        _require_cuda(points, "PillarNet")
+        if batch_size is None:
+            batch_size = int(points[:, 0].max().item()) + 1 if points.shape[0] else 1
+        return ops.voxelize(points, batch_size, self.voxel_size, self.pc_range)
+
+
+class Pyramid:
+    """Active-site levels + neighbour tables of the sparse backbone for one batch (built once per step)."""
+    pass
+
+
+def build_pyramid(vox, strides):
+    """Level 0 = pillars; level s+1 = SparseConv2d(k3,p1,stride) dilation of level s.  One host sync for all
+    site counts.  Returns Pyramid with levels[0..4], entry specs (regular conv) and subm specs per stage."""
+    lv0 = ops.level_from_bitmap(vox.bitmap, vox.word_prefix, vox.counts[0:1], vox.batch, vox.gx, vox.gy)
+    levels = [lv0]
+    for s in strides:
+        levels.append(ops.level_dilate(levels[-1], int(s)))
+    counts = torch.cat([vox.counts] + [lv.count for lv in levels[1:]]).cpu().tolist()   # the one sync
+    vox.P, vox.Nv = int(counts[0]), int(counts[1])
+    ns = [vox.P] + [int(c) for c in counts[2:]]
+    for lv, n in zip(levels, ns):
+        ops.level_coords(lv, n)
+    pyr = Pyramid()
+    pyr.levels, pyr.entry, pyr.subm = levels, [], []
+    for s, stride in enumerate(strides):
+        src, dst = levels[s], levels[s + 1]
+        nbr = ops.nbr_table(dst, src, int(stride), False)
+        nbr_t = ops.nbr_table(src, dst, int(stride), True)
+        pyr.entry.append(Fn.ConvSpec(dst.n, src.n, 9, nbr=nbr, d_nbr=nbr_t, d_flip=False))
+        sub = ops.nbr_table(dst, dst, 1, False)
+        pyr.subm.append(Fn.ConvSpec(dst.n, dst.n, 9, nbr=sub, d_nbr=sub, d_flip=True))
+    last = levels[-1]
+    pyr.map1x1 = Fn.ConvSpec(last.n, last.n, 1)
+    return pyr
+
+
+class PillarFeatureNet(nn.Module):
+    def __init__(self, num_input_features, num_filters, voxel_size, pc_range, norm_cfg=None):
+        super().__init__()
+        assert len(num_filters) > 0
+        num_input_features += 5
+        num_filters = [num_input_features] + list(num_filters)
+        if list(num_filters) != [10, 64, 64]:
+            raise NotImplementedError("pillarnext_b200 implements the PillarNeXt-B reader: 5+5 inputs, num_filters=[64,64]")
+        layers = []
+        for i in range(len(num_filters) - 1):
+            layers.append(PFNLayer(num_filters[i], num_filters[i + 1], norm_cfg=norm_cfg, last_layer=i == len(num_filters) - 2))
+        self.pfn_layers = nn.ModuleList(layers)
+        self.feature_output_dim = num_filters[-1]
+        self.voxel_size = np.array(voxel_size)
+        self.pc_range = np.array(pc_range)
+        self.voxelization = PillarNet(num_input_features, voxel_size, pc_range)
+        self.pyramid_strides = None      # set by SingleStageDetector: build the backbone rulebook in the same sync
+        self.batch_size = None           # frames per batch when known by the caller (else read from the points)
+
+    def forward(self, points):
+        """points [N, 6] (batch_idx, x, y, z, intensity, time) -> (feat_max [P,64] fp32, coords [P,3] int32 (b,y,x),
+        grid_size np.int64[2] (H, W)) exactly like pillar_encoder.py:174-182."""
+        _require_cuda(points, "PillarFeatureNet")
+        points = points.float()
+        B = self.batch_size
+        if B is None:
+            B = int(points[:, 0].max().item()) + 1 if points.shape[0] else 1
+        vox = ops.voxelize(points, B, self.voxel_size, self.pc_range)
+        if self.pyramid_strides is not None:
+            vox.pyramid = build_pyramid(vox, self.pyramid_strides)
+        l0, l1 = self.pfn_layers[0], self.pfn_layers[1]
+        feat = Fn.PFNFn.apply(l0.linear.weight, l0.norm.weight, l0.norm.bias, l1.linear.weight, l1.norm.weight,
+                              l1.norm.bias, vox, l0.norm, l1.norm, self.training)
+        coords = vox.coords[:vox.P]
+        feat._pnx_vox = vox              # lets SparseResNet reuse the bitmap / rulebook (plain tensors also work)
+        grid = ops.grid_size_xy(self.voxel_size, self.pc_range)
+        return feat, coords, grid[[1, 0]]
+
+
+# =========================================================================================== backbone
+class _SpConv(nn.Module):
+    """Holds `weight` in spconv's layout [Cout, kH, kW, Cin] (bias=False everywhere in the reference)."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, k, k, cin))
+        nn.init.kaiming_uniform_(self.weight.view(cout, -1), a=5 ** 0.5)   # spconv default init (uniform, fan_in = k*k*cin)
+        self.in_channels, self.out_channels, self.kernel_size = cin, cout, k
+
+
+class SparseConvBlock(nn.Module):
+    """sparse_conv.py:16-39: conv + BatchNorm1d(eps 1e-3, mom 0.01) + ReLU"""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, use_subm=True, bias=False):
+        super().__init__()
+        assert not bias
+        self.conv = _SpConv(in_channels, out_channels, kernel_size)
+        self.norm = nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01)
+        self.act = nn.ReLU()
+        self.stride, self.subm = stride, (stride == 1 and use_subm)
+
+    def run(self, x, spec):
+        raw, stats = Fn.conv(x, self.conv.weight, None, spec, Fn.WLayout("sp"), want_stats=True)
+        return Fn.bn_act(raw, stats, self.norm, relu=True)
+
+
+class SparseBasicBlock(nn.Module):
+    """sparse_conv.py:42-63"""
+
+    def __init__(self, channels, kernel_size):
+        super().__init__()
+        self.block1 = SparseConvBlock(channels, channels, kernel_size, 1)
+        self.conv2 = _SpConv(channels, channels, kernel_size)
+        self.norm2 = nn.BatchNorm1d(channels, eps=1e-3, momentum=0.01)
+        self.act2 = nn.ReLU()
+
+    def run(self, x, spec):
+        out = self.block1.run(x, spec)
+        raw, stats = Fn.conv(out, self.conv2.weight, None, spec, Fn.WLayout("sp"), want_stats=True)
+        return Fn.bn_act(raw, stats, self.norm2, relu=True, residual=x)      # relu(bn(conv) + identity)
+
+
+class _Stage(nn.Sequential):
+    pass
+
+
+class SparseResNet(nn.Module):
+    def __init__(self, layer_nums, ds_layer_strides, ds_num_filters, num_input_features, kernel_size=[3, 3, 3, 3],
+                 out_channels=256):
+        super().__init__()
+        self._layer_strides = [int(s) for s in ds_layer_strides]
+        self._num_filters = [int(c) for c in ds_num_filters]
+        self._layer_nums = [int(n) for n in layer_nums]
+        self._num_input_features = int(num_input_features)
+        assert len(self._layer_strides) == len(self._layer_nums) == len(self._num_filters)
+        assert all(int(k) == 3 for k in kernel_size), "PillarNeXt-B uses 3x3 kernels"
+        in_filters = [self._num_input_features, *self._num_filters[:-1]]
+        blocks = []
+        for i, n in enumerate(self._layer_nums):
+            layers = [SparseConvBlock(in_filters[i], self._num_filters[i], 3, self._layer_strides[i], use_subm=False)]
+            layers += [SparseBasicBlock(self._num_filters[i], 3) for _ in range(n)]
+            blocks.append(_Stage(*layers))
+        self.blocks = nn.ModuleList(blocks)
+        self.mapping = nn.Sequential(_SpConv(self._num_filters[-1], out_channels, 1),
+                                     nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01), nn.ReLU())
+        self.out_channels = out_channels
+
+    def _pyramid_from_plain(self, feat, coors, input_shape):
+        raise NotImplementedError(
+            "SparseResNet needs the rulebook built by pillarnext_b200's PillarFeatureNet (feat._pnx_vox); "
+            "feeding hand-made (features, coords) tensors is not supported yet")
+
+    def forward(self, pillar_features, coors, input_shape):
+        """-> dense [B, 256, H/8, W/8] (bf16, channels-last memory) like sparse_resnet.py:61-68.
+        NOTE (Appendix A): B is the collated batch size, not len(unique(coors[:,0]))."""
+        _require_cuda(pillar_features, "SparseResNet")
+        vox = getattr(pillar_features, "_pnx_vox", None)
+        if vox is None:
+            return self._pyramid_from_plain(pillar_features, coors, input_shape)
+        pyr = getattr(vox, "pyramid", None)
+        if pyr is None:
+            pyr = vox.pyramid = build_pyramid(vox, self._layer_strides)
+        x = Fn.ToBF16RowsFn.apply(pillar_features, vox.feat_bf16)
+        for s, stage in enumerate(self.blocks):
+            x = stage[0].run(x, pyr.entry[s])
+            for blk in list(stage)[1:]:
+                x = blk.run(x, pyr.subm[s])
+        raw, stats = Fn.conv(x, self.mapping[0].weight, None, pyr.map1x1, Fn.WLayout("sp"), want_stats=True)
+        x = Fn.bn_act(raw, stats, self.mapping[1], relu=True)
+        last = pyr.levels[-1]
+        rows = Fn.DensifyFn.apply(x, last)
+        return rows.view(last.batch, last.V, last.U, self.out_channels).permute(0, 3, 1, 2)
+
+
+# =========================================================================================== neck
+class _Conv(nn.Module):
+    """conv.py:3-14 `Conv`: holds .conv (nn.Conv2d / nn.ConvTranspose2d parameters only)."""
+
+    def __init__(self, inplanes, planes, kernel_size, stride, conv_layer=nn.Conv2d, bias=False, **kwargs):
+        super().__init__()
+        padding = kwargs.get("padding", kernel_size // 2)
+        self.conv = conv_layer(inplanes, planes, kernel_size=kernel_size, stride=stride, padding=padding, bias=bias)
+
+
+class ConvBlock(nn.Module):
+    """conv.py:17-34: conv(bias=False) + BatchNorm2d + ReLU on channels-last rows."""
+
+    def __init__(self, inplanes, planes, kernel_size, stride=1, conv_layer=nn.Conv2d, norm_layer=nn.BatchNorm2d,
+                 act_layer=nn.ReLU, **kwargs):
+        super().__init__()
+        padding = kwargs.get("padding", kernel_size // 2)
+        self.conv = _Conv(inplanes, planes, kernel_size=kernel_size, stride=stride, padding=padding, bias=False,
+                          conv_layer=conv_layer)
+        self.norm = norm_layer(planes)
+        self.act = act_layer()
+        self.is_transpose = conv_layer is nn.ConvTranspose2d
+        self.kernel_size = kernel_size
+
+    def run(self, x, B, H, W):
+        if self.is_transpose:
+            raw, stats = Fn.conv(x, self.conv.conv.weight, None, Fn.convT_spec(B, H, W), Fn.WLayout("convT"), want_stats=True)
+        else:
+            raw, stats = Fn.conv(x, self.conv.conv.weight, None, Fn.dense_spec(B, H, W, self.kernel_size),
+                                 Fn.WLayout("dense"), want_stats=True)
+        return Fn.bn_act(raw, stats, self.norm, relu=True)
+
+
+class BasicBlock(nn.Module):
+    """conv.py:37-51: relu(block2(block1(x)) + x), both blocks with their own ReLU."""
+
+    def __init__(self, inplanes, kernel_size=3):
+        super().__init__()
+        self.block1 = ConvBlock(inplanes, inplanes, kernel_size=kernel_size)
+        self.block2 = ConvBlock(inplanes, inplanes, kernel_size=kernel_size)
+        self.act = nn.ReLU()
+
+
+def _to_rows(x):
+    """NCHW tensor (any dtype/strides) -> (rows bf16 [B*H*W, C], B, H, W); free if already channels-last bf16."""
+    B, C, H, W = x.shape
+    r = x.permute(0, 2, 3, 1)
+    if r.dtype != torch.bfloat16:
+        r = r.to(torch.bfloat16)
+    return r.contiguous().view(B * H * W, C), B, H, W
+
+
+class ASPPNeck(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        self.pre_conv = BasicBlock(in_channels)
+        self.conv1x1 = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, bias=False, padding=0)
+        self.weight = nn.Parameter(torch.randn(in_channels, in_channels, 3, 3))
+        self.post_conv = ConvBlock(in_channels * 6, in_channels, kernel_size=1, stride=1)
+        self.in_channels = in_channels
+
+    def forward(self, x):
+        """aspp.py:19-40 (activation checkpointing dropped: values identical, B200 has the memory)."""
+        _require_cuda(x, "ASPPNeck")
+        rows, B, H, W = _to_rows(x)
+        C = self.in_channels
+        o = self.pre_conv.block1.run(rows, B, H, W)
+        o = self.pre_conv.block2.run(o, B, H, W)
+        cat = torch.empty(rows.shape[0], 6 * C, dtype=torch.bfloat16, device=rows.device)
+        cat = Fn.AddReluIntoFn.apply(o, rows, cat)
+        cat = Fn.ASPPBranchesFn.apply(cat, self.conv1x1.weight, self.weight, B, H, W)
+        y = self.post_conv.run(cat, B, H, W)
+        return y.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+# =========================================================================================== head
+class SepHead(nn.Module):
+    """centerhead.py:12-59.  Parameters are kept per head with the reference's names
+    (`<head>.0` conv, `<head>.1` BN, `<head>.3` final conv); the forward batches all sibling heads of a task:
+    one 64->(64*heads) 3x3 GEMM + one BatchNorm over the concatenated channels + one block-diagonal
+    (64*heads)->sum(classes) 3x3 GEMM (same arithmetic per output channel)."""
+
+    def __init__(self, in_channels, heads, stride=1, head_conv=64, final_kernel=1, bn=True, init_bias=-2.19, **kwargs):
+        super().__init__(**kwargs)
+        if stride > 1:
+            self.deblock = ConvBlock(in_channels, head_conv, kernel_size=int(stride), stride=int(stride), padding=0,
+                                     conv_layer=nn.ConvTranspose2d)
+            in_channels = head_conv
+        else:
+            self.deblock = nn.Identity()
+        self.stride = int(stride)
+        assert self.stride in (1, 2), "CenterHead strides 1 or 2"
+        self.heads = heads
+        self.head_conv, self.final_kernel = head_conv, final_kernel
+        for head in self.heads:
+            classes, num_conv = self.heads[head]
+            assert num_conv == 2 and bn and final_kernel == 3, "PillarNeXt-B heads: conv3x3+BN+ReLU+conv3x3"
+            fc = nn.Sequential()
+            fc.append(nn.Conv2d(in_channels, head_conv, kernel_size=final_kernel, stride=1, padding=final_kernel // 2, bias=True))
+            fc.append(nn.BatchNorm2d(head_conv))
+            fc.append(nn.ReLU())
+            fc.append(nn.Conv2d(head_conv, classes, kernel_size=final_kernel, stride=1, padding=final_kernel // 2, bias=True))
+            if "hm" in head:
+                fc[-1].bias.data.fill_(init_bias)
+            self.__setattr__(head, fc)
+        self._bn_cat = None
+
+    def _cat_bn(self, names):
+        """One BatchNorm2d-like holder over the concatenated sibling channels; running stats are views that are
+        copied back to the per-head buffers after each forward."""
+        hc = self.head_conv
+        bn = self._bn_cat
+        if bn is None or bn.running_mean.device != getattr(self, names[0])[1].running_mean.device:
+            bn = nn.BatchNorm2d(hc * len(names)).to(getattr(self, names[0])[1].running_mean.device)
+            object.__setattr__(self, "_bn_cat", bn)   # not a registered submodule: no extra state-dict keys
+        bn.training = self.training
+        ref = getattr(self, names[0])[1]
+        bn.eps, bn.momentum = ref.eps, ref.momentum
+        bn.pnx_sync = getattr(ref, "pnx_sync", False)
+        with torch.no_grad():
+            bn.running_mean.copy_(torch.cat([getattr(self, n)[1].running_mean for n in names]))
+            bn.running_var.copy_(torch.cat([getattr(self, n)[1].running_var for n in names]))
+        return bn
+
+    def run(self, x, B, H, W):
+        names = list(self.heads.keys())
+        hc = self.head_conv
+        if self.stride > 1:
+            x = self.deblock.run(x, B, H, W)
+            H, W = 2 * H, 2 * W
+        wa = torch.cat([getattr(self, n)[0].weight for n in names], 0)
+        ba = torch.cat([getattr(self, n)[0].bias for n in names], 0)
+        ga = torch.cat([getattr(self, n)[1].weight for n in names], 0)
+        be = torch.cat([getattr(self, n)[1].bias for n in names], 0)
+        bn = self._cat_bn(names)
+        raw, stats = Fn.conv(x, wa, ba, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), want_stats=True)
+        y = Fn.BNActFn.apply(raw, stats, ga, be, None, bn, True, raw.shape[0])
+        if self.training:
+            with torch.no_grad():
+                for i, n in enumerate(names):
+                    m = getattr(self, n)[1]
+                    m.running_mean.copy_(bn.running_mean[i * hc:(i + 1) * hc])
+                    m.running_var.copy_(bn.running_var[i * hc:(i + 1) * hc])
+                    m.num_batches_tracked += 1
+        classes = [self.heads[n][0] for n in names]
+        tot = sum(classes)
+        npad = (tot + 15) // 16 * 16
+        wb = x.new_zeros((npad, hc * len(names), 3, 3), dtype=torch.float32)
+        bb = x.new_zeros((npad,), dtype=torch.float32)
+        rows_w, rows_b, o = [], [], 0
+        for i, n in enumerate(names):
+            w = getattr(self, n)[3].weight                                   # [c, 64, 3, 3]
+            rows_w.append(torch.nn.functional.pad(w, (0, 0, 0, 0, i * hc, (len(names) - 1 - i) * hc)))
+            rows_b.append(getattr(self, n)[3].bias)
+            o += classes[i]
+        wb = torch.cat(rows_w + ([wb[tot:]] if npad > tot else []), 0)
+        bb = torch.cat(rows_b + ([bb[tot:]] if npad > tot else []), 0)
+        out, _ = Fn.conv(y, wb, bb, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), out_fp32=True)
+        out = out.view(B, H, W, npad)
+        ret, o = dict(), 0
+        for i, n in enumerate(names):
+            ret[n] = out[..., o:o + classes[i]].permute(0, 3, 1, 2)
+            o += classes[i]
+        return ret
+
+    def forward(self, x):
+        rows, B, H, W = _to_rows(x)
+        return self.run(rows, B, H, W)
+
+
+class CenterHead(nn.Module):
+    def __init__(self, in_channels, tasks, weight, code_weights, common_heads, strides, init_bias=-2.19,
+                 share_conv_channel=64, num_hm_conv=2, with_reg_iou=False, voxel_size=None, pc_range=None,
+                 out_size_factor=None, rectifier=[[0.], [0.], [0.]]):
+        super().__init__()
+        tasks = [list(t) for t in tasks]
+        num_classes = [len(t) for t in tasks]
+        self.class_names = tasks
+        self.code_weights = [float(c) for c in code_weights]
+        self.weight = float(weight)
+        self.in_channels = in_channels
+        self.num_classes = num_classes
+        self.with_reg_iou = with_reg_iou
+        common_heads = OrderedDict((k, (int(v[0]), int(v[1]))) for k, v in dict(common_heads).items())
+        self.with_iou = "iou" in common_heads
+        if self.with_iou or with_reg_iou:
+            self.voxel_size = [float(v) for v in voxel_size]
+            self.pc_range = [float(v) for v in pc_range]
+            self.out_size_factor = [int(v) for v in out_size_factor]
+        self.strides = [int(s) for s in strides]
+        self.rectifier = rectifier
+        self.shared_conv = nn.Sequential(
+            nn.Conv2d(in_channels, share_conv_channel, kernel_size=3, padding=1, bias=True),
+            nn.BatchNorm2d(share_conv_channel), nn.ReLU(inplace=True))
+        self.tasks = nn.ModuleList()
+        for num_cls, stride in zip(num_classes, self.strides):
+            heads = copy.deepcopy(common_heads)
+            heads.update(dict(hm=(num_cls, num_hm_conv)))
+            self.tasks.append(SepHead(share_conv_channel, heads, stride=stride, bn=True, init_bias=init_bias, final_kernel=3))
+
+    def forward(self, x, *kwargs):
+        """centerhead.py:128-136 -> list (one per task) of dict head-name -> [B, c, H', W'] fp32."""
+        _require_cuda(x, "CenterHead")
+        rows, B, H, W = _to_rows(x)
+        raw, stats = Fn.conv(rows, self.shared_conv[0].weight, self.shared_conv[0].bias, Fn.dense_spec(B, H, W, 3),
+                             Fn.WLayout("dense"), want_stats=True)
+        y = Fn.bn_act(raw, stats, self.shared_conv[1], relu=True)
+        return [task.run(y, B, H, W) for task in self.tasks]
+
+    def loss(self, example, preds_dicts, **kwargs):
+        """centerhead.py:142-229 (nuScenes / Waymo without the `iou` head)."""
+        if self.with_iou:
+            raise NotImplementedError("the Waymo `iou` head loss (rotated aligned IoU target) is a 'next' row (F2)")
+        return L.center_loss(example, preds_dicts, self.class_names, self.weight, self.code_weights, self.with_reg_iou,
+                             getattr(self, "voxel_size", None), getattr(self, "pc_range", None),
+                             getattr(self, "out_size_factor", None))
+
+    @torch.no_grad()
+    def predict(self, example, preds_dicts, test_cfg):
+        raise NotImplementedError("decode + rotated NMS is SURVEY.md section 8f row F1 (not built yet)")
+
+
+# =========================================================================================== detector
+class SingleStageDetector(nn.Module):
+    def __init__(self, reader, backbone=None, neck=None, head=None, post_processing=None, **kwargs):
+        super().__init__()
+        self.reader = reader
+        self.backbone = backbone
+        self.neck = neck
+        self.head = head
+        self.post_processing = post_processing
+        if kwargs.get("sync_batchnorm", False):
+            enable_sync_batchnorm(self)
+        if backbone is not None and hasattr(reader, "pyramid_strides"):
+            reader.pyramid_strides = list(backbone._layer_strides)
+
+    def extract_feat(self, data):
+        x = self.reader(data)
+        if self.backbone is not None:
+            x = self.backbone(*x)
+        if self.neck is not None:
+            x = self.neck(x)
+        return x
+
+    def _forward(self, example):
+        points = example["points"]
+        if hasattr(self.reader, "batch_size"):
+            tok = example.get("token") if isinstance(example, dict) else None
+            self.reader.batch_size = len(tok) if tok is not None and len(tok) > 0 else None
+        x = self.extract_feat(points)
+        return self.head(x)
+
+    def forward(self, example):
+        return self.training_step(example) if self.training else self.validation_step(example)
+
+    def training_step(self, example):
+        preds = self._forward(example)
+        return self.head.loss(example, preds)
+
+    @torch.no_grad()
+    def validation_step(self, example):
+        preds = self._forward(example)
+        outputs = self.head.predict(example, preds, self.post_processing)
+        detections = {}
+        for output in outputs:
+            token = output["token"]
+            for k, v in output.items():
+                if k != "token":
+                    output[k] = v.to(torch.device("cpu"))
+            detections.update({token: output})
+        return detections
+
+
+def enable_sync_batchnorm(module, enabled=True):
+    """SyncBatchNorm semantics (reference tools/train.py:55-56) for this package's fused BN ops:
+    statistics are all-reduced over the default process group.  Off by default (BASELINE north_star:
+    gradient all-reduce only)."""
+    for m in module.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.pnx_sync = enabled
+    return module
+
+
+def build_pillarnext_b(cfg, sync_batchnorm=False):
+    """PillarNeXt-B (`pillarnet18_aspp`) from a synth-style config dict (what hydra would instantiate from
+    configs/experiments/nusc_det_pp18_aspp_iou_sp.yaml)."""
+    reader = PillarFeatureNet(5, [64, 64], cfg["voxel_size"], cfg["pc_range"])
+    backbone = SparseResNet([2, 2, 2, 2], cfg["strides"], [64, 128, 256, 256], 64)
+    neck = ASPPNeck(256)
+    head = CenterHead(256, cfg["tasks"], cfg["weight"], cfg["code_weights"], cfg["common_heads"], cfg["head_strides"],
+                      with_reg_iou=cfg["with_reg_iou"], voxel_size=cfg["voxel_size"], pc_range=cfg["pc_range"],
+                      out_size_factor=cfg["out_size_factor"])
+    return SingleStageDetector(reader, backbone, neck, head, sync_batchnorm=sync_batchnorm)

@@ -143,6 +143,33 @@ def pfn_forward(v, w0, bn0, w1, bn1, training, eps=1e-3, momentum=0.01, want_f32
     return out
 
 
+def pfn_backward(v, fwd, dfeat, w1, gamma0, gamma1):
+    """Backward of pfn_forward (training mode). dfeat fp32 [>=P, 64] contiguous.
+    Returns dW0 [32,10], dW1 [64,64], dgamma0, dbeta0, dgamma1, dbeta1 (fp32)."""
+    dev = dfeat.device
+    n, cap_p = max(v.n, 1), max(v.cap_p, 1)
+    assert dfeat.dtype == torch.float32 and dfeat.is_contiguous() and dfeat.shape[0] >= min(v.P or 0, cap_p)
+    if dfeat.shape[0] < cap_p:
+        full = torch.zeros(cap_p, 64, dtype=torch.float32, device=dev)
+        full[:dfeat.shape[0]] = dfeat
+        dfeat = full
+    argq1 = torch.empty(cap_p, 64, dtype=torch.int32, device=dev)
+    d_x0 = torch.empty(n, 32, dtype=torch.float32, device=dev)
+    dxm = torch.empty(n, 32, dtype=torch.float32, device=dev)
+    red = torch.zeros(64 + 128, dtype=torch.float64, device=dev)
+    dW0 = torch.zeros(32, 10, dtype=torch.float32, device=dev)
+    dW1 = torch.zeros(64, 64, dtype=torch.float32, device=dev)
+    check(lib().pnx_pfn_backward(ptr(v.points), ptr(v.bucket_off), ptr(v.bucket_pts), ptr(v.pillar_of_point),
+                                 ptr(v.coords), ptr(v.counts), v.n, v.cap_p, v.min_x, v.min_y, v.vs_x, v.vs_y,
+                                 ptr(fwd["mean"]), ptr(fwd["y0"]), ptr(fwd["y1"]), ptr(fwd["x0max"]), ptr(fwd["feat"]),
+                                 ptr(dfeat), ptr(w1), ptr(fwd["sc0"]), ptr(fwd["sh0"]), ptr(fwd["mean0"]),
+                                 ptr(fwd["invstd0"]), ptr(gamma0), ptr(fwd["sc1"]), ptr(fwd["sh1"]), ptr(fwd["mean1"]),
+                                 ptr(fwd["invstd1"]), ptr(gamma1), ptr(argq1), ptr(d_x0), ptr(dxm), ptr(red), ptr(dW0),
+                                 ptr(dW1), stream()))
+    r = red.float()
+    return dW0, dW1, r[32:64], r[0:32], r[128:192], r[64:128]
+
+
 # --------------------------------------------------------------------------------- sites / rulebook
 class Level:
     """Active-site set of one backbone level: bitmap (b,u,v), prefix, coords [n,3], count."""

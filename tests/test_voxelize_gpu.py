@@ -92,7 +92,7 @@ def test_pfn_forward_matches_oracle():
         err = (feat - feat_ref).abs().max().item()
         assert err < 2e-4, "PFN feature max abs err %g (training=%s)" % (err, training)   # fp32, tolerance 2e-4 abs
         fb = out["feat_bf16"][:P].float().cpu()
-        assert bool(((fb - feat_ref).abs() <= feat_ref.abs() * 2.0 ** -8 + 1e-6).all())  # bf16 round-to-nearest of the fp32 result
+        assert torch.equal(fb, feat.bfloat16().float())  # bf16 copy == round-to-nearest of the fp32 result
         if training:
             for i in (0, 1):
                 for k in ("running_mean", "running_var"):
