@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the PillarNeXt-B hot path (BASELINE.json metric) on N GPUs of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W                       (N=1)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W                       (N>1, one rank per GPU, NCCL)
+  python bench.py --impl reference ...                                 (the reference's algorithm on host CPU cores)
+
+A "step" = one training pass of the hot path over one batch of synthetic nuScenes-shaped frames:
+reader (voxelize + PillarFeatureNet) -> sparse ResNet-18 -> ASPP -> CenterHead -> CenterPoint loss -> backward
+(-> NCCL gradient all-reduce when N>1) -> AdamW step.  Weights are random-init PillarNeXt-B
+(10,379,782 parameters), data is synthetic (no dataset / checkpoint is reachable), compute is bf16
+tensor-core GEMMs with fp32 accumulation (reader fp32).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec PillarNeXt-B fwd+bwd"
+WORKLOAD = "PillarNeXt-B nuScenes-shape synthetic, bf16, fwd+loss+bwd+AdamW (BASELINE.json configs[1]): " \
+           "%d pts/frame, 0.075 m pillars, 1344^2 BEV, %d frames/GPU/step"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def to_device(ex, dev, non_blocking=False):
+    out = {}
+    for k, v in ex.items():
+        if torch.is_tensor(v):
+            out[k] = v.to(dev, non_blocking=non_blocking)
+        elif isinstance(v, list) and v and torch.is_tensor(v[0]):
+            out[k] = [e.to(dev, non_blocking=non_blocking) for e in v]
+        else:
+            out[k] = v
+    return out
+
+
+def pin(ex):
+    out = {}
+    for k, v in ex.items():
+        if torch.is_tensor(v):
+            out[k] = v.pin_memory()
+        elif isinstance(v, list) and v and torch.is_tensor(v[0]):
+            out[k] = [e.pin_memory() for e in v]
+        else:
+            out[k] = v
+    return out
+
+
+def nbytes(ex):
+    n = 0
+    for v in ex.values():
+        if torch.is_tensor(v):
+            n += v.numel() * v.element_size()
+        elif isinstance(v, list) and v and torch.is_tensor(v[0]):
+            n += sum(e.numel() * e.element_size() for e in v)
+    return n
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step(cfg, sd, ex, frames):
+    """The reference's algorithm (oracle port: fp32 torch CPU restatement of reader / sparse backbone
+    (gather-GEMM form) / ASPP / CenterHead / loss, oracle/pillarnext_oracle.py) fwd+bwd on `frames` frames."""
+    from oracle import pillarnext_oracle as O
+    p = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    preds = O.detector_forward(ex["points"], p, cfg, frames, train=True, backbone="gather")
+    loss, _ = O.center_loss(ex, preds, cfg["weight"], cfg["code_weights"], cfg["with_reg_iou"], cfg["voxel_size"],
+                            cfg["pc_range"], cfg["out_size_factor"])
+    loss.backward()
+    return float(loss)
+
+
+def run_cpu_baseline(cfg, n_points, steps, warmup):
+    from pillarnext_b200 import modules, synth
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in modules.build_pillarnext_b(cfg).state_dict().items()}
+    exs = [synth.make_batch([100 + i], n_points, cfg, kind="lidar", n_boxes=40, sweeps=10) for i in range(2)]
+    for i in range(warmup):
+        cpu_reference_step(cfg, sd, exs[i % 2], 1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_reference_step(cfg, sd, exs[i % 2], 1)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pillarnext_b200 import synth
+    cfg = synth.NUSC
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    fps, spf = run_cpu_baseline(cfg, args.points, steps, warmup)
+    cores = torch.get_num_threads()
+    sample = "%d timed single-frame fwd+loss+bwd steps (%d pts, 1344^2) of the fp32 oracle port, %d torch CPU threads" % (steps, args.points, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": spf * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD % (args.points, 1), "note": "CPU port of the reference algorithm (spconv/torch_scatter absent: oracle restatement)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=6, help="frames per GPU per step (reference: 6/GPU, docs/RUN.md:9)")
+    ap.add_argument("--points", type=int, default=30000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--voxelize-sweep", action="store_true", help="also report voxelizer GB/s over batch sizes")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch.distributed as dist
+    from pillarnext_b200 import modules, ops, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    cfg = synth.NUSC
+    torch.manual_seed(0)
+    model = modules.build_pillarnext_b(cfg).to(dev).train()
+    params = [p for p in model.parameters()]
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.01, fused=True)
+    nb = 4                                                     # distinct synthetic batches, rotated
+    host = [pin(synth.make_batch([rank * 1000 + b * args.frames + f for f in range(args.frames)], args.points, cfg,
+                                 kind="lidar", n_boxes=40, sweeps=10)) for b in range(nb)]
+    resident = [to_device(h, dev) for h in host]
+    flat = None
+
+    def allreduce_grads():
+        nonlocal flat
+        if world == 1:
+            return
+        grads = [p.grad for p in params]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g.copy_(s)
+
+    def step(ex):
+        loss, _ = model(ex)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def timed(n, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(n):
+            if e2e:
+                ex = to_device(host[i % nb], dev, non_blocking=True)   # pinned host -> device inside the timed region
+                loss = step(ex)
+                _ = loss.item()                                        # device -> host read of the step's result
+            else:
+                step(resident[i % nb])
+        t1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return ms.item()
+
+    for i in range(warmup):
+        step(resident[i % nb])
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ops.LAUNCHES
+    ms = timed(args.steps, False)
+    launches = ops.LAUNCHES - l0
+    clocks = sampler.finish() if sampler else None
+    ms_e2e = timed(args.steps, True)
+    frames_total = args.frames * world * args.steps
+    value = frames_total / (ms / 1e3)
+    e2e = frames_total / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM + weight-gradient GEMM), one probe step with
+    #      CUDA events around every launch on the launching stream
+    ops.PROFILE = []
+    step(resident[0])
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    agg = {}
+    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        per = {}
+        for kind, flops, nb_, a, b, tag in prof:
+            d = per.setdefault(kind + ":" + tag, [0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+            d[2] += flops
+        rows = sorted(((v[1], k, v[0], v[2]) for k, v in per.items()), reverse=True)
+        with open(os.path.join(ROOT, "gpurun_out", "probe_gemm_calls.txt"), "w") as fh:
+            fh.write("# ms_total  calls  TFLOP/s  kind:shape   (one probe step, CUDA events per launch)\n")
+            for t, k, c, f in rows:
+                fh.write("%9.3f %4d %8.1f  %s\n" % (t, c, f / (t * 1e-3) / 1e12 if t > 0 else 0, k))
+    for kind, flops, nb_, a, b, _tag in prof:
+        d = agg.setdefault(kind, [0.0, 0.0, 0])
+        d[0] += flops
+        d[1] += a.elapsed_time(b)
+        d[2] += 1
+    pk = peaks()
+    gemm_ms = sum(v[1] for v in agg.values())
+    gemm_fl = sum(v[0] for v in agg.values())
+    ig = agg.get("igemm", [0.0, 1e-9, 0])
+    roof = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 gather implicit GEMM, fwd+dgrad)",
+            "achieved": ig[0] / (ig[1] * 1e-3) / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+            "frac": ig[0] / (ig[1] * 1e-3) / 1e12 / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+            "launches": ig[2], "flops_per_step": ig[0], "share_of_step": ig[1] / (ms / args.steps),
+            "wgrad": {"achieved": agg["wgrad"][0] / (agg["wgrad"][1] * 1e-3) / 1e12, "launches": agg["wgrad"][2],
+                      "share_of_step": agg["wgrad"][1] / (ms / args.steps)} if "wgrad" in agg else None,
+            "note": "executed MMA flops (zero-filled absent neighbours included); per-launch CUDA events in a probe step"}
+
+    # ---- voxelizer HBM roofline (second half of the BASELINE metric): many frames per launch so bytes >= 64 MB
+    vox = None
+    if rank == 0:
+        vox = voxelize_roofline(dev, cfg, pk)
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            torch.cuda.synchronize()
+            fps, spf = run_cpu_baseline(cfg, args.points, 1, 0)
+            cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": "1 single-frame fwd+loss+bwd step (%d pts, 1344^2 grid) of the fp32 oracle port on the host CPU (%.1f s)" % (args.points, spf)}
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD % (args.points, args.frames), "global_batch": args.frames * world,
+                           "parallelism": "dp%d (frames sharded, NCCL gradient all-reduce, local BatchNorm)" % world,
+                           "l2": "per-step activation working set (GBs) >> 126 MB L2; 4 distinct input batches rotated",
+                           "timed_step": "reader+backbone+neck+head fwd, loss, bwd, grad all-reduce (N>1), AdamW"},
+                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": nbytes(host[0]), "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "voxelize": vox, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def voxelize_roofline(dev, cfg, pk):
+    """Index-generation voxelizer (pnx_voxelize: V1-V3) on a large multi-frame batch.
+    Algorithmic bytes: 24*N + 4*Nv + 12*P."""
+    from pillarnext_b200 import ops, synth
+    frames, n = 64, 30000
+    pts = synth.collate_points([synth.make_frame(5000 + i, n, cfg, "lidar", sweeps=10) for i in range(frames)]).to(dev)
+    out = {}
+    v = ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"])
+    P, Nv = v.sync_counts()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"])
+    torch.cuda.synchronize()
+    reps = 10
+    t0.record()
+    for _ in range(reps):
+        ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"])
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / reps
+    alg = 24.0 * pts.shape[0] + 4.0 * Nv + 12.0 * P
+    out = {"bound": "hbm", "frames_per_launch": frames, "points": int(pts.shape[0]), "pillars": P, "algorithmic_bytes": alg,
+           "ms": ms, "achieved": alg / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm"],
+           "peak_source": pk["src"], "note": "11 kernels + 3 memsets per call incl. bitmap zeroing/scan over %d grid cells" % (frames * 1344 * 1344)}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,19 @@ import torch.nn.functional as F
 
 
 # ----------------------------------------------------------------------------- helpers
+# QUANT=True makes the restatement "bf16-faithful": weights and every stored activation are rounded to bf16
+# (round-to-nearest-even, straight-through for autograd) at exactly the points where the CUDA product stores
+# bf16, all arithmetic staying fp32.  The product must match THIS variant tightly (only accumulation order
+# differs) and the plain fp32 variant within bf16 noise.
+QUANT = False
+
+
+def q(x):
+    if not QUANT:
+        return x
+    return x + (x.to(torch.bfloat16).to(torch.float32) - x).detach()
+
+
 def grid_size_xy(voxel_size, pc_range):
     """pillar_encoder.py:87-89 -- float64 numpy, round to int64. Returns (Gx, Gy, Gz)."""
     vs = np.array(voxel_size, dtype=np.float64)
@@ -196,8 +209,8 @@ def _gather_conv(feat, in_coords, in_shape, out_coords, w, stride, pad=1):
             src[ok] = grid[ob[ok], iy[ok], ix[ok]]
             sel = src >= 0
             if sel.any():
-                out[sel] += feat[src[sel]] @ w[:, ky, kx, :].t()
-    return out
+                out[sel] += feat[src[sel]] @ q(w[:, ky, kx, :]).t()
+    return q(out)
 
 
 def _dilate_sites(coords, in_shape, stride):
@@ -216,23 +229,23 @@ def sparse_resnet_gather(feat, coords, grid_hw, batch_size, sd, strides=(1, 2, 2
     Returns (features [N4,256], coords [N4,3] (b,y,x), (B,H4,W4))."""
     c = coords.long()
     shape = (batch_size, int(grid_hw[0]), int(grid_hw[1]))
-    x = feat
+    x = q(feat)
     for s in range(4):
         p = "%sblocks.%d." % (prefix, s)
         oc, oshape = _dilate_sites(c, shape, strides[s])
         x = _gather_conv(x, c, shape, oc, sd[p + "0.conv.weight"], strides[s])
         c, shape = oc, oshape
-        x = F.relu(_bn(x, sd, p + "0.norm.", 1e-3, [0], 1, train, stats, 0.01))
+        x = q(F.relu(_bn(x, sd, p + "0.norm.", 1e-3, [0], 1, train, stats, 0.01)))
         for j in (1, 2):
-            q = "%s%d." % (p, j)
+            bq = "%s%d." % (p, j)
             idt = x
-            o = _gather_conv(x, c, shape, c, sd[q + "block1.conv.weight"], 1)
-            o = F.relu(_bn(o, sd, q + "block1.norm.", 1e-3, [0], 1, train, stats, 0.01))
-            o = _gather_conv(o, c, shape, c, sd[q + "conv2.weight"], 1)
-            o = _bn(o, sd, q + "norm2.", 1e-3, [0], 1, train, stats, 0.01)
-            x = F.relu(o + idt)
-    x = x @ sd[prefix + "mapping.0.weight"][:, 0, 0, :].t()
-    x = F.relu(_bn(x, sd, prefix + "mapping.1.", 1e-3, [0], 1, train, stats, 0.01))
+            o = _gather_conv(x, c, shape, c, sd[bq + "block1.conv.weight"], 1)
+            o = q(F.relu(_bn(o, sd, bq + "block1.norm.", 1e-3, [0], 1, train, stats, 0.01)))
+            o = _gather_conv(o, c, shape, c, sd[bq + "conv2.weight"], 1)
+            o = _bn(o, sd, bq + "norm2.", 1e-3, [0], 1, train, stats, 0.01)
+            x = q(F.relu(o + idt))
+    x = q(x @ q(sd[prefix + "mapping.0.weight"][:, 0, 0, :]).t())
+    x = q(F.relu(_bn(x, sd, prefix + "mapping.1.", 1e-3, [0], 1, train, stats, 0.01)))
     return x, c, shape
 
 
@@ -247,9 +260,9 @@ def densify(feat, coords, shape):
 # ----------------------------------------------------------------------------- N1 neck
 def _convblock2d(x, sd, pfx, train, stats, padding):
     """ConvBlock: conv(bias=False) + BatchNorm2d(eps 1e-5, mom 0.1) + ReLU, conv.py:14-34."""
-    x = F.conv2d(x, sd[pfx + "conv.conv.weight"], padding=padding)
+    x = q(F.conv2d(x, q(sd[pfx + "conv.conv.weight"]), padding=padding))
     x = _bn(x, sd, pfx + "norm.", 1e-5, [0, 2, 3], 1, train, stats, 0.1)
-    return F.relu(x)
+    return q(F.relu(x))
 
 
 def aspp_forward(x, sd, prefix="neck.", train=True, stats=None):
@@ -257,11 +270,11 @@ def aspp_forward(x, sd, prefix="neck.", train=True, stats=None):
     idt = x
     o = _convblock2d(x, sd, prefix + "pre_conv.block1.", train, stats, 1)    # conv.py:44-51
     o = _convblock2d(o, sd, prefix + "pre_conv.block2.", train, stats, 1)
-    x = F.relu(o + idt)
-    w = sd[prefix + "weight"]
-    br = [x, F.conv2d(x, sd[prefix + "conv1x1.weight"])]
+    x = q(F.relu(o + idt))
+    w = q(sd[prefix + "weight"])
+    br = [x, q(F.conv2d(x, q(sd[prefix + "conv1x1.weight"])))]
     for d in (1, 6, 12, 18):
-        br.append(F.conv2d(x, w, padding=d, dilation=d))                     # :22-29 shared weight
+        br.append(q(F.conv2d(x, w, padding=d, dilation=d)))                  # :22-29 shared weight
     x = torch.cat(br, dim=1)
     return _convblock2d(x, sd, prefix + "post_conv.", train, stats, 0)       # :30-31
 
@@ -271,20 +284,20 @@ def centerhead_forward(x, sd, tasks, common_heads, prefix="head.", train=True, s
     """CenterHead.forward / SepHead.forward, centerhead.py:128-136, 53-59.
     tasks: list of class-name lists; common_heads: ordered dict name -> (channels, num_conv)."""
     p = prefix + "shared_conv."
-    x = F.conv2d(x, sd[p + "0.weight"], sd[p + "0.bias"], padding=1)         # :108-114
-    x = F.relu(_bn(x, sd, p + "1.", 1e-5, [0, 2, 3], 1, train, stats, 0.1))
+    x = q(F.conv2d(x, q(sd[p + "0.weight"]), sd[p + "0.bias"], padding=1))   # :108-114
+    x = q(F.relu(_bn(x, sd, p + "1.", 1e-5, [0, 2, 3], 1, train, stats, 0.1)))
     rets = []
     for t, names in enumerate(tasks):
-        q = "%stasks.%d." % (prefix, t)
-        y = F.conv_transpose2d(x, sd[q + "deblock.conv.conv.weight"], stride=2)   # :26-27
-        y = F.relu(_bn(y, sd, q + "deblock.norm.", 1e-5, [0, 2, 3], 1, train, stats, 0.1))
+        tq = "%stasks.%d." % (prefix, t)
+        y = q(F.conv_transpose2d(x, q(sd[tq + "deblock.conv.conv.weight"]), stride=2))   # :26-27
+        y = q(F.relu(_bn(y, sd, tq + "deblock.norm.", 1e-5, [0, 2, 3], 1, train, stats, 0.1)))
         heads = list(common_heads.keys()) + ["hm"]                           # :121-122 order
         ret = {}
         for h in heads:
-            r = q + h + "."
-            z = F.conv2d(y, sd[r + "0.weight"], sd[r + "0.bias"], padding=1)       # :36-38
-            z = F.relu(_bn(z, sd, r + "1.", 1e-5, [0, 2, 3], 1, train, stats, 0.1))
-            ret[h] = F.conv2d(z, sd[r + "3.weight"], sd[r + "3.bias"], padding=1)  # :44-46
+            r = tq + h + "."
+            z = q(F.conv2d(y, q(sd[r + "0.weight"]), sd[r + "0.bias"], padding=1))   # :36-38
+            z = q(F.relu(_bn(z, sd, r + "1.", 1e-5, [0, 2, 3], 1, train, stats, 0.1)))
+            ret[h] = F.conv2d(z, q(sd[r + "3.weight"]), sd[r + "3.bias"], padding=1)  # :44-46 (fp32 output)
         rets.append(ret)
     return rets
 

@@ -3,6 +3,8 @@ backward call libpnx kernels (pillarnext_b200/ops.py).  Activations between ops 
 [rows, channels] (rows = active sites or channels-last pixels); parameters stay fp32 in the reference's
 own layouts (state-dict compatible) and are repacked to the kernels' bf16 [tap, Cout, Cin] layout on the fly.
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -63,11 +65,13 @@ def packed(w, layout, which, flip=False):
     key = (id(w), which, flip, layout.kind)
     ent = _pack_cache.get(key)
     ver = w._version
-    if ent is not None and ent[0] == ver and ent[1] == w.data_ptr():
+    if ent is not None and ent[0] == ver and ent[1]() is w and ent[3] == w.data_ptr():
         return ent[2]
     with torch.no_grad():
         p = layout.pack_fwd(w) if which == "fwd" else layout.pack_dgrad(w, flip)
-    _pack_cache[key] = (ver, w.data_ptr(), p)
+    if len(_pack_cache) > 4096:      # ids of dead tensors: drop everything rather than grow without bound
+        _pack_cache.clear()
+    _pack_cache[key] = (ver, weakref.ref(w), p, w.data_ptr())
     return p
 
 
@@ -245,28 +249,6 @@ def bn_act(x_raw, stats, bn, relu=True, residual=None, count=None):
     return BNActFn.apply(x_raw, stats, bn.weight, bn.bias, residual, bn, relu, x_raw.shape[0] if count is None else count)
 
 
-class AddReluIntoFn(torch.autograd.Function):
-    """cat_buf[:, :C] = relu(a + b) (BasicBlock tail, conv.py:48-50) written straight into slot 0 of the
-    ASPP concat buffer; returns the buffer."""
-
-    @staticmethod
-    def forward(ctx, a, b, cat_buf):
-        M, C = a.shape
-        ops.add_relu(a, b, M, C, cat_buf[:, :C])
-        ctx.save_for_backward(cat_buf)
-        ctx.C = C
-        ctx.mark_dirty(cat_buf)
-        return cat_buf
-
-    @staticmethod
-    def backward(ctx, dcat):
-        (cat_buf,) = ctx.saved_tensors
-        M, C = cat_buf.shape[0], ctx.C
-        g = torch.empty(M, C, dtype=torch.bfloat16, device=dcat.device)
-        ops.relu_bwd(dcat[:, :C], cat_buf[:, :C], M, C, g)
-        return g, g, None
-
-
 # ------------------------------------------------------------------------------------------- dense()
 class DensifyFn(torch.autograd.Function):
     """SparseConvTensor.dense() (sparse_resnet.py:68) into channels-last rows [B*H*W, C]; backward gathers."""
@@ -290,24 +272,26 @@ class DensifyFn(torch.autograd.Function):
 
 # ------------------------------------------------------------------------------------------- ASPP branches
 class ASPPBranchesFn(torch.autograd.Function):
-    """cat(x, conv1x1(x), W(*)x d=1, d=6, d=12, d=18) (aspp.py:21-31): five GEMMs writing the column slots of one
-    [M, 6C] buffer whose slot 0 already holds x.  Backward: five data-gradient GEMMs chained through the
-    epilogue addend, weight gradients of the four dilations accumulated into the one shared tensor."""
+    """x = relu(o + idt) (BasicBlock tail, conv.py:48-50) written straight into slot 0 of the concat buffer, then
+    cat(x, conv1x1(x), W(*)x d=1, d=6, d=12, d=18) (aspp.py:21-31): five GEMMs writing the other column slots of
+    the one [M, 6C] buffer.  Backward: five data-gradient GEMMs chained through the epilogue addend, weight
+    gradients of the four dilations accumulated into the one shared tensor, then the ReLU mask."""
     DILS = (1, 6, 12, 18)
 
     @staticmethod
-    def forward(ctx, cat_buf, w1x1, wshared, B, H, W):
-        M, C6 = cat_buf.shape
-        C = C6 // 6
+    def forward(ctx, o, idt, w1x1, wshared, B, H, W):
+        M, C = o.shape
+        C6 = 6 * C
+        cat_buf = torch.empty(M, C6, dtype=torch.bfloat16, device=o.device)
         l = WLayout("dense")
         x = cat_buf[:, :C]
+        ops.add_relu(o, idt, M, C, x)
         ops.igemm(x, M, packed(w1x1, l, "fwd"), 1, C, C, cat_buf[:, C:2 * C], lda=C6, ldc=C6)
         wp = packed(wshared, l, "fwd")
         for j, d in enumerate(ASPPBranchesFn.DILS):
             ops.igemm(x, M, wp, 9, C, C, cat_buf[:, (2 + j) * C:(3 + j) * C], lda=C6, ldc=C6, dense=(H, W, H, W, 3, 1, d, d))
         ctx.save_for_backward(cat_buf, w1x1, wshared)
         ctx.geo = (B, H, W, C)
-        ctx.mark_dirty(cat_buf)
         return cat_buf
 
     @staticmethod
@@ -331,9 +315,9 @@ class ASPPBranchesFn(torch.autograd.Function):
         gs = torch.zeros(9, C, C, dtype=torch.float32, device=dcat.device)
         for j, d in enumerate(ASPPBranchesFn.DILS):
             ops.wgrad(dcat[:, (2 + j) * C:(3 + j) * C], C, False, x, C, True, M, 9, gs, dense=(H, W, H, W, 3, 1, d, d))
-        dbuf = torch.empty_like(dcat)          # only slot 0 is consumed upstream (AddReluIntoFn.backward)
-        dbuf[:, :C] = dx
-        return dbuf, l.unpack_grad(g1, tuple(w1x1.shape)), l.unpack_grad(gs, tuple(wshared.shape)), None, None, None
+        g = torch.empty(M, C, dtype=torch.bfloat16, device=dcat.device)
+        ops.relu_bwd(dx, x, M, C, g)
+        return g, g, l.unpack_grad(g1, tuple(w1x1.shape)), l.unpack_grad(gs, tuple(wshared.shape)), None, None, None
 
 
 # ------------------------------------------------------------------------------------------- reader

@@ -291,9 +291,7 @@ class ASPPNeck(nn.Module):
         C = self.in_channels
         o = self.pre_conv.block1.run(rows, B, H, W)
         o = self.pre_conv.block2.run(o, B, H, W)
-        cat = torch.empty(rows.shape[0], 6 * C, dtype=torch.bfloat16, device=rows.device)
-        cat = Fn.AddReluIntoFn.apply(o, rows, cat)
-        cat = Fn.ASPPBranchesFn.apply(cat, self.conv1x1.weight, self.weight, B, H, W)
+        cat = Fn.ASPPBranchesFn.apply(o, rows, self.conv1x1.weight, self.weight, B, H, W)
         y = self.post_conv.run(cat, B, H, W)
         return y.view(B, H, W, C).permute(0, 3, 1, 2)
 

@@ -7,6 +7,31 @@ import torch
 
 from ._lib import check, lib, ptr, sm_count, stream
 
+# ---- instrumentation used by bench.py: kernel-launch counter and optional per-call CUDA-event timing
+LAUNCHES = 0            # number of libpnx kernels launched so far (each wrapper adds its own kernel count)
+PROFILE = None          # when a list: (kind, flops, bytes, start_event, end_event) per tensor-core GEMM call
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _Timed:
+    def __init__(self, kind, flops, nbytes, tag=""):
+        self.rec = None
+        if PROFILE is not None:
+            self.rec = [kind, flops, nbytes, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), tag]
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.rec[3].record()
+
+    def __exit__(self, *a):
+        if self.rec is not None:
+            self.rec[4].record()
+            PROFILE.append(tuple(self.rec))
+
 
 # --------------------------------------------------------------------------------- geometry
 def grid_size_xy(voxel_size, pc_range):
@@ -65,6 +90,7 @@ def voxelize(points, batch, voxel_size, pc_range):
     bucket_tmp = torch.empty(max(n, 1), **i32)
     v.bucket_pts = torch.empty(max(n, 1), **i32)
     v.counts = torch.empty(2, **i32)
+    _count(11 if n > 0 else 7)
     check(L.pnx_voxelize(ptr(points), n, batch, v.min_x, v.min_y, v.vs_x, v.vs_y, gx, gy, ptr(v.bitmap),
                          ptr(v.word_prefix), ptr(scratch), ptr(cell), ptr(v.pillar_of_point), ptr(v.coords), cap_p,
                          ptr(bucket_cnt), ptr(v.bucket_off), ptr(bucket_tmp), ptr(v.bucket_pts), ptr(v.counts),
@@ -80,6 +106,7 @@ def bn_finalize(stats, channels, count_ptr, count_mult, gamma, beta, eps, moment
     shift = torch.empty_like(scale)
     mean = torch.empty_like(scale) if want_saved else None
     invstd = torch.empty_like(scale) if want_saved else None
+    _count(1)
     check(lib().pnx_bn_finalize(ptr(stats), channels, ptr(count_ptr) if count_ptr is not None else None,
                                 int(count_mult), ptr(gamma), ptr(beta), float(eps), float(momentum),
                                 ptr(running_mean) if running_mean is not None else None,
@@ -93,6 +120,7 @@ def bn_eval_affine(gamma, beta, rm, rv, eps):
     c = gamma.shape[0]
     scale = torch.empty(c, dtype=torch.float32, device=gamma.device)
     shift = torch.empty_like(scale)
+    _count(1)
     check(lib().pnx_bn_eval_affine(c, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), float(eps), ptr(scale), ptr(shift),
                                    stream()))
     return scale, shift
@@ -115,6 +143,7 @@ def pfn_forward(v, w0, bn0, w1, bn1, training, eps=1e-3, momentum=0.01, want_f32
     s0, s1 = stats[:64], stats[64:]
     nv_ptr = v.counts[1:2]
     tr = 1 if training else 0
+    _count(5)
     check(L.pnx_pfn_mean(ptr(v.points), ptr(v.bucket_off), ptr(v.bucket_pts), ptr(v.counts), v.cap_p, ptr(mean),
                          stream()))
     check(L.pnx_pfn_lin0(ptr(v.points), ptr(v.bucket_pts), ptr(v.pillar_of_point), ptr(v.coords), ptr(mean),
@@ -159,6 +188,7 @@ def pfn_backward(v, fwd, dfeat, w1, gamma0, gamma1):
     red = torch.zeros(64 + 128, dtype=torch.float64, device=dev)
     dW0 = torch.zeros(32, 10, dtype=torch.float32, device=dev)
     dW1 = torch.zeros(64, 64, dtype=torch.float32, device=dev)
+    _count(4)
     check(lib().pnx_pfn_backward(ptr(v.points), ptr(v.bucket_off), ptr(v.bucket_pts), ptr(v.pillar_of_point),
                                  ptr(v.coords), ptr(v.counts), v.n, v.cap_p, v.min_x, v.min_y, v.vs_x, v.vs_y,
                                  ptr(fwd["mean"]), ptr(fwd["y0"]), ptr(fwd["y1"]), ptr(fwd["x0max"]), ptr(fwd["feat"]),
@@ -181,6 +211,7 @@ def _scan_bitmap(bm):
     prefix = torch.empty(words + 1, dtype=torch.int32, device=bm.device)
     scratch = torch.empty(words // 2048 + 4, dtype=torch.int32, device=bm.device)
     count = torch.empty(1, dtype=torch.int32, device=bm.device)
+    _count(3)
     check(lib().pnx_scan_u32(ptr(bm), words, 1, ptr(prefix), ptr(scratch), ptr(count), stream()))
     return prefix, count
 
@@ -197,6 +228,7 @@ def level_dilate(src, stride):
     L = lib()
     uo, vo = L.pnx_sites_out_dim(src.U, stride), L.pnx_sites_out_dim(src.V, stride)
     bm = torch.empty(src.batch * uo * ((vo + 31) // 32), dtype=torch.int32, device=src.bm.device)
+    _count(1)
     check(L.pnx_sites_dilate(ptr(src.bm), src.batch, src.U, src.V, stride, ptr(bm), stream()))
     prefix, count = _scan_bitmap(bm)
     return level_from_bitmap(bm, prefix, count, src.batch, uo, vo)
@@ -205,12 +237,14 @@ def level_dilate(src, stride):
 def level_coords(lv, n):
     lv.n = n
     lv.coords = torch.empty(max(n, 1), 3, dtype=torch.int32, device=lv.bm.device)
+    _count(1)
     check(lib().pnx_sites_coords(ptr(lv.bm), ptr(lv.prefix), lv.batch, lv.U, lv.V, ptr(lv.coords), n, stream()))
     return lv.coords
 
 
 def nbr_table(dst, src, stride, transposed):
     nbr = torch.empty(max(dst.n, 1), 9, dtype=torch.int32, device=dst.bm.device)
+    _count(1)
     check(lib().pnx_nbr_table(ptr(dst.coords), ptr(dst.count), dst.n, ptr(src.bm), ptr(src.prefix), src.batch, src.U,
                               src.V, stride, 1 if transposed else 0, ptr(nbr), stream()))
     return nbr
@@ -220,6 +254,7 @@ def scatter_dense(feat, lv, channels, canvas=None, gather=False):
     """feat [n,C] bf16 <-> canvas [B, V(y), U(x), C] bf16."""
     if canvas is None:
         canvas = torch.zeros(lv.batch, lv.V, lv.U, channels, dtype=torch.bfloat16, device=feat.device)
+    _count(1)
     check(lib().pnx_scatter_dense(ptr(feat), ptr(lv.coords), ptr(lv.count), lv.n, channels, lv.batch, lv.U, lv.V,
                                   ptr(canvas), 1 if gather else 0, stream()))
     return canvas
@@ -246,7 +281,10 @@ def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None,
     out_fp32 = 1 if out.dtype == torch.float32 else 0
     assert out.dtype in (torch.float32, torch.bfloat16)
     sC = stats.numel() // 2 if stats is not None else 0
-    check(lib().pnx_igemm(ptr(A), lda, M, taps, cin, ptr(w_packed), cout, bn, ptr(nbr) if nbr is not None else None,
+    _count(1)
+    with _Timed("igemm", 2.0 * M * taps * cin * cout, 2.0 * M * (cin * min(taps, 2) + cout) + 2.0 * taps * cin * cout,
+                "M%d_T%d_K%d_N%d_bn%d%s" % (M, taps, cin, cout, bn, "_tbl" if nbr is not None else ("_dense" if dense else ""))):
+      check(lib().pnx_igemm(ptr(A), lda, M, taps, cin, ptr(w_packed), cout, bn, ptr(nbr) if nbr is not None else None,
                           1 if dense else 0, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], ptr(out), ldc, out_fp32,
                           ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None, sC,
                           stats_mod or (sC if sC else 1), 1 if shuffle else 0, 1 if relu else 0,
@@ -260,7 +298,10 @@ def wgrad(X, x_channels, gather_x, Y, y_channels, gather_y, M, taps, dW, *, nbr=
     assert X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16 and dW.dtype == torch.float32
     assert tuple(dW.shape) == (taps, x_channels, y_channels) and dW.is_contiguous()
     d = dense or (0, 0, 0, 0, 1, 1, 1, 0)
-    check(lib().pnx_wgrad(ptr(X), X.stride(0), x_channels, 1 if gather_x else 0, ptr(Y), Y.stride(0), y_channels,
+    _count(1)
+    with _Timed("wgrad", 2.0 * M * taps * x_channels * y_channels, 2.0 * M * taps * (x_channels + y_channels),
+                "M%d_T%d_X%d_Y%d" % (M, taps, x_channels, y_channels)):
+      check(lib().pnx_wgrad(ptr(X), X.stride(0), x_channels, 1 if gather_x else 0, ptr(Y), Y.stride(0), y_channels,
                           1 if gather_y else 0, M, taps, ptr(nbr) if nbr is not None else None,
                           1 if (dense and not shuffle) else 0, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7],
                           1 if shuffle else 0, ptr(dW), sm_count(), stream()))
@@ -269,6 +310,7 @@ def wgrad(X, x_channels, gather_x, Y, y_channels, gather_y, M, taps, dW, *, nbr=
 
 # --------------------------------------------------------------------------------- row-wise kernels
 def bn_apply(x, M, C, scale, shift, y, res=None, relu=True):
+    _count(1)
     check(lib().pnx_bn_apply(ptr(x), x.stride(0), M, C, ptr(scale), ptr(shift), ptr(res) if res is not None else None,
                              res.stride(0) if res is not None else 8, 1 if relu else 0, ptr(y), y.stride(0), stream()))
     return y
@@ -279,6 +321,7 @@ def bn_bwd(dy, y, x, M, C, mean, invstd, gamma, count, relu, dx, dres=None, dres
     red = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
     L = lib()
     yy = y if y is not None else dy
+    _count(2)
     check(L.pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), ptr(yy), yy.stride(0), ptr(x), x.stride(0), M, C, ptr(mean),
                               ptr(invstd), 1 if relu else 0, ptr(red), stream()))
     check(L.pnx_bn_bwd_apply(ptr(dy), dy.stride(0), ptr(yy), yy.stride(0), ptr(x), x.stride(0), M, C, ptr(mean),
@@ -289,16 +332,19 @@ def bn_bwd(dy, y, x, M, C, mean, invstd, gamma, count, relu, dx, dres=None, dres
 
 
 def add_rows(a, b, M, C):
+    _count(1)
     check(lib().pnx_add_rows(ptr(a), a.stride(0), ptr(b), b.stride(0), M, C, stream()))
     return a
 
 
 def add_relu(a, b, M, C, y):
+    _count(1)
     check(lib().pnx_add_relu(ptr(a), a.stride(0), ptr(b), b.stride(0), M, C, ptr(y), y.stride(0), stream()))
     return y
 
 
 def relu_bwd(dy, y, M, C, g, accumulate=False):
+    _count(1)
     check(lib().pnx_relu_bwd(ptr(dy), dy.stride(0), ptr(y), y.stride(0), M, C, ptr(g), g.stride(0),
                              1 if accumulate else 0, stream()))
     return g
