@@ -146,15 +146,14 @@ int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void
               long long ld_add, int sm_count, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- tcgen05 weight gradient
- * dW[t, x, y] += sum_m X[ix(m,t), x] * Y[iy(m,t), y]   (fp32, red.global.add; zero dW first)
- * Exactly one of X / Y may be read through the neighbour map (gather_x / gather_y): the layer input is
- * the gathered operand, the output gradient the direct one (swapped for ConvTranspose2d, shuffle=1).
- * x_channels: 64 or a multiple of 128; y_channels: multiple of 64, <= 256.  Backward of the layers
+ * dW[t, x, y] += sum_m X[m, x] * Y[g(m,t), y]   (fp32, red.global.add; zero dW first)
+ * X = direct operand (output gradient; layer input for ConvTranspose2d, shuffle=1), Y = operand read through
+ * the neighbour map: nbr[m*taps+t] if nbr != NULL, else the dense geometry (as pnx_igemm), else row m (taps==1,
+ * gathered=0).  x_channels: 64 or a multiple of 128; y_channels: multiple of 64.  Backward of the layers
  * pnx_igemm replaces (autograd in the reference: trainer/trainer/trainer.py:94-108). */
-int pnx_wgrad(const void* X, long long ldx, int x_channels, int gather_x, const void* Y, long long ldy,
-              int y_channels, int gather_y, int M, int taps, const int* nbr, int dense, int Hout, int Wout,
-              int Hin, int Win, int kw, int mul, int dil, int pad, int shuffle, float* dW, int sm_count,
-              cudaStream_t stream);
+int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long long ldy, int y_channels,
+              int gathered, int M, int taps, const int* nbr, int Hout, int Wout, int Hin, int Win, int kw,
+              int mul, int dil, int pad, int shuffle, float* dW, int sm_count, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- row-wise bf16 kernels
  * y = relu?(x*scale + shift (+ res))  -- BatchNorm apply (+residual)(+ReLU): sparse_conv.py:33-39,55-63,

@@ -39,7 +39,7 @@ _SIGS = {
     "pnx_nbr_table": [P, P, I, P, P, I, I, I, I, I, P, P],
     "pnx_scatter_dense": [P, P, P, I, I, I, I, I, P, I, P],
     "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, P, L, I, P],
-    "pnx_wgrad": [P, L, I, I, P, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, I, P, I, P],
+    "pnx_wgrad": [P, L, I, P, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, P, I, P],
     "pnx_bn_apply": [P, L, L, I, P, P, P, L, I, P, L, P],
     "pnx_bn_bwd_reduce": [P, L, P, L, P, L, L, I, P, P, I, P, P],
     "pnx_bn_bwd_apply": [P, L, P, L, P, L, L, I, P, P, P, P, ctypes.c_double, I, P, L, P, L, I, P],

@@ -99,6 +99,8 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long 
 }
 
 // dx = scale * (g - sum_g/n - xhat * sum_gx/n) ; optional dres (+)= g
+// Per-channel coefficients are staged once per block in shared memory: [A = gamma*invstd | B = sum_g/n |
+// Cc = sum_gx/n | mean | invstd] so the row loop is pure 128-bit streaming.
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
                                     const __nv_bfloat16* __restrict__ y, long long ldy,
                                     const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
@@ -106,6 +108,16 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long l
                                     const float* __restrict__ gamma, const double* __restrict__ red, float inv_n,
                                     int relu, __nv_bfloat16* __restrict__ dx, long long lddx,
                                     __nv_bfloat16* __restrict__ dres, long long lddres, int dres_accumulate) {
+  extern __shared__ float coef[];  // [5][C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float is = invstd[c];
+    coef[c] = gamma[c] * is;
+    coef[C + c] = (float)red[c] * inv_n;
+    coef[2 * C + c] = (float)red[C + c] * inv_n;
+    coef[3 * C + c] = mean[c];
+    coef[4 * C + c] = is;
+  }
+  __syncthreads();
   const int cg = C >> 3;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = M * cg;
@@ -121,9 +133,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long l
       const int c = c0 + k;
       const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
       g[k] = gg;
-      const float is = invstd[c];
-      const float xh = (xx[k] - mean[c]) * is;
-      o[k] = gamma[c] * is * (gg - (float)red[c] * inv_n - xh * (float)red[C + c] * inv_n);
+      const float xh = (xx[k] - coef[3 * C + c]) * coef[4 * C + c];
+      o[k] = coef[c] * (gg - coef[C + c] - xh * coef[2 * C + c]);
     }
     *reinterpret_cast<uint4*>(dx + m * lddx + c0) = pack8(o);
     if (dres) {
@@ -240,7 +251,8 @@ extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, l
                                 cudaStream_t stream) {
   PNX_CHECK_ARG(C % 8 == 0, "C % 8");
   if (M == 0) return PNX_OK;
-  bn_bwd_apply_kernel<<<ew_blocks(M * (C / 8), 256), 256, 0, stream>>>(
+  PNX_CHECK_ARG(C <= 2048, "C <= 2048");
+  bn_bwd_apply_kernel<<<ew_blocks(M * (C / 8), 256), 256, 5 * C * sizeof(float), stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M, C, mean, invstd,
       gamma, red, (float)(1.0 / count), relu, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddres,
       dres_accumulate);

@@ -36,16 +36,18 @@ struct IgemmParams {
   long long ld_add;
 };
 
-constexpr int kThreads = 320;
+// threads = TMA warp + MMA warp + PW gather-producer warps + 4 epilogue warps.  PW = 8 for the A-bound shapes
+// (small N: two producer warps per scheduler hide the gather latency), PW = 4 for the epilogue-heavy ones (wide N,
+// short K: the epilogue warps need the issue slots and the registers).
 constexpr uint32_t kABytes = 128 * 128;
 constexpr int kLag = 2;
 
 template <int BN>
 struct Cfg {
   static constexpr uint32_t kBBytes = BN * 128;
-  static constexpr int kStagesRaw = (196 * 1024) / (int)(kABytes + kBBytes);
+  static constexpr int kStagesRaw = (192 * 1024) / (int)(kABytes + kBBytes);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + 128 * 9 * 4 + 256;
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + 128 * 9 * 8 + 256 + 4 * 4096 + 4 * 2 * BN * 4;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
@@ -67,9 +69,11 @@ __device__ __forceinline__ float colsum32(float (&v)[32]) {
   return v[0];
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, IgemmParams p) {
+template <int BN, int PW>
+__global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, IgemmParams p) {
   using C = Cfg<BN>;
+  constexpr int kProducerWarps = PW;
+  constexpr int kProducerThreads = PW * 32;
   constexpr int kStages = C::kStages;
   constexpr uint32_t kBBytes = C::kBBytes;
   constexpr int kColBlk = BN >= 32 ? 32 : 16;
@@ -79,12 +83,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)kStages * kABytes;
-  int* s_idx = reinterpret_cast<int*>(sB + (size_t)kStages * kBBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_idx + 128 * 9);
+  long long* s_off = reinterpret_cast<long long*>(sB + (size_t)kStages * kBBytes);  // [128 rows][T] element offsets, -1 = absent
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_off + 128 * 9);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [4 warps][4 KB] store staging slabs
+  float* s_stat = s_tr + 4096;                                                        // [4 warps][2][BN] per-channel sum / sumsq
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   if (warp == 0 && pnx::elect_one()) {
     pnx::tma_prefetch_desc(&wmap);
     for (int s = 0; s < kStages; ++s) {
-      pnx::mbar_init(&full[s], 1 + 4);
+      pnx::mbar_init(&full[s], 1 + kProducerWarps);
       pnx::mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -158,46 +164,57 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp < 6) {
-    // ---------------------------------------------------------------- A gather producers (128 threads)
+  } else if (warp < 2 + kProducerWarps) {
+    // ---------------------------------------------------------------- A gather producers
+    // Row offsets (row * lda, 64-bit) are computed once per tile into shared memory so the per-stage loop is one
+    // add + cp.async per 16 bytes.
     const int ptid = threadIdx.x - 64;
     const int sub_row = ptid >> 3, chunk = ptid & 7;
+    const int hw = p.Hout * p.Wout;
+    const float inv_hw = 1.0f / (float)hw, inv_w = 1.0f / (float)p.Wout;
     int stage = 0, arr_stage = 0, pending = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      named_bar_sync(1, 128);
-      {
-        const int m = tile * 128 + ptid;
-        int* row = s_idx + ptid * 9;
-        if (m >= p.M) {
-          for (int t = 0; t < p.T; ++t) row[t] = -1;
-        } else if (p.nbr) {
-          for (int t = 0; t < p.T; ++t) row[t] = p.nbr[(size_t)m * p.T + t];
-        } else if (p.dense) {
-          const int hw = p.Hout * p.Wout;
-          const int b = m / hw, rem = m - b * hw;
-          const int y = rem / p.Wout, x = rem - y * p.Wout;
-          for (int t = 0; t < p.T; ++t) {
-            const int r = t / p.kw, s = t - r * p.kw;
-            const int yi = y * p.mul + r * p.dil - p.pad, xi = x * p.mul + s * p.dil - p.pad;
-            row[t] = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
+      named_bar_sync(1, kProducerThreads);
+      for (int e = ptid; e < 128 * p.T; e += kProducerThreads) {
+        const int r = e / p.T, t = e - r * p.T;
+        const int m = tile * 128 + r;
+        int idx = -1;
+        if (m < p.M) {
+          if (p.nbr) {
+            idx = p.nbr[(size_t)m * p.T + t];
+          } else if (p.dense) {
+            int b, rem, y, x;
+            if (m < (1 << 24)) {
+              b = __float2int_rz(__int2float_rn(m) * inv_hw);
+              rem = m - b * hw;
+              if (rem < 0) { --b; rem += hw; } else if (rem >= hw) { ++b; rem -= hw; }
+              y = __float2int_rz(__int2float_rn(rem) * inv_w);
+              x = rem - y * p.Wout;
+              if (x < 0) { --y; x += p.Wout; } else if (x >= p.Wout) { ++y; x -= p.Wout; }
+            } else {
+              b = m / hw; rem = m - b * hw; y = rem / p.Wout; x = rem - y * p.Wout;
+            }
+            const int rr = t / p.kw, ss = t - rr * p.kw;
+            const int yi = y * p.mul + rr * p.dil - p.pad, xi = x * p.mul + ss * p.dil - p.pad;
+            idx = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
+          } else {
+            idx = m;
           }
-        } else {
-          row[0] = m;
         }
+        s_off[r * 9 + t] = idx < 0 ? -1ll : (long long)idx * p.lda;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kProducerThreads);
       for (int kc = 0; kc < num_k; ++kc) {
         const int t = kc / kpt, cc = kc - t * kpt;
         pnx::mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t dst = pnx::smem_u32(sA + (size_t)stage * kABytes);
         const __nv_bfloat16* col = p.A + cc * 64 + chunk * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = j * 16 + sub_row;
-          const int idx = s_idx[r * 9 + t];
-          const __nv_bfloat16* src = col + (size_t)(idx < 0 ? 0 : idx) * p.lda;
-          pnx::cp_async16(dst + r * 128 + ((chunk ^ (r & 7)) << 4), src, idx < 0 ? 0u : 16u);
+        for (int j = 0; j < 128 / (kProducerThreads / 8); ++j) {
+          const int r = j * (kProducerThreads / 8) + sub_row;
+          const long long off = s_off[r * 9 + t];
+          pnx::cp_async16(dst + r * 128 + ((chunk ^ (r & 7)) << 4), col + (off < 0 ? 0 : off), off < 0 ? 0u : 16u);
         }
         pnx::cp_async_commit();
         if (pending == kLag) {
@@ -221,15 +238,20 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
   } else {
     // ---------------------------------------------------------------- epilogue (4 warps = 128 TMEM lanes)
+    // The column-block loop is deliberately NOT unrolled: the unrolled form was >170 KB of SASS and the epilogue
+    // ran out of the instruction cache (stall_no_inst); per-channel statistics live in shared memory.
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    double ssum[kNumCB], ssq[kNumCB];
-#pragma unroll
-    for (int i = 0; i < kNumCB; ++i) ssum[i] = ssq[i] = 0.0;
+    float* st_sum = s_stat + quarter * (2 * BN);
+    float* st_sq = st_sum + BN;
+    for (int c = lane; c < 2 * BN; c += 32) st_sum[c] = 0.f;
+    __syncwarp();
+    uint8_t* slab = reinterpret_cast<uint8_t*>(s_tr) + quarter * 4096;
     const int hw = p.Hout * p.Wout;
+    const bool staged = (BN % 64 == 0) && !p.out_fp32 && !p.shuffle;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      pnx::mbar_wait(&tfull[acc], acc_phase);
+      while (!pnx::mbar_try_wait(&tfull[acc], acc_phase)) __nanosleep(64);  // leave the issue slots to the producers
       pnx::tc_fence_after();
       const int m = tile * 128 + quarter * 32 + lane;
       const bool active = m < p.M;
@@ -241,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         sh_y = rem / p.Wout;
         sh_x = rem - sh_y * p.Wout;
       }
-#pragma unroll
+#pragma unroll 1
       for (int cb = 0; cb < kNumCB; ++cb) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb * kColBlk;
@@ -261,7 +283,31 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
 #pragma unroll
         for (int k = kColBlk; k < 32; ++k) v[k] = 0.f;
-        if (active) {
+        if (staged) {
+          // coalesced store: two 32-column blocks are staged per warp as a [32 rows x 128 B] slab (16-byte chunks
+          // XOR-swizzled by row), then written back 8 lanes per row = full 128-byte lines
+          const int half = cb & 1;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint4 pk = make_uint4(pnx::pack_bf16x2(v[8 * k], v[8 * k + 1]), pnx::pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                        pnx::pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pnx::pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+            *reinterpret_cast<uint4*>(slab + lane * 128 + (((half * 4 + k) ^ (lane & 7)) << 4)) = pk;
+          }
+          if (half == 1) {
+            __syncwarp();
+            const int ch = lane & 7;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + (lane >> 3);
+              const long long mr = (long long)tile * 128 + quarter * 32 + row;
+              if (mr < p.M) {
+                const uint4 val = *reinterpret_cast<const uint4*>(slab + row * 128 + ((ch ^ (row & 7)) << 4));
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + mr * p.ldc + (ncol0 - 32) + ch * 8) = val;
+              }
+            }
+            __syncwarp();
+          }
+        } else if (active) {
           int col = ncol0;
           if (p.shuffle) {
             const int q = ncol0 >> 6;
@@ -281,15 +327,20 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           }
         }
         if (p.stats) {
-          float a[32], b2[32];
+          float a[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float x = active ? v[k] : 0.f;
-            a[k] = x;
-            b2[k] = x * x;
+            v[k] = active ? v[k] : 0.f;
+            a[k] = v[k];
           }
-          ssum[cb] += (double)colsum32(a);
-          ssq[cb] += (double)colsum32(b2);
+          const float s1 = colsum32(a);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] *= v[k];
+          const float s2 = colsum32(v);
+          if (lane < kColBlk) {  // lane c owns column c of this warp's accumulators: plain read-modify-write
+            st_sum[cb * kColBlk + lane] += s1;
+            st_sq[cb * kColBlk + lane] += s2;
+          }
         }
       }
       pnx::tc_fence_before();
@@ -299,13 +350,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.stats) {
-#pragma unroll
-      for (int cb = 0; cb < kNumCB; ++cb) {
-        if (lane < kColBlk) {
-          const int ch = (n0 + cb * kColBlk + lane) % p.stats_mod;
-          atomicAdd(&p.stats[ch], ssum[cb]);
-          atomicAdd(&p.stats[p.stats_C + ch], ssq[cb]);
-        }
+      __syncwarp();
+      for (int c = lane; c < BN; c += 32) {
+        const int ch = (n0 + c) % p.stats_mod;
+        atomicAdd(&p.stats[ch], (double)st_sum[c]);
+        atomicAdd(&p.stats[p.stats_C + ch], (double)st_sq[c]);
       }
     }
   }
@@ -316,11 +365,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int BN>
+template <int BN, int PW>
 int launch_igemm(const CUtensorMap& wmap, const IgemmParams& p, int n_blocks, int sm_count, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmem));
+    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmem));
     attr_set = true;
   }
   const int num_tiles = (p.M + 127) / 128;
@@ -328,7 +377,7 @@ int launch_igemm(const CUtensorMap& wmap, const IgemmParams& p, int n_blocks, in
   if (gx < 1) gx = 1;
   if (gx > num_tiles) gx = num_tiles;
   dim3 grid(gx, n_blocks);
-  igemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, stream>>>(wmap, p);
+  igemm_kernel<BN, PW><<<grid, 64 + PW * 32 + 128, Cfg<BN>::kSmem, stream>>>(wmap, p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -373,12 +422,12 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   if (rc) return rc;
   const int n_blocks = Cout / block_n;
   switch (block_n) {
-    case 16: return launch_igemm<16>(wmap, p, n_blocks, sm_count, stream);
-    case 32: return launch_igemm<32>(wmap, p, n_blocks, sm_count, stream);
-    case 64: return launch_igemm<64>(wmap, p, n_blocks, sm_count, stream);
-    case 128: return launch_igemm<128>(wmap, p, n_blocks, sm_count, stream);
-    case 192: return launch_igemm<192>(wmap, p, n_blocks, sm_count, stream);
-    case 256: return launch_igemm<256>(wmap, p, n_blocks, sm_count, stream);
+    case 16: return launch_igemm<16, 8>(wmap, p, n_blocks, sm_count, stream);
+    case 32: return launch_igemm<32, 8>(wmap, p, n_blocks, sm_count, stream);
+    case 64: return launch_igemm<64, 8>(wmap, p, n_blocks, sm_count, stream);
+    case 128: return launch_igemm<128, 4>(wmap, p, n_blocks, sm_count, stream);
+    case 192: return launch_igemm<192, 4>(wmap, p, n_blocks, sm_count, stream);
+    case 256: return launch_igemm<256, 4>(wmap, p, n_blocks, sm_count, stream);
     default:
       pnx_set_error("pnx_igemm: unsupported block_n %d (16/32/64/128/192/256)", block_n);
       return PNX_ERR_ARG;

@@ -1,13 +1,16 @@
 // wgrad.cu -- weight-gradient of every convolution on the path as a tcgen05 GEMM over rows (sm_100a).
 //
-//   dW[t, x, y] += sum_m  X[ix(m,t), x] * Y[iy(m,t), y]          fp32, accumulated with red.global.add
-// X / Y are the two row-major bf16 operands of the convolution at tap t: the layer input gathered
-// through the neighbour table (or the dense geometry) and the output gradient read directly -- in
-// either role, so the 128-wide MMA M side can always be the wider channel count.
+//   dW[t, x, y] += sum_m  X[m, x] * Y[g(m,t), y]          fp32, accumulated with red.global.add
+// X is the DIRECT operand (read at row m), Y the GATHERED one (read through the neighbour table / the dense
+// geometry at tap t).  For a convolution X = output gradient, Y = layer input; for ConvTranspose2d k2s2 the
+// roles swap (X = input, Y = output gradient at the pixel-shuffled position).
 // Both operands are MN-major for the MMA (the reduction index K = row m is the slow one in memory):
 // tiles are staged as [64 rows x 128 B] blocks per 64-channel group with the 128-byte swizzle and
 // described to tcgen05.mma with MN-major descriptors (LBO = block stride, SBO = 8-row group stride).
-// Grid = (x groups, taps, K splits); each CTA owns one fp32 accumulator set in TMEM for its K range.
+// One CTA owns a 128-channel block of X, a <=256-channel chunk of Y and a GROUP of taps: the X tile of a
+// 64-row chunk is staged ONCE and multiplied against the gathered Y tile of every tap of the group (taps are
+// extra N columns of the accumulator, up to 512 TMEM columns), so the direct operand is not re-read per tap.
+// Grid = (x blocks * y chunks, tap groups, K splits).
 // This is the backward of: spconv SparseConv2d/SubMConv2d (reference sparse_conv.py:25-29,50-51),
 // nn.Conv2d/F.conv2d (aspp.py:19-32, conv.py:9-10, centerhead.py:35-46,108-114), nn.ConvTranspose2d
 // (centerhead.py:26-27) -- autograd derives these in the reference (trainer.py:94-108 loss.backward()).
@@ -20,67 +23,75 @@ struct WgradParams {
   const __nv_bfloat16* Y;
   long long ldx, ldy;
   int M, T;
-  int gather_x, gather_y;  // which operand goes through the neighbour map (0/1)
-  const int* nbr;          // [M, T] or null
-  int dense, Hout, Wout, Hin, Win, kw, mul, dil, pad;
-  int shuffle;             // ConvTranspose k2s2: tap q selects output pixel (2y+q/2, 2x+q%2) of the gathered operand
-  float* dW;               // [T, X_total, Y_total]
+  const int* nbr;  // [M, T] or null
+  int gathered;    // 0: Y read at row m (taps == 1)
+  int Hout, Wout, Hin, Win, kw, mul, dil, pad;
+  int shuffle;     // ConvTranspose k2s2: tap q selects pixel (2y+q/2, 2x+q%2) of the gathered operand
+  float* dW;       // [T, X_total, Y_total]
   int X_total, Y_total;
-  int x_dup;               // X has only 64 channels: second MN atom aliases the first (rows 64..127 ignored)
+  int x_dup;       // X has only 64 channels: second MN atom aliases the first (rows 64..127 ignored)
+  int y_chunks;    // Y_total / NYC
+  int taps_per_group;
   int rows_per_split;
+  float inv_hw, inv_w, inv_kw;
 };
 
-constexpr int kThreads = 320;
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kThreads = 64 + kProducerThreads + 128;
 constexpr int kKS = 64;               // rows (K) per stage
 constexpr uint32_t kBlk = kKS * 128;  // bytes of one [64 rows x 64 ch] block
-constexpr int kLag = 2;
+constexpr int kMaxTG = 8;
 
-template <int NY, int XB>
+// NYC = Y channels per CTA (64..256), TG = max taps per group (NYC * TG <= 512 TMEM columns)
+template <int NYC, int TG>
 struct WCfg {
-  static constexpr int kXBlocks = XB * 2;
-  static constexpr int kYBlocks = NY / 64;
-  static constexpr uint32_t kStageBytes = (kXBlocks + kYBlocks) * kBlk;
-  static constexpr int kStagesRaw = (192 * 1024) / (int)kStageBytes;
+  static constexpr int kYAtoms = NYC / 64;
+  static constexpr uint32_t kStageBytes = (2 + TG * kYAtoms) * kBlk;
+  static constexpr int kStagesRaw = (196 * 1024) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256;
+  static constexpr int kLag = kStages >= 4 ? kStages - 2 : (kStages == 3 ? 1 : 0);
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + (size_t)kStages * kKS * (TG + 1) * 8;
+  static_assert(NYC * TG <= 512, "TMEM budget");
+  static_assert(kStages >= 2, "need at least two stages");
 };
 
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return pnx::make_smem_desc_sw128(addr, lbo, sbo);
+// exact n / d for 0 <= n via one float multiply + correction (n < 2^24), integer divide otherwise
+__device__ __forceinline__ void divmod_fast(int n, int d, float inv_d, int& q, int& r) {
+  if (n < (1 << 24)) {
+    q = __float2int_rz(__int2float_rn(n) * inv_d);
+    r = n - q * d;
+    if (r < 0) { --q; r += d; } else if (r >= d) { ++q; r -= d; }
+  } else {
+    q = n / d;
+    r = n - q * d;
+  }
 }
 
-__device__ __forceinline__ int map_row(const WgradParams& p, int m, int t) {
-  if (p.nbr) return p.nbr[(size_t)m * p.T + t];
-  const int hw = p.Hout * p.Wout;
-  const int b = m / hw, rem = m - b * hw;
-  const int y = rem / p.Wout, x = rem - y * p.Wout;
-  if (p.shuffle) return (b * 2 * p.Hout + 2 * y + (t >> 1)) * (2 * p.Wout) + 2 * x + (t & 1);
-  const int r = t / p.kw, s = t - r * p.kw;
-  const int yi = y * p.mul + r * p.dil - p.pad, xi = x * p.mul + s * p.dil - p.pad;
-  return (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
-}
-
-template <int NY, int XB>
+template <int NYC, int TG>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
-  using C = WCfg<NY, XB>;
-  constexpr int kStages = C::kStages;
-  constexpr int kXBlocks = C::kXBlocks, kYBlocks = C::kYBlocks;
+  using C = WCfg<NYC, TG>;
+  constexpr int kStages = C::kStages, kLag = C::kLag, kYAtoms = C::kYAtoms;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * C::kStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* done = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  long long* s_rows = reinterpret_cast<long long*>(smem + (size_t)kStages * C::kStageBytes + 256);  // [kStages][TG+1][kKS] element offsets
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int xg = blockIdx.x, t = blockIdx.y, split = blockIdx.z;
+  const int xb = blockIdx.x / p.y_chunks, yc = blockIdx.x - xb * p.y_chunks;
+  const int t0 = blockIdx.y * p.taps_per_group;
+  const int ntaps = min(p.taps_per_group, p.T - t0);
+  const int split = blockIdx.z;
   const int m_begin = split * p.rows_per_split;
   const int m_end = min(p.M, m_begin + p.rows_per_split);
   const int num_k = (m_end - m_begin + kKS - 1) / kKS;
 
   if (warp == 0 && pnx::elect_one()) {
     for (int s = 0; s < kStages; ++s) {
-      pnx::mbar_init(&full[s], 4);
+      pnx::mbar_init(&full[s], kProducerWarps);
       pnx::mbar_init(&empty[s], 1);
     }
     pnx::mbar_init(done, 1);
@@ -94,23 +105,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
 
   if (num_k > 0) {
     if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer
       if (pnx::elect_one()) {
-        constexpr uint32_t idesc = pnx::make_idesc_bf16(128, NY, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t x_lbo = p.x_dup ? 0u : kBlk;
+        // taps are merged into MMAs of up to 256 columns (N-major atoms of 64 channels are simply consecutive blocks)
+        constexpr int kAtomsPerMma = kYAtoms >= 3 ? kYAtoms : (kYAtoms == 2 ? 4 : 4);
+        const int total_atoms = ntaps * kYAtoms;
         for (int kc = 0; kc < num_k; ++kc) {
           pnx::mbar_wait(&full[stage], phase);
           pnx::tc_fence_after();
           const uint32_t sx = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
-          const uint32_t sy = sx + kXBlocks * kBlk;
+          const uint32_t sy = sx + 2 * kBlk;
 #pragma unroll
           for (int k = 0; k < kKS / 16; ++k) {
-            const uint64_t dy = make_desc_mn_sw128(sy + k * 2048, kBlk, 1024);
-#pragma unroll
-            for (int xb = 0; xb < XB; ++xb) {
-              const uint64_t dx = make_desc_mn_sw128(sx + xb * 2 * kBlk + k * 2048, x_lbo, 1024);
-              pnx::umma_f16(tmem_base + xb * NY, dx, dy, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            const uint64_t dx = pnx::make_smem_desc_sw128(sx + k * 2048, x_lbo, 1024);
+            for (int a0 = 0; a0 < total_atoms; a0 += kAtomsPerMma) {
+              const int na = min(kAtomsPerMma, total_atoms - a0);
+              const uint64_t dy = pnx::make_smem_desc_sw128(sy + a0 * kBlk + k * 2048, kBlk, 1024);
+              pnx::umma_f16(tmem_base + a0 * 64, dx, dy, pnx::make_idesc_bf16(128, na * 64, 1, 1),
+                            (kc > 0 || k > 0) ? 1u : 0u);
             }
           }
           pnx::umma_commit(&empty[stage]);
@@ -118,35 +133,72 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
         }
         pnx::umma_commit(done);
       }
-    } else if (warp >= 2 && warp < 6) {
+    } else if (warp >= 2 && warp < 2 + kProducerWarps) {
+      // ---------------------------------------------------------------- producers (8 warps: two per scheduler so the
+      // integer/address latency of the copy loop is hidden; 64-bit row offsets come from a per-chunk smem table)
       const int ptid = threadIdx.x - 64;
       const int sub_row = ptid >> 3, chunk = ptid & 7;
-      const int x_ch0 = xg * XB * 128;
+      const int x_ch0 = xb * 128, y_ch0 = yc * NYC;
+      const int hw = p.Hout * p.Wout;
+      const __nv_bfloat16* xbase = p.X + x_ch0 + chunk * 8;
+      const __nv_bfloat16* ybase = p.Y + y_ch0 + chunk * 8;
       int stage = 0, arr_stage = 0, pending = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < num_k; ++kc) {
-        pnx::mbar_wait(&empty[stage], phase ^ 1);
-        const uint32_t sx = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
-        const uint32_t sy = sx + kXBlocks * kBlk;
-#pragma unroll
-        for (int j = 0; j < kKS / 16; ++j) {
-          const int r = j * 16 + sub_row;
+        // rows[0][r] = direct row offset (or -1), rows[1+j][r] = gathered row offset of tap t0+j
+        long long* rows = s_rows + stage * (TG + 1) * kKS;
+        for (int e = ptid; e < (ntaps + 1) * kKS; e += kProducerThreads) {
+          const int j = e / kKS, r = e - j * kKS;
           const int m = m_begin + kc * kKS + r;
-          int ix = -1, iy = -1;
+          long long off = -1;
           if (m < m_end) {
-            const int g = map_row(p, m, t);
-            ix = p.gather_x ? g : m;
-            iy = p.gather_y ? g : m;
-            if (ix < 0 || iy < 0) ix = iy = -1;
+            if (j == 0) {
+              off = (long long)m * p.ldx;
+            } else {
+              const int t = t0 + j - 1;
+              int g;
+              if (!p.gathered) {
+                g = m;
+              } else if (p.nbr) {
+                g = p.nbr[(size_t)m * p.T + t];
+              } else {
+                int b, rem, y, x;
+                divmod_fast(m, hw, p.inv_hw, b, rem);
+                divmod_fast(rem, p.Wout, p.inv_w, y, x);
+                if (p.shuffle) {
+                  g = (b * 2 * p.Hout + 2 * y + (t >> 1)) * (2 * p.Wout) + 2 * x + (t & 1);
+                } else {
+                  int rr, ss;
+                  divmod_fast(t, p.kw, p.inv_kw, rr, ss);
+                  const int yi = y * p.mul + rr * p.dil - p.pad, xi = x * p.mul + ss * p.dil - p.pad;
+                  g = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
+                }
+              }
+              off = g < 0 ? -1ll : (long long)g * p.ldy;
+            }
           }
-          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
-          const __nv_bfloat16* xs = p.X + (size_t)(ix < 0 ? 0 : ix) * p.ldx + x_ch0 + chunk * 8;
-          const __nv_bfloat16* ys = p.Y + (size_t)(iy < 0 ? 0 : iy) * p.ldy + chunk * 8;
-          const uint32_t nb = ix < 0 ? 0u : 16u;
-          const int nxb = p.x_dup ? 1 : kXBlocks;
-          for (int b = 0; b < nxb; ++b) pnx::cp_async16(sx + b * kBlk + off, xs + b * 64, nb);
+          rows[j * kKS + r] = off;
+        }
+        pnx::mbar_wait(&empty[stage], phase ^ 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint32_t sx = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
+        const uint32_t sy = sx + 2 * kBlk;
 #pragma unroll
-          for (int b = 0; b < kYBlocks; ++b) pnx::cp_async16(sy + b * kBlk + off, ys + b * 64, nb);
+        for (int j2 = 0; j2 < kKS / 32; ++j2) {
+          const int r = j2 * 32 + sub_row;
+          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+          const long long ox = rows[r];
+          const __nv_bfloat16* xs = xbase + (ox < 0 ? 0 : ox);
+          const uint32_t nbx = ox < 0 ? 0u : 16u;
+          pnx::cp_async16(sx + off, xs, nbx);
+          if (!p.x_dup) pnx::cp_async16(sx + kBlk + off, xs + 64, nbx);
+          for (int j = 0; j < ntaps; ++j) {
+            const long long oy = rows[(1 + j) * kKS + r];
+            const __nv_bfloat16* ys = ybase + (oy < 0 ? 0 : oy);
+            const uint32_t nby = (oy < 0 || ox < 0) ? 0u : 16u;
+#pragma unroll
+            for (int a = 0; a < kYAtoms; ++a) pnx::cp_async16(sy + (j * kYAtoms + a) * kBlk + off, ys + a * 64, nby);
+          }
         }
         pnx::cp_async_commit();
         if (pending == kLag) {
@@ -167,20 +219,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
         if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
         if (++arr_stage == kStages) arr_stage = 0;
       }
-    } else if (warp >= 6) {
+    } else if (warp >= 2 + kProducerWarps) {
+      // ---------------------------------------------------------------- epilogue: TMEM -> red.global.add
       const int quarter = warp & 3;
-      pnx::mbar_wait(done, 0);
+      while (!pnx::mbar_try_wait(done, 0)) __nanosleep(256);  // long wait: leave the issue slots to the producers
       pnx::tc_fence_after();
       const int xrow_local = quarter * 32 + lane;
+      const int xch = xb * 128 + xrow_local;
+      const bool ok = xch < p.X_total && !(p.x_dup && xrow_local >= 64);
+      for (int j = 0; j < ntaps; ++j) {
+        float* dst = p.dW + ((size_t)(t0 + j) * p.X_total + (ok ? xch : 0)) * p.Y_total + yc * NYC;
 #pragma unroll
-      for (int xb = 0; xb < XB; ++xb) {
-        const int xch = xg * XB * 128 + xb * 128 + xrow_local;
-        const bool ok = xch < p.X_total && !(p.x_dup && xrow_local >= 64);
-        float* dst = p.dW + ((size_t)t * p.X_total + (ok ? xch : 0)) * p.Y_total;
-#pragma unroll
-        for (int cb = 0; cb < NY / 32; ++cb) {
+        for (int cb = 0; cb < NYC / 32; ++cb) {
           uint32_t r[32];
-          pnx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + xb * NY + cb * 32, r);
+          pnx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + j * NYC + cb * 32, r);
           pnx::tmem_ld_wait();
           if (ok) {
 #pragma unroll
@@ -196,16 +248,29 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
   if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int NY, int XB>
-int launch_wgrad(const WgradParams& p, int x_groups, int splits, cudaStream_t stream) {
+template <int NYC, int TG>
+int launch_wgrad(WgradParams p, int x_blocks, int sm_count, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNX_CUDA(cudaFuncSetAttribute(wgrad_kernel<NY, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)WCfg<NY, XB>::kSmem));
+    PNX_CUDA(cudaFuncSetAttribute(wgrad_kernel<NYC, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)WCfg<NYC, TG>::kSmem));
     attr_set = true;
   }
-  dim3 grid(x_groups, p.T, splits);
-  wgrad_kernel<NY, XB><<<grid, kThreads, WCfg<NY, XB>::kSmem, stream>>>(p);
+  p.y_chunks = p.Y_total / NYC;
+  p.taps_per_group = p.T < TG ? p.T : TG;
+  int groups = (p.T + p.taps_per_group - 1) / p.taps_per_group;
+  // balance the groups (e.g. 9 taps, TG = 8 -> 5 + 4)
+  p.taps_per_group = (p.T + groups - 1) / groups;
+  groups = (p.T + p.taps_per_group - 1) / p.taps_per_group;
+  const int ctas_xy = x_blocks * p.y_chunks * groups;
+  int splits = (2 * sm_count + ctas_xy - 1) / ctas_xy;
+  const int max_splits = (p.M + 8 * kKS - 1) / (8 * kKS);  // at least 8 K-chunks per CTA
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.rows_per_split = ((p.M + splits - 1) / splits + kKS - 1) / kKS * kKS;
+  splits = (p.M + p.rows_per_split - 1) / p.rows_per_split;
+  dim3 grid(x_blocks * p.y_chunks, groups, splits);
+  wgrad_kernel<NYC, TG><<<grid, kThreads, WCfg<NYC, TG>::kSmem, stream>>>(p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -213,41 +278,34 @@ int launch_wgrad(const WgradParams& p, int x_groups, int splits, cudaStream_t st
 }  // namespace
 
 // Contract: include/pnx.h (pnx_wgrad).  dW must be zeroed (or hold the value to accumulate into).
-extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, int gather_x, const void* Y, long long ldy,
-                         int y_channels, int gather_y, int M, int taps, const int* nbr, int dense, int Hout, int Wout,
-                         int Hin, int Win, int kw, int mul, int dil, int pad, int shuffle, float* dW, int sm_count,
-                         cudaStream_t stream) {
+extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long long ldy, int y_channels,
+                         int gathered, int M, int taps, const int* nbr, int Hout, int Wout, int Hin, int Win, int kw,
+                         int mul, int dil, int pad, int shuffle, float* dW, int sm_count, cudaStream_t stream) {
   PNX_CHECK_ARG(M >= 0, "M");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(taps >= 1 && taps <= 9, "taps");
   PNX_CHECK_ARG(x_channels % 64 == 0 && y_channels % 64 == 0, "channel counts must be multiples of 64");
-  PNX_CHECK_ARG(y_channels <= 256, "y_channels <= 256 (put the wider operand on X)");
   PNX_CHECK_ARG(x_channels == 64 || x_channels % 128 == 0, "x_channels must be 64 or a multiple of 128");
-  PNX_CHECK_ARG(gather_x + gather_y <= 1, "at most one gathered operand");
-  PNX_CHECK_ARG(!(gather_x + gather_y) || nbr || dense || shuffle, "gather needs a table or geometry");
+  PNX_CHECK_ARG(gathered || taps == 1, "taps > 1 needs a gathered operand");
+  PNX_CHECK_ARG(!gathered || nbr || shuffle || (Hout > 0 && Wout > 0), "gather needs a table or geometry");
   PNX_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "ldx/ldy % 8");
   if (sm_count <= 0) sm_count = 148;
   WgradParams p;
   p.X = (const __nv_bfloat16*)X; p.Y = (const __nv_bfloat16*)Y;
   p.ldx = ldx; p.ldy = ldy; p.M = M; p.T = taps;
-  p.gather_x = gather_x; p.gather_y = gather_y; p.nbr = nbr; p.dense = dense;
+  p.nbr = nbr; p.gathered = gathered;
   p.Hout = Hout > 0 ? Hout : 1; p.Wout = Wout > 0 ? Wout : 1; p.Hin = Hin; p.Win = Win;
   p.kw = kw > 0 ? kw : 1; p.mul = mul; p.dil = dil; p.pad = pad; p.shuffle = shuffle;
   p.dW = dW; p.X_total = x_channels; p.Y_total = y_channels;
   p.x_dup = x_channels == 64 ? 1 : 0;
-  // one CTA owns XB*128 X channels; XB=2 only when the TMEM (512 columns) and smem budgets allow
-  const int xb = (x_channels % 256 == 0 && y_channels <= 256) ? 2 : 1;
-  const int x_groups = x_channels == 64 ? 1 : x_channels / (128 * xb);
-  int splits = (2 * sm_count) / (x_groups * taps);
-  const int max_splits = (M + 4 * kKS - 1) / (4 * kKS);  // at least 4 K-chunks per CTA
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  p.rows_per_split = ((M + splits - 1) / splits + kKS - 1) / kKS * kKS;
-  splits = (M + p.rows_per_split - 1) / p.rows_per_split;
-#define PNX_WG(NYV, XBV) \
-  if (y_channels == NYV && xb == XBV) return launch_wgrad<NYV, XBV>(p, x_groups, splits, stream);
-  PNX_WG(64, 1) PNX_WG(64, 2) PNX_WG(128, 1) PNX_WG(128, 2) PNX_WG(192, 1) PNX_WG(192, 2) PNX_WG(256, 1) PNX_WG(256, 2)
-#undef PNX_WG
-  pnx_set_error("pnx_wgrad: unsupported shape x=%d y=%d", x_channels, y_channels);
-  return PNX_ERR_ARG;
+  p.inv_hw = 1.0f / (float)(p.Hout * p.Wout);
+  p.inv_w = 1.0f / (float)p.Wout;
+  p.inv_kw = 1.0f / (float)p.kw;
+  p.y_chunks = 1; p.taps_per_group = 1; p.rows_per_split = M;
+  const int x_blocks = x_channels == 64 ? 1 : x_channels / 128;
+  // Y chunk: the largest of 256/192/128/64 dividing y_channels; taps per group bounded by 512 TMEM columns
+  if (y_channels % 256 == 0) return launch_wgrad<256, 1>(p, x_blocks, sm_count, stream);
+  if (y_channels % 192 == 0) return launch_wgrad<192, 2>(p, x_blocks, sm_count, stream);
+  if (y_channels % 128 == 0) return launch_wgrad<128, 3>(p, x_blocks, sm_count, stream);
+  return launch_wgrad<64, 5>(p, x_blocks, sm_count, stream);
 }

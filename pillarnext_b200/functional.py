@@ -167,18 +167,14 @@ class ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             if layout.kind == "convT":
                 g = torch.zeros(4, cin, cout, dtype=torch.float32, device=dy.device)
-                ops.wgrad(x, cin, False, dy, cout, True, spec.M_out, 4, g, dense=spec.d_dense, shuffle=True)
-                dw = layout.unpack_grad(g, shape)
-            elif cout >= cin and cin <= 256 and cpad == cout:
-                g = torch.zeros(spec.taps, cout, cin, dtype=torch.float32, device=dy.device)
-                ops.wgrad(dy, cout, False, x, cin, spec.taps > 1 or spec.nbr is not None, spec.M_out, spec.taps, g,
-                          nbr=spec.nbr, dense=spec.dense)
-                dw = layout.unpack_grad(g, shape)
+                ops.wgrad(x, cin, dy, cout, spec.M_out, 4, g, dense=spec.d_dense, shuffle=True)
             else:
-                g = torch.zeros(spec.taps, cin, cpad, dtype=torch.float32, device=dy.device)
-                ops.wgrad(x, cin, spec.taps > 1 or spec.nbr is not None, dy, cpad, False, spec.M_out, spec.taps, g,
-                          nbr=spec.nbr, dense=spec.dense)
-                dw = layout.unpack_grad(g[:, :, :cout].transpose(1, 2).contiguous(), shape)
+                # X = output gradient (direct), Y = layer input (gathered): result is [tap, Cout(pad), Cin]
+                g = torch.zeros(spec.taps, cpad, cin, dtype=torch.float32, device=dy.device)
+                ops.wgrad(dy, cpad, x, cin, spec.M_out, spec.taps, g, nbr=spec.nbr, dense=spec.dense)
+                if cpad != cout:
+                    g = g[:, :cout].contiguous()
+            dw = layout.unpack_grad(g, shape)
         return dx, dw, dbias, None, None, None, None, None, None
 
 
@@ -311,10 +307,10 @@ class ASPPBranchesFn(torch.autograd.Function):
             ops.igemm(dcat[:, (2 + j) * C:(3 + j) * C], M, wd, 9, C, C, nxt, lda=C6, dense=(H, W, H, W, 3, 1, d, d), addend=dx)
             dx = nxt
         g1 = torch.zeros(1, C, C, dtype=torch.float32, device=dcat.device)
-        ops.wgrad(dcat[:, C:2 * C], C, False, x, C, False, M, 1, g1)
+        ops.wgrad(dcat[:, C:2 * C], C, x, C, M, 1, g1)
         gs = torch.zeros(9, C, C, dtype=torch.float32, device=dcat.device)
         for j, d in enumerate(ASPPBranchesFn.DILS):
-            ops.wgrad(dcat[:, (2 + j) * C:(3 + j) * C], C, False, x, C, True, M, 9, gs, dense=(H, W, H, W, 3, 1, d, d))
+            ops.wgrad(dcat[:, (2 + j) * C:(3 + j) * C], C, x, C, M, 9, gs, dense=(H, W, H, W, 3, 1, d, d))
         g = torch.empty(M, C, dtype=torch.bfloat16, device=dcat.device)
         ops.relu_bwd(dx, x, M, C, g)
         return g, g, l.unpack_grad(g1, tuple(w1x1.shape)), l.unpack_grad(gs, tuple(wshared.shape)), None, None, None

@@ -293,17 +293,18 @@ def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None,
     return out
 
 
-def wgrad(X, x_channels, gather_x, Y, y_channels, gather_y, M, taps, dW, *, nbr=None, dense=None, shuffle=False):
-    """dW[t, x, y] += sum_m X[ix(m,t), x] * Y[iy(m,t), y]; dW fp32 [taps, x_channels, y_channels]."""
+def wgrad(X, x_channels, Y, y_channels, M, taps, dW, *, nbr=None, dense=None, shuffle=False, gathered=None):
+    """dW[t, x, y] += sum_m X[m, x] * Y[g(m,t), y]; X direct, Y gathered; dW fp32 [taps, x_channels, y_channels]."""
     assert X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16 and dW.dtype == torch.float32
     assert tuple(dW.shape) == (taps, x_channels, y_channels) and dW.is_contiguous()
     d = dense or (0, 0, 0, 0, 1, 1, 1, 0)
+    if gathered is None:
+        gathered = nbr is not None or dense is not None or shuffle
     _count(1)
-    with _Timed("wgrad", 2.0 * M * taps * x_channels * y_channels, 2.0 * M * taps * (x_channels + y_channels),
+    with _Timed("wgrad", 2.0 * M * taps * x_channels * y_channels, 2.0 * M * (x_channels + taps * y_channels),
                 "M%d_T%d_X%d_Y%d" % (M, taps, x_channels, y_channels)):
-      check(lib().pnx_wgrad(ptr(X), X.stride(0), x_channels, 1 if gather_x else 0, ptr(Y), Y.stride(0), y_channels,
-                          1 if gather_y else 0, M, taps, ptr(nbr) if nbr is not None else None,
-                          1 if (dense and not shuffle) else 0, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7],
+      check(lib().pnx_wgrad(ptr(X), X.stride(0), x_channels, ptr(Y), Y.stride(0), y_channels, 1 if gathered else 0, M,
+                          taps, ptr(nbr) if nbr is not None else None, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7],
                           1 if shuffle else 0, ptr(dW), sm_count(), stream()))
     return dW
 

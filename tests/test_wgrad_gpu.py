@@ -16,32 +16,28 @@ def _close(out, ref, extra=0.0):
     assert err <= (3e-3 + extra) * scale, "max abs err %g (scale %g)" % (err, scale)
 
 
-@pytest.mark.parametrize("M,Min,Cx,Cy,gx", [(5000, 4000, 64, 64, False), (20000, 20000, 256, 256, False), (3000, 3000, 128, 64, False),
-                                            (7777, 9000, 384, 64, True), (700, 900, 256, 128, False), (100, 100, 1536, 256, True)])
-def test_wgrad_table(M, Min, Cx, Cy, gx):
-    """gx=False: X = dOut (direct, M rows), Y = In (gathered).  gx=True: X = In (gathered), Y = dOut."""
+@pytest.mark.parametrize("M,Min,Cx,Cy", [(5000, 4000, 64, 64), (20000, 20000, 256, 256), (3000, 3000, 128, 64), (7777, 9000, 384, 64),
+                                         (700, 900, 256, 128), (100, 100, 256, 1536), (6000, 5000, 64, 384), (4100, 4100, 128, 192)])
+def test_wgrad_table(M, Min, Cx, Cy):
+    """X = dOut (direct, M rows), Y = In (gathered through a random neighbour table with holes)."""
     torch.manual_seed(M + Cx)
     T = 9
     nbr = torch.randint(-Min // 3, Min, (M, T), device="cuda", dtype=torch.int32).clamp(min=-1)
-    if gx:
-        X = torch.randn(Min, Cx, device="cuda").bfloat16()
-        Y = torch.randn(M, Cy, device="cuda").bfloat16()
-    else:
-        X = torch.randn(M, Cx, device="cuda").bfloat16()
-        Y = torch.randn(Min, Cy, device="cuda").bfloat16()
+    X = torch.randn(M, Cx, device="cuda").bfloat16()
+    Y = torch.randn(Min, Cy, device="cuda").bfloat16()
     ref = torch.zeros(T, Cx, Cy, device="cuda")
     for t in range(T):
         idx = nbr[:, t].long()
-        ok = (idx >= 0).unsqueeze(1)
-        if gx:
-            xg = torch.where(ok, X[idx.clamp(min=0)].float(), torch.zeros(1, device="cuda"))
-            ref[t] = xg.t() @ Y.float()
-        else:
-            yg = torch.where(ok, Y[idx.clamp(min=0)].float(), torch.zeros(1, device="cuda"))
-            ref[t] = X.float().t() @ yg
+        yg = torch.where((idx >= 0).unsqueeze(1), Y[idx.clamp(min=0)].float(), torch.zeros(1, device="cuda"))
+        ref[t] = X.float().t() @ yg
     dW = torch.zeros(T, Cx, Cy, device="cuda")
-    ops.wgrad(X, Cx, gx, Y, Cy, not gx, M, T, dW, nbr=nbr)
+    ops.wgrad(X, Cx, Y, Cy, M, T, dW, nbr=nbr)
     _close(dW, ref)
+    # no gather, single tap (1x1 convolutions)
+    Y1 = torch.randn(M, Cy, device="cuda").bfloat16()
+    d1 = torch.zeros(1, Cx, Cy, device="cuda")
+    ops.wgrad(X, Cx, Y1, Cy, M, 1, d1)
+    _close(d1[0], X.float().t() @ Y1.float())
 
 
 @pytest.mark.parametrize("B,H,W_,Cin,Cout,k,stride,dil", [(2, 24, 24, 64, 64, 3, 1, 1), (1, 40, 36, 256, 256, 3, 1, 6), (1, 21, 33, 128, 256, 3, 2, 1), (2, 16, 16, 256, 256, 1, 1, 1)])
@@ -58,7 +54,7 @@ def test_wgrad_dense_conv(B, H, W_, Cin, Cout, k, stride, dil):
     x_rows = x.permute(0, 2, 3, 1).contiguous().view(-1, Cin)
     dy_rows = dy.permute(0, 2, 3, 1).contiguous().view(-1, Cout)
     dW = torch.zeros(k * k, Cout, Cin, device="cuda")
-    ops.wgrad(dy_rows, Cout, False, x_rows, Cin, True, M, k * k, dW, dense=(Ho, Wo, H, W_, k, stride, dil, pad))
+    ops.wgrad(dy_rows, Cout, x_rows, Cin, M, k * k, dW, dense=(Ho, Wo, H, W_, k, stride, dil, pad) if k > 1 else None)
     got = dW.view(k, k, Cout, Cin).permute(2, 3, 0, 1)
     _close(got, w.grad)
 
@@ -74,7 +70,7 @@ def test_wgrad_conv_transpose():
     x_rows = x.permute(0, 2, 3, 1).contiguous().view(-1, C)
     dy_rows = dy.permute(0, 2, 3, 1).contiguous().view(-1, C)
     dW = torch.zeros(4, C, C, device="cuda")                      # [q, ci, co]
-    ops.wgrad(x_rows, C, False, dy_rows, C, True, B * H * W_, 4, dW, dense=(H, W_, 2 * H, 2 * W_, 2, 2, 1, 0), shuffle=True)
+    ops.wgrad(x_rows, C, dy_rows, C, B * H * W_, 4, dW, dense=(H, W_, 2 * H, 2 * W_, 2, 2, 1, 0), shuffle=True)
     got = dW.view(2, 2, C, C).permute(2, 3, 0, 1)                 # [ci, co, dy, dx]
     _close(got, w.grad)
 
