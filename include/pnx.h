@@ -40,27 +40,39 @@ int pnx_sm_count(void);
 int pnx_scan_u32(const uint32_t* in, int n, int popc, int* out, int* block_sums, int* total_out,
                  cudaStream_t stream);
 
+/* Exclusive scan of the per-32-word-block counts of a bitmap in ONE launch (two-level: the count buffer holds
+ * the block counts followed by one count per 1024 blocks; pnx_blockcnt_size() ints).  out [n_blocks+1]. */
+int pnx_blockcnt_size(int n_blocks);
+int pnx_scan_blocks(const int* counts, int n_blocks, int* out, int* total_out, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- V1-V3 voxelizer
  * Replaces PillarNet.forward index generation, det3d/models/readers/pillar_encoder.py:86-111
  * (range mask, trunc, torch.unique(dim=0, return_inverse=True)) bit-exactly, without a sort.
  *   points        [n_points, 6] fp32 (batch_idx, x, y, z, intensity, time), 16-byte aligned
- *   bitmap        pnx_voxelize_bitmap_words() u32, occupancy in (b, xi, yi) order (zeroed here)
- *   word_prefix   [words+1]  exclusive popcount prefix (rank of a bit = pillar id)
- *   scan_scratch  [max(words, cap_pillars)/2048 + 2]
+ *   bitmap        pnx_voxelize_bitmap_words() u32 (padded to whole 32-word blocks), occupancy in (b, xi, yi)
+ *                 order (zeroed here)
+ *   inblk         [words] u16 OUT: in-block exclusive popcount prefix (also used by the rulebook)
+ *   blockcnt      [pnx_blockcnt_size(words/32)] int32: pillars per 32-word block (+ per 1024 blocks), zeroed here
+ *   blockpref     [words/32 + 1] exclusive scan of blockcnt; rank of a cell = blockpref[block] +
+ *                 popcount of the block's earlier words + popcount of the lower bits of its word
  *   cell_of_point [n_points] scratch
  *   pillar_of_point [n_points] OUT: pillar id (== reference `unq_inv`) or -1 for dropped points
  *   coords        [cap_pillars, 3] OUT int32 (b, yi, xi), rows in the reference's sorted-unique order
- *   bucket_cnt    [2*(cap_pillars+1)] scratch;  bucket_off [cap_pillars+1] OUT CSR offsets
- *   bucket_tmp    [n_points] scratch;           bucket_pts [n_points] OUT point ids grouped by pillar,
- *                                                ascending inside a pillar
- *   counts        [2] OUT device ints: {#pillars P, #kept points Nv}
- * cap_pillars must be >= min(n_points, batch*gx*gy). */
+ *   bucket_cnt    [2*(cap_pillars+1)] OUT (optional, may be NULL): points per pillar + zeroed cursors for
+ *                 pnx_bucketize
+ *   counts        [2] device ints: counts[0] = #pillars P (counts[1] = #kept points, set by pnx_bucketize)
+ * cap_pillars must be >= min(n_points, batch*gx*gy).  4 kernels: mark | scan | coords | rank. */
 size_t pnx_voxelize_bitmap_words(int batch, int gx, int gy);
 int pnx_voxelize(const float* points, int n_points, int batch, float min_x, float min_y, float vs_x,
-                 float vs_y, int gx, int gy, uint32_t* bitmap, int* word_prefix, int* scan_scratch,
+                 float vs_y, int gx, int gy, uint32_t* bitmap, uint16_t* inblk, int* blockcnt, int* blockpref,
                  int* cell_of_point, int* pillar_of_point, int* coords, int cap_pillars,
-                 uint32_t* bucket_cnt, int* bucket_off, int* bucket_tmp, int* bucket_pts, int* counts,
-                 cudaStream_t stream);
+                 uint32_t* bucket_cnt, int* counts, cudaStream_t stream);
+/* CSR grouping of the kept points by pillar (input of the per-pillar mean / max, pillar_encoder.py:113-114,43):
+ * bucket_off [cap_pillars+1], bucket_pts [n_points] (ascending point id inside a pillar), bucket_tmp scratch,
+ * scan_scratch [cap_pillars/2048 + 4]; counts[1] receives the number of kept points. */
+int pnx_bucketize(const int* pillar_of_point, int n_points, int cap_pillars, uint32_t* bucket_cnt,
+                  int* scan_scratch, int* bucket_off, int* bucket_tmp, int* bucket_pts, int* counts,
+                  cudaStream_t stream);
 
 /* ---------------------------------------------------------------- BatchNorm statistics
  * stats = [2*C] fp64 (sum, sum of squares) accumulated by the producing kernel.
@@ -111,17 +123,19 @@ int pnx_pfn_backward(const float* points, const int* bucket_off, const int* buck
 
 /* ---------------------------------------------------------------- B1-B4 active sites / rulebook
  * Replaces spconv index-pair generation (sparse_conv.py:25-29,50-51; sparse_resnet.py:43-48,63-64).
- * Bitmaps are in (b, u=x, v=y) order, v padded to 32 bits; coords are (b, u, v) int32. */
+ * A level = bitmap in (b, u=x, v=y) order (v padded to 32 bits, words padded to whole 32-word blocks) +
+ * inblk [words] u16 (in-block exclusive popcount prefix) + blockpref [words/32+1]; coords are (b, u, v) int32. */
 int pnx_sites_out_dim(int in_dim, int stride);
 int pnx_sites_dilate(const uint32_t* bm_in, int batch, int u_in, int v_in, int stride, uint32_t* bm_out,
-                     cudaStream_t stream);
-int pnx_sites_coords(const uint32_t* bm, const int* prefix, int batch, int u, int v, int* coords, int cap,
-                     cudaStream_t stream);
+                     uint16_t* inblk, int* blockcnt, cudaStream_t stream);
+int pnx_sites_inblock(const uint32_t* bm, int n_words_pad, uint16_t* inblk, cudaStream_t stream);
+int pnx_sites_coords(const uint32_t* bm, const int* blockpref, const uint16_t* inblk, int batch, int u, int v,
+                     int* coords, int cap, cudaStream_t stream);
 /* nbr [cap, 9] int32: row index in the source level feeding site i through tap t = ku*3+kv, -1 = absent.
  * transposed=1 builds the data-gradient table of a (strided) SparseConv2d. */
 int pnx_nbr_table(const int* dst_coords, const int* n_dst_ptr, int cap, const uint32_t* src_bm,
-                  const int* src_prefix, int batch, int src_u, int src_v, int stride, int transposed,
-                  int* nbr, cudaStream_t stream);
+                  const int* src_blockpref, const uint16_t* src_inblk, int batch, int src_u, int src_v,
+                  int stride, int transposed, int* nbr, cudaStream_t stream);
 /* x.dense() (sparse_resnet.py:68): feat [n, C] bf16 -> zeroed channels-last canvas [B, V, U, C]
  * (gather=0) or the reverse (gather=1, used by backward). */
 int pnx_scatter_dense(const void* feat, const int* coords, const int* n_ptr, int cap, int channels,

@@ -24,7 +24,10 @@ _SIGS = {
     "pnx_sm_count": [],
     "pnx_scan_u32": [P, I, I, P, P, P, P],
     "pnx_voxelize_bitmap_words": [I, I, I],
-    "pnx_voxelize": [P, I, I, F, F, F, F, I, I, P, P, P, P, P, P, I, P, P, P, P, P, P],
+    "pnx_scan_blocks": [P, I, P, P, P],
+    "pnx_blockcnt_size": [I],
+    "pnx_voxelize": [P, I, I, F, F, F, F, I, I, P, P, P, P, P, P, P, I, P, P, P],
+    "pnx_bucketize": [P, I, I, P, P, P, P, P, P, P],
     "pnx_bn_finalize": [P, I, P, L, P, P, F, F, P, P, P, P, P, P, P],
     "pnx_bn_eval_affine": [I, P, P, P, P, F, P, P, P],
     "pnx_pfn_mean": [P, P, P, P, I, P, P],
@@ -34,9 +37,10 @@ _SIGS = {
     "pnx_pfn_max1": [P, P, P, I, P, P, P, P, P],
     "pnx_pfn_backward": [P, P, P, P, P, P, I, I, F, F, F, F] + [P] * 23 + [P],
     "pnx_sites_out_dim": [I, I],
-    "pnx_sites_dilate": [P, I, I, I, I, P, P],
-    "pnx_sites_coords": [P, P, I, I, I, P, I, P],
-    "pnx_nbr_table": [P, P, I, P, P, I, I, I, I, I, P, P],
+    "pnx_sites_dilate": [P, I, I, I, I, P, P, P, P],
+    "pnx_sites_inblock": [P, I, P, P],
+    "pnx_sites_coords": [P, P, P, I, I, I, P, I, P],
+    "pnx_nbr_table": [P, P, I, P, P, P, I, I, I, I, I, P, P],
     "pnx_scatter_dense": [P, P, P, I, I, I, I, I, P, I, P],
     "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, P, L, I, P],
     "pnx_wgrad": [P, L, I, P, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, P, I, P],

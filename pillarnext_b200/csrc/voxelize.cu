@@ -5,11 +5,15 @@
 //   torch.unique(dim=0, return_inverse=True) over (b, xi, yi)   [lexicographically sorted]
 // WITHOUT a sort: the BEV grid is bounded (B*Gx*Gy cells), so occupancy is a direct-address bitmap
 // laid out in the reference's sort order (bit index = (b*Gx + xi)*GyPad + yi); the rank of a set
-// bit (popcount prefix) IS the sorted-unique pillar id, i.e. `unq_inv`.
-// Points are then bucketed by pillar (CSR, ascending point id inside a bucket) so every later
+// bit IS the sorted-unique pillar id, i.e. `unq_inv`.  Ranks are hierarchical so that no dense prefix
+// array is ever written: per 32-word block (1024 cells) a count is maintained by the marking kernel
+// itself (one extra atomic per NEW pillar), one small scan turns the counts into block offsets, and
+//   rank(cell) = blockpref[block] + popc(words before it in the block) + popc(bits below it).
+// Index generation = 4 kernels: mark | scan(block counts) | rank | coords.
+// pnx_bucketize then groups points by pillar (CSR, ascending point id inside a bucket) so every later
 // per-pillar reduction (mean, max) is a plain in-order loop -- no atomics on any reduction.
 //
-// HBM traffic (algorithmic): 24 B/point read + 4 B/point pillar id + 12 B/pillar coords.
+// HBM traffic (algorithmic, SURVEY 8d): 24 B/point read + 4 B/point pillar id + 12 B/pillar coords.
 #include "pnx_common.cuh"
 
 namespace {
@@ -27,19 +31,20 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
   return v;
 }
 
-// block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix, total in *total
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, total in *total
+template <int kThreads>
 __device__ __forceinline__ int block_excl_scan(int v, int* total) {
-  __shared__ int wsum[kScanThreads / 32];
+  __shared__ int wsum[kThreads / 32];
   __shared__ int wtot;
   int incl = warp_incl_scan(v);
   int w = threadIdx.x >> 5;
   if (pnx::lane_id() == 31) wsum[w] = incl;
   __syncthreads();
   if (w == 0) {
-    int s = (pnx::lane_id() < kScanThreads / 32) ? wsum[pnx::lane_id()] : 0;
+    int s = (pnx::lane_id() < kThreads / 32) ? wsum[pnx::lane_id()] : 0;
     int si = warp_incl_scan(s);
-    if (pnx::lane_id() < kScanThreads / 32) wsum[pnx::lane_id()] = si - s;
-    if (pnx::lane_id() == kScanThreads / 32 - 1) wtot = si;
+    if (pnx::lane_id() < kThreads / 32) wsum[pnx::lane_id()] = si - s;
+    if (pnx::lane_id() == kThreads / 32 - 1) wtot = si;
   }
   __syncthreads();
   int r = incl - v + wsum[w];
@@ -61,7 +66,7 @@ __global__ void scan_reduce_kernel(const uint32_t* __restrict__ in, int n, int* 
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) s += scan_val<kPopc>(in, base + k * kScanThreads + threadIdx.x, n);
   int tot;
-  block_excl_scan(s, &tot);
+  block_excl_scan<kScanThreads>(s, &tot);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
@@ -71,7 +76,7 @@ __global__ void scan_top_kernel(int* __restrict__ block_sums, int n_blocks, int*
     int i = base + threadIdx.x;
     int v = i < n_blocks ? block_sums[i] : 0;
     int tot;
-    int ex = block_excl_scan(v, &tot);
+    int ex = block_excl_scan<kScanThreads>(v, &tot);
     if (i < n_blocks) block_sums[i] = ex + carry;
     carry += tot;
   }
@@ -91,19 +96,50 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, int n, const 
     s += v[k];
   }
   int tot;
-  int ex = block_excl_scan(s, &tot) + block_sums[blockIdx.x];
+  int ex = block_excl_scan<kScanThreads>(s, &tot) + block_sums[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     if (base + k < n) out[base + k] = ex;
     ex += v[k];
   }
-  if (base <= n && n < base + kScanItems) out[n] = ex - 0;  // total (exclusive prefix at n)
+  if (base <= n && n < base + kScanItems) out[n] = ex;  // total (exclusive prefix at n)
+}
+
+// Exclusive scan of per-block counts, two-level: `counts` holds n_blocks block counts followed (at n_blocks
+// rounded up to 4, see super_offset) by one count per superblock of 1024 blocks (maintained by the same atomics /
+// warps that produce the block counts).  One CTA per superblock: prefix of the earlier superblocks (<= a few
+// hundred adds) + one 1024-wide block scan.  One launch, all SMs.
+constexpr int kSuper = 1024;
+__host__ __device__ inline int super_offset(int n_blocks) { return (n_blocks + 3) / 4 * 4; }
+
+__global__ void __launch_bounds__(kSuper) scan_blocks_kernel(const int* __restrict__ counts, int n_blocks,
+                                                             int* __restrict__ out, int* __restrict__ total_out) {
+  __shared__ int s_base;
+  const int* supercnt = counts + super_offset(n_blocks);
+  const int sb = blockIdx.x;
+  if (threadIdx.x < 32) {
+    int acc = 0;
+    for (int j = threadIdx.x; j < sb; j += 32) acc += supercnt[j];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) s_base = acc;
+  }
+  __syncthreads();
+  const int i = sb * kSuper + threadIdx.x;
+  const int v = i < n_blocks ? counts[i] : 0;
+  int tot;
+  const int ex = block_excl_scan<kSuper>(v, &tot) + s_base;
+  if (i < n_blocks) out[i] = ex;
+  if (sb == gridDim.x - 1 && threadIdx.x == 0) {
+    out[n_blocks] = s_base + tot;
+    if (total_out) *total_out = s_base + tot;
+  }
 }
 
 }  // namespace
 
 // Exclusive prefix sum of popcounts (popc=1) or raw int32 values (popc=0).
-// out has n+1 entries (out[n] = total); block_sums scratch needs ceil(n/2048)+1 ints.
+// out has n+1 entries (out[n] = total); block_sums scratch needs ceil((n+1)/2048)+1 ints.
 extern "C" int pnx_scan_u32(const uint32_t* in, int n, int popc, int* out, int* block_sums, int* total_out,
                             cudaStream_t stream) {
   PNX_CHECK_ARG(n >= 0, "n < 0");
@@ -121,6 +157,18 @@ extern "C" int pnx_scan_u32(const uint32_t* in, int n, int popc, int* out, int* 
   return PNX_OK;
 }
 
+// Size (in int32) of a block-count buffer: block counts + superblock counts (see scan_blocks_kernel).
+extern "C" int pnx_blockcnt_size(int n_blocks) { return super_offset(n_blocks) + (n_blocks + kSuper - 1) / kSuper + 4; }
+
+// Exclusive scan of the per-block counts of a bitmap in ONE launch.  counts = pnx_blockcnt_size(n_blocks) ints
+// (block counts + superblock counts); out [n_blocks+1] (out[n_blocks] = total), total_out optional.
+extern "C" int pnx_scan_blocks(const int* counts, int n_blocks, int* out, int* total_out, cudaStream_t stream) {
+  PNX_CHECK_ARG(n_blocks >= 1, "n_blocks");
+  scan_blocks_kernel<<<(n_blocks + kSuper - 1) / kSuper, kSuper, 0, stream>>>(counts, n_blocks, out, total_out);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
 namespace {
 
 struct VoxGeom {
@@ -128,10 +176,10 @@ struct VoxGeom {
   int gx, gy, vwords, batch;
 };
 
-// V1: cell index per point + occupancy bitmap.  One thread per point; the block stages its
-// 256 points (6 KB) through shared memory with 128-bit coalesced loads.
+// V1: cell index per point + occupancy bitmap + per-block pillar counts.  One thread per point; the block
+// stages its 256 points (6 KB) through shared memory with 128-bit coalesced loads.
 __global__ void __launch_bounds__(256) vox_mark_kernel(const float* __restrict__ points, int n, VoxGeom g,
-                                                       uint32_t* __restrict__ bitmap,
+                                                       uint32_t* __restrict__ bitmap, int* __restrict__ blockcnt,
                                                        int* __restrict__ cell_of_point) {
   __shared__ float4 stage[256 * 6 / 4];
   const long long first = (long long)blockIdx.x * 256;
@@ -164,36 +212,59 @@ __global__ void __launch_bounds__(256) vox_mark_kernel(const float* __restrict__
   if (keep) {
     const int xi = (int)cx, yi = (int)cy;  // :106 trunc
     const int word = (b * g.gx + xi) * g.vwords + (yi >> 5);
-    atomicOr(&bitmap[word], 1u << (yi & 31));
+    const uint32_t bit = 1u << (yi & 31);
+    const uint32_t old = atomicOr(&bitmap[word], bit);
+    if (!(old & bit)) atomicAdd(&blockcnt[word >> 5], 1);  // first point of a new pillar
     cell = word * 32 + (yi & 31);
   }
   cell_of_point[first + threadIdx.x] = cell;
 }
 
-// V2b: pillar id per point (= rank of its bit) and per-pillar point counts.
+// per-superblock (1024 blocks) totals of the block counts (only ~B*100 counters: atomics from the marking kernel
+// would all collide on them)
+__global__ void super_reduce_kernel(const int* __restrict__ blockcnt, int n_blocks, int* __restrict__ supercnt) {
+  __shared__ int red[8];
+  const int base = blockIdx.x * 1024;
+  int acc = 0;
+  for (int k = threadIdx.x; k < 1024; k += 256) acc += (base + k < n_blocks) ? blockcnt[base + k] : 0;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    supercnt[blockIdx.x] = t;
+  }
+}
+
+// V2b: pillar id per point (= hierarchical rank of its bit) and per-pillar point counts.
 __global__ void vox_rank_kernel(const int* __restrict__ cell_of_point, int n, const uint32_t* __restrict__ bitmap,
-                                const int* __restrict__ word_prefix, int* __restrict__ pillar_of_point,
-                                uint32_t* __restrict__ bucket_cnt) {
+                                const int* __restrict__ blockpref, const uint16_t* __restrict__ inblk,
+                                int* __restrict__ pillar_of_point, uint32_t* __restrict__ bucket_cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int cell = cell_of_point[i];
   int pid = -1;
   if (cell >= 0) {
-    int word = cell >> 5, bit = cell & 31;
-    pid = word_prefix[word] + __popc(bitmap[word] & ((1u << bit) - 1u));
-    atomicAdd(&bucket_cnt[pid], 1u);  // integer count: order-independent
+    const int word = cell >> 5, bit = cell & 31;
+    pid = blockpref[word >> 5] + (int)inblk[word] + __popc(bitmap[word] & ((1u << bit) - 1u));
+    if (bucket_cnt) atomicAdd(&bucket_cnt[pid], 1u);  // integer count: order-independent
   }
   pillar_of_point[i] = pid;
 }
 
-// V2c: coords (b, yi, xi) of every pillar in sorted-unique order. One thread per bitmap word.
-__global__ void vox_coords_kernel(const uint32_t* __restrict__ bitmap, const int* __restrict__ word_prefix,
-                                  int n_words, VoxGeom g, int* __restrict__ coords, int cap) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= n_words) return;
-  uint32_t bits = bitmap[w];
+// V2c: coords (b, yi, xi) of every pillar in sorted-unique order.  One warp per 32-word block (one coalesced
+// 128-byte read), lanes = words, in-block offsets by a warp scan of the popcounts.
+__global__ void vox_coords_kernel(const uint32_t* __restrict__ bitmap, const int* __restrict__ blockpref, int n_words,
+                                  VoxGeom g, int* __restrict__ coords, int cap, uint16_t* __restrict__ inblk) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t bits = w < n_words ? bitmap[w] : 0u;
+  const int cnt = __popc(bits);
+  const int incl = warp_incl_scan(cnt);
+  if (w < n_words) inblk[w] = (uint16_t)(incl - cnt);  // in-block prefix: used by the rank kernel and the rulebook
   if (!bits) return;
-  int idx = word_prefix[w];
+  int idx = blockpref[w >> 5] + incl - cnt;
   int row = w / g.vwords, vw = w - row * g.vwords;
   int b = row / g.gx, xi = row - b * g.gx;
   while (bits) {
@@ -235,47 +306,59 @@ __global__ void vox_sort_kernel(const int* __restrict__ bucket_tmp, const int* _
 }  // namespace
 
 extern "C" size_t pnx_voxelize_bitmap_words(int batch, int gx, int gy) {
-  return (size_t)batch * gx * ((gy + 31) / 32);
+  size_t w = (size_t)batch * gx * ((gy + 31) / 32);
+  return (w + 31) / 32 * 32;  // whole 32-word blocks
 }
 
-// See include/pnx.h for the contract.  All buffers are caller-owned device memory.
+// Index generation (V1-V2).  See include/pnx.h for the contract.  All buffers are caller-owned device memory.
 extern "C" int pnx_voxelize(const float* points, int n_points, int batch, float min_x, float min_y, float vs_x,
-                            float vs_y, int gx, int gy, uint32_t* bitmap, int* word_prefix, int* scan_scratch,
+                            float vs_y, int gx, int gy, uint32_t* bitmap, uint16_t* inblk, int* blockcnt, int* blockpref,
                             int* cell_of_point, int* pillar_of_point, int* coords, int cap_pillars,
-                            uint32_t* bucket_cnt, int* bucket_off, int* bucket_tmp, int* bucket_pts,
-                            int* counts /* [0]=P, [1]=Nv */, cudaStream_t stream) {
+                            uint32_t* bucket_cnt, int* counts /* [0]=P */, cudaStream_t stream) {
   PNX_CHECK_ARG(n_points >= 0 && batch > 0 && gx > 0 && gy > 0, "bad sizes");
   PNX_CHECK_ARG(vs_x > 0.f && vs_y > 0.f, "voxel size must be positive");
   PNX_CHECK_ARG((long long)batch * gx * ((gy + 31) / 32) * 32 < 2147483647LL, "grid too large for int32 cell ids");
   PNX_CHECK_ARG(cap_pillars >= 0, "cap_pillars");
   VoxGeom g{min_x, min_y, vs_x, vs_y, gx, gy, (gy + 31) / 32, batch};
-  const int n_words = batch * gx * g.vwords;
+  const int n_words = (int)pnx_voxelize_bitmap_words(batch, gx, gy);
+  const int n_blocks = n_words / 32;
   PNX_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)n_words * 4, stream));
-  PNX_CUDA(cudaMemsetAsync(bucket_cnt, 0, (size_t)(cap_pillars + 1) * 4 * 2, stream));  // counts + cursors
-  PNX_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int), stream));
+  PNX_CUDA(cudaMemsetAsync(blockcnt, 0, (size_t)pnx_blockcnt_size(n_blocks) * 4, stream));
+  int* supercnt = blockcnt + super_offset(n_blocks);
+  if (bucket_cnt) PNX_CUDA(cudaMemsetAsync(bucket_cnt, 0, (size_t)(cap_pillars + 1) * 4 * 2, stream));  // counts + cursors
   if (n_points > 0) {
-    vox_mark_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(points, n_points, g, bitmap, cell_of_point);
+    vox_mark_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(points, n_points, g, bitmap, blockcnt, cell_of_point);
     PNX_CHECK_LAUNCH();
   }
-  int rc = pnx_scan_u32(bitmap, n_words, 1, word_prefix, scan_scratch, counts + 0, stream);
+  super_reduce_kernel<<<(n_blocks + 1023) / 1024, 256, 0, stream>>>(blockcnt, n_blocks, supercnt);
+  PNX_CHECK_LAUNCH();
+  int rc = pnx_scan_blocks(blockcnt, n_blocks, blockpref, counts, stream);
   if (rc) return rc;
-  vox_coords_kernel<<<pnx_cdiv(n_words, 256), 256, 0, stream>>>(bitmap, word_prefix, n_words, g, coords,
-                                                                cap_pillars);
+  vox_coords_kernel<<<pnx_cdiv(n_words, 256), 256, 0, stream>>>(bitmap, blockpref, n_words, g, coords, cap_pillars,
+                                                                inblk);
   PNX_CHECK_LAUNCH();
   if (n_points > 0) {
-    vox_rank_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(cell_of_point, n_points, bitmap, word_prefix,
+    vox_rank_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(cell_of_point, n_points, bitmap, blockpref, inblk,
                                                                  pillar_of_point, bucket_cnt);
     PNX_CHECK_LAUNCH();
   }
-  // bucket offsets = exclusive scan of per-pillar counts over the pillar CAPACITY (device-side P unknown to host)
-  rc = pnx_scan_u32(bucket_cnt, cap_pillars, 0, bucket_off, scan_scratch, counts + 1, stream);
+  return PNX_OK;
+}
+
+// V3 preparation: CSR grouping of the kept points by pillar (ascending point id inside a pillar).
+// bucket_cnt comes from pnx_voxelize ([cap+1] counts followed by [cap+1] zeroed cursors); counts[1] receives Nv.
+extern "C" int pnx_bucketize(const int* pillar_of_point, int n_points, int cap_pillars, uint32_t* bucket_cnt,
+                             int* scan_scratch, int* bucket_off, int* bucket_tmp, int* bucket_pts, int* counts,
+                             cudaStream_t stream) {
+  PNX_CHECK_ARG(n_points >= 0 && cap_pillars >= 0, "sizes");
+  int rc = pnx_scan_u32(bucket_cnt, cap_pillars, 0, bucket_off, scan_scratch, counts + 1, stream);
   if (rc) return rc;
   if (n_points > 0) {
     uint32_t* cursor = bucket_cnt + cap_pillars + 1;
     vox_fill_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(pillar_of_point, n_points, bucket_off, cursor,
                                                                  bucket_tmp);
-    vox_sort_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(bucket_tmp, pillar_of_point, bucket_off,
-                                                                 n_points, counts + 1, bucket_pts);
+    vox_sort_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(bucket_tmp, pillar_of_point, bucket_off, n_points,
+                                                                 counts + 1, bucket_pts);
     PNX_CHECK_LAUNCH();
   }
   return PNX_OK;

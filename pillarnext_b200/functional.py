@@ -151,7 +151,7 @@ class ConvFn(torch.autograd.Function):
             g = torch.empty_like(dy)
             ops.relu_bwd(dy, out, rows, cout, g)
             dy = g
-        dbias = dy[:, :cout].float().sum(0) if ctx.has_bias else None
+        dbias = torch.sum(dy[:, :cout], dim=0, dtype=torch.float32) if ctx.has_bias else None   # fp32 accumulate, no fp32 copy
         dx = None
         if ctx.needs_input_grad[0]:
             wd = packed(w, layout, "dgrad", spec.d_flip)            # [taps_d, Cin, Cout]

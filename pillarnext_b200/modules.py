@@ -66,7 +66,7 @@ class Pyramid:
 def build_pyramid(vox, strides):
     """Level 0 = pillars; level s+1 = SparseConv2d(k3,p1,stride) dilation of level s.  One host sync for all
     site counts.  Returns Pyramid with levels[0..4], entry specs (regular conv) and subm specs per stage."""
-    lv0 = ops.level_from_bitmap(vox.bitmap, vox.word_prefix, vox.counts[0:1], vox.batch, vox.gx, vox.gy)
+    lv0 = ops.level_from_bitmap(vox.bitmap, vox.blockpref, vox.counts[0:1], vox.batch, vox.gx, vox.gy, inblk=vox.inblk)
     levels = [lv0]
     for s in strides:
         levels.append(ops.level_dilate(levels[-1], int(s)))

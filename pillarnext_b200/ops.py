@@ -60,8 +60,9 @@ class Voxels:
         return self.P, self.Nv
 
 
-def voxelize(points, batch, voxel_size, pc_range):
-    """V1-V3 index generation (pnx_voxelize). points [N,6] fp32 cuda (b,x,y,z,i,t)."""
+def voxelize(points, batch, voxel_size, pc_range, buckets=True):
+    """V1-V2 index generation (pnx_voxelize) and, with buckets=True, the CSR grouping the PFN needs
+    (pnx_bucketize). points [N,6] fp32 cuda (b,x,y,z,i,t)."""
     assert points.is_cuda and points.dtype == torch.float32 and points.dim() == 2 and points.shape[1] == 6, \
         "points must be a CUDA float32 [N, 6] tensor (batch_idx, x, y, z, intensity, time)"
     points = points.contiguous()
@@ -80,21 +81,26 @@ def voxelize(points, batch, voxel_size, pc_range):
     v.vs_x, v.vs_y = _f32(voxel_size[0]), _f32(voxel_size[1])
     i32 = dict(dtype=torch.int32, device=dev)
     v.bitmap = torch.empty(words, **i32)
-    v.word_prefix = torch.empty(words + 1, **i32)
-    scratch = torch.empty(max(words, cap_p) // 2048 + 4, **i32)
+    v.blockcnt = torch.empty(L.pnx_blockcnt_size(words // 32), **i32)
+    v.inblk = torch.empty(words, dtype=torch.int16, device=dev)
+    v.blockpref = torch.empty(words // 32 + 1, **i32)
     cell = torch.empty(max(n, 1), **i32)
     v.pillar_of_point = torch.empty(max(n, 1), **i32)
     v.coords = torch.empty(max(cap_p, 1), 3, **i32)
-    bucket_cnt = torch.empty(2 * (cap_p + 1), **i32)
-    v.bucket_off = torch.empty(cap_p + 1, **i32)
-    bucket_tmp = torch.empty(max(n, 1), **i32)
-    v.bucket_pts = torch.empty(max(n, 1), **i32)
-    v.counts = torch.empty(2, **i32)
-    _count(11 if n > 0 else 7)
-    check(L.pnx_voxelize(ptr(points), n, batch, v.min_x, v.min_y, v.vs_x, v.vs_y, gx, gy, ptr(v.bitmap),
-                         ptr(v.word_prefix), ptr(scratch), ptr(cell), ptr(v.pillar_of_point), ptr(v.coords), cap_p,
-                         ptr(bucket_cnt), ptr(v.bucket_off), ptr(bucket_tmp), ptr(v.bucket_pts), ptr(v.counts),
-                         stream()))
+    bucket_cnt = torch.empty(2 * (cap_p + 1), **i32) if buckets else None
+    v.counts = torch.zeros(2, **i32)
+    _count(5 if n > 0 else 3)
+    check(L.pnx_voxelize(ptr(points), n, batch, v.min_x, v.min_y, v.vs_x, v.vs_y, gx, gy, ptr(v.bitmap), ptr(v.inblk),
+                         ptr(v.blockcnt), ptr(v.blockpref), ptr(cell), ptr(v.pillar_of_point), ptr(v.coords), cap_p,
+                         ptr(bucket_cnt) if buckets else None, ptr(v.counts), stream()))
+    if buckets:
+        scratch = torch.empty(cap_p // 2048 + 4, **i32)
+        v.bucket_off = torch.empty(cap_p + 1, **i32)
+        bucket_tmp = torch.empty(max(n, 1), **i32)
+        v.bucket_pts = torch.empty(max(n, 1), **i32)
+        _count(5 if n > 0 else 3)
+        check(L.pnx_bucketize(ptr(v.pillar_of_point), n, cap_p, ptr(bucket_cnt), ptr(scratch), ptr(v.bucket_off),
+                              ptr(bucket_tmp), ptr(v.bucket_pts), ptr(v.counts), stream()))
     return v
 
 
@@ -202,51 +208,82 @@ def pfn_backward(v, fwd, dfeat, w1, gamma0, gamma1):
 
 # --------------------------------------------------------------------------------- sites / rulebook
 class Level:
-    """Active-site set of one backbone level: bitmap (b,u,v), prefix, coords [n,3], count."""
+    """Active-site set of one backbone level: bitmap (b,u,v), inblk (u16 per word), blockpref, coords [n,3], count."""
     pass
 
 
-def _scan_bitmap(bm):
-    words = bm.numel()
-    prefix = torch.empty(words + 1, dtype=torch.int32, device=bm.device)
-    scratch = torch.empty(words // 2048 + 4, dtype=torch.int32, device=bm.device)
-    count = torch.empty(1, dtype=torch.int32, device=bm.device)
-    _count(3)
-    check(lib().pnx_scan_u32(ptr(bm), words, 1, ptr(prefix), ptr(scratch), ptr(count), stream()))
-    return prefix, count
-
-
-def level_from_bitmap(bm, prefix, count, batch, U, V):
+def level_from_bitmap(bm, blockpref, count, batch, U, V, inblk=None):
+    """Wrap an existing bitmap (e.g. the voxelizer's level 0); inblk is computed here when not given."""
     lv = Level()
-    lv.bm, lv.prefix, lv.count, lv.batch, lv.U, lv.V = bm, prefix, count, batch, U, V
+    lv.bm, lv.blockpref, lv.count, lv.batch, lv.U, lv.V = bm, blockpref, count, batch, U, V
+    if inblk is None:
+        inblk = torch.empty(bm.numel(), dtype=torch.int16, device=bm.device)
+        _count(1)
+        check(lib().pnx_sites_inblock(ptr(bm), bm.numel(), ptr(inblk), stream()))
+    lv.inblk = inblk
     lv.n = None
     lv.coords = None
     return lv
 
 
+def level_from_mask_words(bm, batch, U, V):
+    """Level from a raw bitmap (words padded to whole blocks): block counts, scan and in-block prefix."""
+    assert bm.numel() % 32 == 0
+    blocks = bm.numel() // 32
+    inblk = torch.empty(bm.numel(), dtype=torch.int16, device=bm.device)
+    _count(1)
+    check(lib().pnx_sites_inblock(ptr(bm), bm.numel(), ptr(inblk), stream()))
+    cnt = torch.zeros(lib().pnx_blockcnt_size(blocks), dtype=torch.int32, device=bm.device)
+    # block counts = in-block prefix of the last word + its popcount (host-side torch plumbing; test helper only)
+    w = bm.view(-1, 32)
+    pc = torch.zeros_like(w)
+    x = w.clone().to(torch.int64) & 0xFFFFFFFF
+    for _ in range(32):
+        pc += (x & 1).to(torch.int32)
+        x >>= 1
+    cnt[:blocks] = pc.sum(1)
+    so = (blocks + 3) // 4 * 4
+    nsb = (blocks + 1023) // 1024
+    padded = torch.zeros(nsb * 1024, dtype=torch.int32, device=bm.device)
+    padded[:blocks] = cnt[:blocks]
+    cnt[so:so + nsb] = padded.view(nsb, 1024).sum(1)
+    blockpref = torch.empty(blocks + 1, dtype=torch.int32, device=bm.device)
+    count = torch.empty(1, dtype=torch.int32, device=bm.device)
+    _count(1)
+    check(lib().pnx_scan_blocks(ptr(cnt), blocks, ptr(blockpref), ptr(count), stream()))
+    return level_from_bitmap(bm, blockpref, count, batch, U, V, inblk=inblk)
+
+
 def level_dilate(src, stride):
     L = lib()
     uo, vo = L.pnx_sites_out_dim(src.U, stride), L.pnx_sites_out_dim(src.V, stride)
-    bm = torch.empty(src.batch * uo * ((vo + 31) // 32), dtype=torch.int32, device=src.bm.device)
-    _count(1)
-    check(L.pnx_sites_dilate(ptr(src.bm), src.batch, src.U, src.V, stride, ptr(bm), stream()))
-    prefix, count = _scan_bitmap(bm)
-    return level_from_bitmap(bm, prefix, count, src.batch, uo, vo)
+    words = (src.batch * uo * ((vo + 31) // 32) + 31) // 32 * 32
+    dev = src.bm.device
+    bm = torch.empty(words, dtype=torch.int32, device=dev)
+    inblk = torch.empty(words, dtype=torch.int16, device=dev)
+    cnt = torch.empty(L.pnx_blockcnt_size(words // 32), dtype=torch.int32, device=dev)
+    blockpref = torch.empty(words // 32 + 1, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    _count(2)
+    check(L.pnx_sites_dilate(ptr(src.bm), src.batch, src.U, src.V, stride, ptr(bm), ptr(inblk), ptr(cnt), stream()))
+    check(L.pnx_scan_blocks(ptr(cnt), words // 32, ptr(blockpref), ptr(count), stream()))
+    return level_from_bitmap(bm, blockpref, count, src.batch, uo, vo, inblk=inblk)
 
 
 def level_coords(lv, n):
     lv.n = n
     lv.coords = torch.empty(max(n, 1), 3, dtype=torch.int32, device=lv.bm.device)
     _count(1)
-    check(lib().pnx_sites_coords(ptr(lv.bm), ptr(lv.prefix), lv.batch, lv.U, lv.V, ptr(lv.coords), n, stream()))
+    check(lib().pnx_sites_coords(ptr(lv.bm), ptr(lv.blockpref), ptr(lv.inblk), lv.batch, lv.U, lv.V, ptr(lv.coords), n,
+                                 stream()))
     return lv.coords
 
 
 def nbr_table(dst, src, stride, transposed):
     nbr = torch.empty(max(dst.n, 1), 9, dtype=torch.int32, device=dst.bm.device)
     _count(1)
-    check(lib().pnx_nbr_table(ptr(dst.coords), ptr(dst.count), dst.n, ptr(src.bm), ptr(src.prefix), src.batch, src.U,
-                              src.V, stride, 1 if transposed else 0, ptr(nbr), stream()))
+    check(lib().pnx_nbr_table(ptr(dst.coords), ptr(dst.count), dst.n, ptr(src.bm), ptr(src.blockpref), ptr(src.inblk),
+                              src.batch, src.U, src.V, stride, 1 if transposed else 0, ptr(nbr), stream()))
     return nbr
 
 

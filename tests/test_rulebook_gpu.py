@@ -15,15 +15,15 @@ def make_level(mask):
     bits = torch.zeros(B, U, vw * 32, dtype=torch.int64)
     bits[:, :, :V] = mask.long()
     w = (bits.view(B, U, vw, 32) << torch.arange(32)).sum(-1)
-    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
-    bm = w.reshape(-1).cuda()
-    prefix, count = ops._scan_bitmap(bm)
-    return ops.level_from_bitmap(bm, prefix, count, B, U, V)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).reshape(-1)
+    pad = (-w.numel()) % 32
+    bm = torch.cat([w, torch.zeros(pad, dtype=torch.int32)]).cuda()
+    return ops.level_from_mask_words(bm, B, U, V)
 
 
 def unpack(lv):
     vw = (lv.V + 31) // 32
-    w = lv.bm.cpu().long() & 0xFFFFFFFF
+    w = lv.bm.cpu().long()[:lv.batch * lv.U * vw] & 0xFFFFFFFF
     bits = (w.view(lv.batch, lv.U, vw, 1) >> torch.arange(32)) & 1
     return bits.reshape(lv.batch, lv.U, vw * 32)[:, :, :lv.V].bool()
 
