@@ -226,9 +226,10 @@ def main():
         t0.record()
         for i in range(n):
             if e2e:
-                ex = to_device(host[i % nb], dev, non_blocking=True)   # pinned host -> device inside the timed region
+                ex = resident[i % nb] if os.environ.get("PNX_E2E_NOCOPY") else to_device(host[i % nb], dev, non_blocking=True)   # pinned host -> device inside the timed region
                 loss = step(ex)
-                _ = loss.item()                                        # device -> host read of the step's result
+                if not os.environ.get("PNX_E2E_NOITEM"):
+                    _ = loss.item()                                    # device -> host read of the step's result
             else:
                 step(resident[i % nb])
         t1.record()

@@ -190,6 +190,22 @@ int pnx_add_relu(const void* a, long long lda, const void* b, long long ldb, lon
 int pnx_relu_bwd(const void* dy, long long lddy, const void* y, long long ldy, long long M, int C, void* g,
                  long long ldg, int accumulate, cudaStream_t stream);
 
+/* ---------------------------------------------------------------- L1 fused CenterPoint loss (forward + gradient)
+ * One task: out/dout [B*H*W, npad] fp32 channels-last head output (columns reg2|height1|dim3|rot2|vel2|hm C|pad)
+ * and its gradient (fully written), labels in the reference's collate format (det3d/datasets/pipelines/assign.py:
+ * 42-48): hm_gt [B,C,H,W] f32, anno [B,M,10] f32, ind [B,M] i64, mask [B,M] u8, cat [B,M] i64, gt_boxes [B,M,7] f32.
+ * acc [16] fp64 (zeroed by the caller) receives the partial sums; pnx_center_loss_finalize turns acc [n_tasks,16]
+ * into res [n_tasks,16] = {loss, hm_loss, loc_loss, iou_reg_loss, num_positive, loc_loss_elem[10]} and total[0].
+ * Replaces CenterHead.loss (centerhead.py:142-229) + FastFocalLoss/RegLoss/IouRegLoss (centerloss.py:8-176). */
+int pnx_center_loss_task(const float* out, float* dout, const float* hm_gt, const float* anno,
+                         const long long* ind, const unsigned char* mask, const long long* cat,
+                         const float* gt_boxes, int B, int H, int W, int npad, int C, int M, int off_reg,
+                         int off_height, int off_dim, int off_rot, int off_vel, int off_hm, float sx, float sy,
+                         float ox, float oy, float weight, const float* code_w_host, int with_iou, double* acc,
+                         cudaStream_t stream);
+int pnx_center_loss_finalize(const double* acc, int n_tasks, const float* weights_dev, const float* code_w_dev,
+                             const int* with_iou_dev, float* res, float* total, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

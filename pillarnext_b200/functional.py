@@ -353,3 +353,43 @@ class ToBF16RowsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d):
         return d.float(), None
+
+
+# ------------------------------------------------------------------------------------------- fused loss
+class CenterLossFn(torch.autograd.Function):
+    """CenterHead.loss (centerhead.py:142-229) for all tasks: value and d(loss)/d(head output) from libpnx
+    (pnx_center_loss_task / _finalize).  Inputs: one channels-last fp32 head matrix [B*H*W, npad] per task."""
+
+    @staticmethod
+    def forward(ctx, meta, *outs):
+        import ctypes
+        from ._lib import check, lib, ptr, stream
+        T = len(outs)
+        dev = outs[0].device
+        acc = torch.zeros(T, 16, dtype=torch.float64, device=dev)
+        res = torch.empty(T, 16, dtype=torch.float32, device=dev)
+        total = torch.empty(1, dtype=torch.float32, device=dev)
+        douts = []
+        cw = (ctypes.c_float * 10)(*meta["code_weights"])
+        for t, out in enumerate(outs):
+            m = meta["tasks"][t]
+            ex = m["labels"]
+            dout = torch.empty_like(out)
+            ops._count(2)
+            check(lib().pnx_center_loss_task(ptr(out), ptr(dout), ptr(ex["hm"]), ptr(ex["anno_box"]), ptr(ex["ind"]),
+                                             ptr(ex["mask"]), ptr(ex["cat"]), ptr(ex["gt_boxes"]), m["B"], m["H"], m["W"],
+                                             m["npad"], m["C"], m["M"], m["off"]["reg"], m["off"]["height"], m["off"]["dim"],
+                                             m["off"]["rot"], m["off"]["vel"], m["off"]["hm"], m["sx"], m["sy"], m["ox"], m["oy"],
+                                             meta["weight"], ctypes.cast(cw, ctypes.c_void_p), 1 if meta["with_reg_iou"] else 0,
+                                             ptr(acc[t]), stream()))
+            douts.append(dout)
+        ops._count(1)
+        check(lib().pnx_center_loss_finalize(ptr(acc), T, ptr(meta["weights_dev"]), ptr(meta["code_w_dev"]),
+                                             ptr(meta["with_iou_dev"]), ptr(res), ptr(total), stream()))
+        ctx.douts = douts
+        ctx.mark_non_differentiable(res)
+        return total[0], res
+
+    @staticmethod
+    def backward(ctx, g_total, _g_res):
+        return (None,) + tuple(d.mul_(g_total) for d in ctx.douts)

@@ -379,11 +379,14 @@ class SepHead(nn.Module):
         wb = torch.cat(rows_w + ([wb[tot:]] if npad > tot else []), 0)
         bb = torch.cat(rows_b + ([bb[tot:]] if npad > tot else []), 0)
         out, _ = Fn.conv(y, wb, bb, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), out_fp32=True)
-        out = out.view(B, H, W, npad)
-        ret, o = dict(), 0
+        out4 = out.view(B, H, W, npad)
+        ret, o, offs = dict(), 0, {}
         for i, n in enumerate(names):
-            ret[n] = out[..., o:o + classes[i]].permute(0, 3, 1, 2)
+            ret[n] = out4[..., o:o + classes[i]].permute(0, 3, 1, 2)
+            offs[n] = o
             o += classes[i]
+        # lets CenterHead.loss run the fused kernel on the channels-last matrix the GEMM wrote (no gathers/permutes)
+        ret["hm"]._pnx_raw = dict(out=out, npad=npad, off=offs, B=B, H=H, W=W, C=classes[names.index("hm")])
         return ret
 
     def forward(self, x):
@@ -434,9 +437,41 @@ class CenterHead(nn.Module):
         """centerhead.py:142-229 (nuScenes / Waymo without the `iou` head)."""
         if self.with_iou:
             raise NotImplementedError("the Waymo `iou` head loss (rotated aligned IoU target) is a 'next' row (F2)")
+        raws = [getattr(pd.get("hm"), "_pnx_raw", None) for pd in preds_dicts]
+        if all(r is not None for r in raws) and all(set(r["off"]) >= {"reg", "height", "dim", "rot", "vel", "hm"} for r in raws):
+            return self._fused_loss(example, preds_dicts, raws)
         return L.center_loss(example, preds_dicts, self.class_names, self.weight, self.code_weights, self.with_reg_iou,
                              getattr(self, "voxel_size", None), getattr(self, "pc_range", None),
                              getattr(self, "out_size_factor", None))
+
+    def _fused_loss(self, example, preds_dicts, raws):
+        """Same value/gradient as loss.center_loss, from the fused libpnx kernels (3 launches per task instead of ~150)."""
+        dev = raws[0]["out"].device
+        if getattr(self, "_loss_consts", None) is None or self._loss_consts[0].device != dev:
+            self._loss_consts = (torch.full((len(raws),), self.weight, dtype=torch.float32, device=dev),
+                                 torch.tensor(self.code_weights, dtype=torch.float32, device=dev),
+                                 torch.full((len(raws),), 1 if self.with_reg_iou else 0, dtype=torch.int32, device=dev))
+        tasks = []
+        for t, r in enumerate(raws):
+            labels = {k: example[k][t].contiguous() for k in ("hm", "anno_box", "ind", "mask", "cat", "gt_boxes")}
+            assert labels["hm"].dtype == torch.float32 and labels["ind"].dtype == torch.int64 and labels["mask"].dtype == torch.uint8
+            osf = self.out_size_factor[t] if self.with_reg_iou else 1
+            vs = self.voxel_size if self.with_reg_iou else [1.0, 1.0]
+            pr = self.pc_range if self.with_reg_iou else [0.0, 0.0]
+            tasks.append(dict(labels=labels, B=r["B"], H=r["H"], W=r["W"], npad=r["npad"], C=r["C"], M=labels["ind"].shape[1],
+                              off=r["off"], sx=float(osf * vs[0]), sy=float(osf * vs[1]), ox=float(pr[0]), oy=float(pr[1])))
+        meta = dict(tasks=tasks, weight=self.weight, code_weights=self.code_weights, with_reg_iou=self.with_reg_iou,
+                    weights_dev=self._loss_consts[0], code_w_dev=self._loss_consts[1], with_iou_dev=self._loss_consts[2])
+        total, res = Fn.CenterLossFn.apply(meta, *[r["out"] for r in raws])
+        rets = []
+        for t in range(len(raws)):
+            ret = OrderedDict()
+            ret.update({"task": self.class_names[t], "loss": res[t, 0], "hm_loss": res[t, 1], "loc_loss": res[t, 2],
+                        "loc_loss_elem": res[t, 5:15], "num_positive": res[t, 4]})
+            if self.with_reg_iou:
+                ret.update({"iou_reg_loss": res[t, 3]})
+            rets.append(ret)
+        return total, rets
 
     @torch.no_grad()
     def predict(self, example, preds_dicts, test_cfg):

@@ -217,3 +217,34 @@ def test_sep_head_batched_equals_per_head():
         a, b = getattr(sh, n)[3].bias.grad, seqs[n][3].bias.grad
         assert rel(a, b) < 1e-2, (n, rel(a, b))
     assert rel(sh.deblock.conv.conv.weight.grad, deb_w.grad) < 0.1
+
+
+def test_fused_center_loss_matches_torch_loss():
+    """pnx_center_loss_* (fused CUDA) vs pillarnext_b200.loss.center_loss (torch restatement pinned to the reference's
+    numbers in tests/test_oracle_cpu.py): loss values 1e-4 relative, gradient w.r.t. the head output 1e-3 of its scale."""
+    from pillarnext_b200 import loss as PL
+    cfg = synth.tiny_config(128, [["car"], ["truck", "construction_vehicle"]])
+    torch.manual_seed(0)
+    head = modules.CenterHead(256, cfg["tasks"], cfg["weight"], cfg["code_weights"], cfg["common_heads"], cfg["head_strides"],
+                              with_reg_iou=True, voxel_size=cfg["voxel_size"], pc_range=cfg["pc_range"],
+                              out_size_factor=cfg["out_size_factor"]).cuda().train()
+    ex = synth.make_batch([0, 1, 2], 1000, cfg, n_boxes=30)
+    exg = {k: [e.cuda() for e in v] for k, v in ex.items() if isinstance(v, list) and torch.is_tensor(v[0])}
+    x = torch.randn(3, 256, 16, 16, device="cuda")
+    preds = head(x)
+    raws = [p["hm"]._pnx_raw["out"] for p in preds]
+    total, rets = head.loss(exg, preds)                       # fused path
+    gf = torch.autograd.grad(total, raws, retain_graph=True)
+    preds2 = [{k: v for k, v in p.items()} for p in preds]    # plain dict views without the fast-path marker
+    for p in preds2:
+        p["hm"] = p["hm"] + 0
+    total2, rets2 = PL.center_loss(exg, preds2, cfg["tasks"], cfg["weight"], cfg["code_weights"], True, cfg["voxel_size"],
+                                   cfg["pc_range"], cfg["out_size_factor"])
+    gt = torch.autograd.grad(total2, raws)
+    assert abs(total.item() - total2.item()) < 1e-4 * abs(total2.item()), (total.item(), total2.item())
+    for t in range(len(rets)):
+        for k in ("hm_loss", "loc_loss", "iou_reg_loss", "num_positive"):
+            assert abs(float(rets[t][k]) - float(rets2[t][k])) < 1e-4 * max(1.0, abs(float(rets2[t][k]))), (t, k)
+        assert torch.allclose(rets[t]["loc_loss_elem"], rets2[t]["loc_loss_elem"], rtol=1e-4, atol=1e-6)
+        e = (gf[t] - gt[t]).abs().max().item()
+        assert e < 1e-3 * gt[t].abs().max().item(), (t, e, gt[t].abs().max().item())
