@@ -190,6 +190,15 @@ int pnx_add_relu(const void* a, long long lda, const void* b, long long ldb, lon
 int pnx_relu_bwd(const void* dy, long long lddy, const void* y, long long ldy, long long M, int C, void* g,
                  long long ldg, int accumulate, cudaStream_t stream);
 
+/* ---------------------------------------------------------------- head final 3x3 convs as GEMM + stencil
+ * out[m, j] = bias16[j] + sum_{t<9} Z[m + off_t, t*16 + j] on a B x H x W channels-last image (zero padding),
+ * Z [M, ldz] fp32 = y . Wz^T from pnx_igemm (taps=1); pnx_tap_scatter is the mirrored backward gather
+ * dZ[m', t*16+j] = dout[m' - off_t, j] (bf16, columns >= 144 zeroed).  Replaces the `<head>.3` Conv2d(64, c, 3)
+ * of SepHead (centerhead.py:44-46) for all sibling heads at once. */
+int pnx_tap_gather_sum(const float* Z, long long ldz, const float* bias16, int B, int H, int W, float* out,
+                       cudaStream_t stream);
+int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- L1 fused CenterPoint loss (forward + gradient)
  * One task: out/dout [B*H*W, npad] fp32 channels-last head output (columns reg2|height1|dim3|rot2|vel2|hm C|pad)
  * and its gradient (fully written), labels in the reference's collate format (det3d/datasets/pipelines/assign.py:

@@ -36,6 +36,8 @@ _SIGS = {
     "pnx_pfn_lin1": [P, P, P, P, P, I, P, P, P, P, P, I, P],
     "pnx_pfn_max1": [P, P, P, I, P, P, P, P, P],
     "pnx_pfn_backward": [P, P, P, P, P, P, I, I, F, F, F, F] + [P] * 23 + [P],
+    "pnx_tap_gather_sum": [P, L, P, I, I, I, P, P],
+    "pnx_tap_scatter": [P, I, I, I, P, L, P],
     "pnx_center_loss_task": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, F, F, F, F, F, P, I, P, P],
     "pnx_center_loss_finalize": [P, I, P, P, P, P, P, P],
     "pnx_sites_out_dim": [I, I],

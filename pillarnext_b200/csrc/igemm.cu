@@ -47,7 +47,7 @@ struct Cfg {
   static constexpr uint32_t kBBytes = BN * 128;
   static constexpr int kStagesRaw = (192 * 1024) / (int)(kABytes + kBBytes);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + 128 * 9 * 8 + 256 + 4 * 4096 + 4 * 2 * BN * 4;
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + 128 * 9 * 8 + 256 + 4 * 4096 + 2 * BN * 4 + BN * 4;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
   using C = Cfg<BN>;
   constexpr int kProducerWarps = PW;
   constexpr int kProducerThreads = PW * 32;
+  constexpr int kThreadsTotal = 64 + PW * 32 + 128;
   constexpr int kStages = C::kStages;
   constexpr uint32_t kBBytes = C::kBBytes;
   constexpr int kColBlk = BN >= 32 ? 32 : 16;
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [4 warps][4 KB] store staging slabs
-  float* s_stat = s_tr + 4096;                                                        // [4 warps][2][BN] per-channel sum / sumsq
+  float* s_stat = s_tr + 4096;                                                        // [2][BN] per-channel sum / sumsq (smem atomics)
+  float* s_bias = s_stat + 2 * BN;                                                // [BN] bias of this CTA's column block
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,6 +110,9 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
     pnx::fence_barrier_init();
   }
   if (warp == 1) pnx::tmem_alloc<512>(tmem_slot);
+  if (p.bias)
+    for (int c = threadIdx.x; c < BN; c += blockDim.x) s_bias[c] = p.bias[blockIdx.y * BN + c];
+  for (int c = threadIdx.x; c < 2 * BN; c += blockDim.x) s_stat[c] = 0.f;
   pnx::tc_fence_before();
   __syncthreads();
   pnx::tc_fence_after();
@@ -243,13 +248,11 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    float* st_sum = s_stat + quarter * (2 * BN);
-    float* st_sq = st_sum + BN;
-    for (int c = lane; c < 2 * BN; c += 32) st_sum[c] = 0.f;
-    __syncwarp();
+    float* st_sum = s_stat;
+    float* st_sq = s_stat + BN;
     uint8_t* slab = reinterpret_cast<uint8_t*>(s_tr) + quarter * 4096;
     const int hw = p.Hout * p.Wout;
-    const bool staged = (BN % 64 == 0) && !p.out_fp32 && !p.shuffle;
+    const bool staged = (BN % 64 == 0) && !p.shuffle;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       while (!pnx::mbar_try_wait(&tfull[acc], acc_phase)) __nanosleep(64);  // leave the issue slots to the producers
       pnx::tc_fence_after();
@@ -273,19 +276,56 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
         const int ncol0 = n0 + cb * kColBlk;
         float v[32];
 #pragma unroll
-        for (int k = 0; k < kColBlk; ++k) {
-          float x = __uint_as_float(r[k]);
-          if (p.bias) x += __ldg(p.bias + ncol0 + k);
-          if (p.addend && active) x += __bfloat162float(p.addend[(long long)m * p.ld_add + ncol0 + k]);
-          if (p.relu) x = fmaxf(x, 0.f);
-          if (!p.out_fp32) x = pnx::bf16_round(x);
-          v[k] = x;
-        }
+        for (int k = 0; k < kColBlk; ++k) v[k] = __uint_as_float(r[k]);
 #pragma unroll
         for (int k = kColBlk; k < 32; ++k) v[k] = 0.f;
-        if (staged) {
-          // coalesced store: two 32-column blocks are staged per warp as a [32 rows x 128 B] slab (16-byte chunks
-          // XOR-swizzled by row), then written back 8 lanes per row = full 128-byte lines
+        if (p.bias) {
+#pragma unroll
+          for (int k = 0; k < kColBlk; k += 4) {
+            const float4 bq = *reinterpret_cast<const float4*>(s_bias + cb * kColBlk + k);  // smem broadcast
+            v[k] += bq.x; v[k + 1] += bq.y; v[k + 2] += bq.z; v[k + 3] += bq.w;
+          }
+        }
+        if (p.addend && active) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.addend + (long long)m * p.ld_add + ncol0);
+#pragma unroll
+          for (int k = 0; k < kColBlk / 8; ++k) {
+            const uint4 u = __ldg(ap + k);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h2[j]);
+              v[8 * k + 2 * j] += f.x;
+              v[8 * k + 2 * j + 1] += f.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int k = 0; k < kColBlk; ++k) v[k] = fmaxf(v[k], 0.f);
+        }
+        if (staged && p.out_fp32) {
+          // fp32 output: one 32-column block = [32 rows x 128 B] slab, flushed as full 128-byte lines
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(slab + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+          const int ch = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + (lane >> 3);
+            const long long mr = (long long)tile * 128 + quarter * 32 + row;
+            if (mr < p.M) {
+              const float4 val = *reinterpret_cast<const float4*>(slab + row * 128 + ((ch ^ (row & 7)) << 4));
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + mr * p.ldc + ncol0 + ch * 4) = val;
+            }
+          }
+          __syncwarp();
+        } else if (staged) {
+          // bf16 output: two 32-column blocks are staged per warp as a [32 rows x 128 B] slab (16-byte chunks
+          // XOR-swizzled by row), then written back 8 lanes per row = full 128-byte lines; the BatchNorm statistics
+          // of the 64 columns are read back from the slab (lane = column pair, 32 conflict-free LDS)
           const int half = cb & 1;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -296,50 +336,70 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
           if (half == 1) {
             __syncwarp();
             const int ch = lane & 7;
+            const long long row0 = (long long)tile * 128 + quarter * 32;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = it * 4 + (lane >> 3);
-              const long long mr = (long long)tile * 128 + quarter * 32 + row;
-              if (mr < p.M) {
+              if (row0 + row < p.M) {
                 const uint4 val = *reinterpret_cast<const uint4*>(slab + row * 128 + ((ch ^ (row & 7)) << 4));
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + mr * p.ldc + (ncol0 - 32) + ch * 8) = val;
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (row0 + row) * p.ldc + (ncol0 - 32) + ch * 8) = val;
               }
+            }
+            if (p.stats) {
+              const int nrows = (int)min((long long)32, (long long)p.M - row0);  // rows past M hold bias-only garbage
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+              const int cpc = lane >> 2, cps = (lane & 3) * 4;
+              for (int row = 0; row < nrows; ++row) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(slab + row * 128 + ((cpc ^ (row & 7)) << 4) + cps);
+                const float2 f = __bfloat1622float2(h2);
+                s0 += f.x; s1 += f.y;
+                q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+              }
+              const int c0 = (cb - 1) * 32 + 2 * lane;  // columns of this pair of blocks owned by this lane
+              atomicAdd(&st_sum[c0], s0); atomicAdd(&st_sum[c0 + 1], s1);
+              atomicAdd(&st_sq[c0], q0); atomicAdd(&st_sq[c0 + 1], q1);
             }
             __syncwarp();
           }
-        } else if (active) {
-          int col = ncol0;
-          if (p.shuffle) {
-            const int q = ncol0 >> 6;
-            out_row = ((long long)(sh_b * 2 * p.Hout + 2 * sh_y + (q >> 1))) * (2 * p.Wout) + 2 * sh_x + (q & 1);
-            col = ncol0 & 63;
+        } else {
+          if (!p.out_fp32) {
+#pragma unroll
+            for (int k = 0; k < kColBlk; ++k) v[k] = pnx::bf16_round(v[k]);
           }
-          if (p.out_fp32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldc + col);
+          if (active) {
+            int col = ncol0;
+            if (p.shuffle) {
+              const int q = ncol0 >> 6;
+              out_row = ((long long)(sh_b * 2 * p.Hout + 2 * sh_y + (q >> 1))) * (2 * p.Wout) + 2 * sh_x + (q & 1);
+              col = ncol0 & 63;
+            }
+            if (p.out_fp32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldc + col);
 #pragma unroll
-            for (int k = 0; k < kColBlk / 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + col);
+              for (int k = 0; k < kColBlk / 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + col);
 #pragma unroll
-            for (int k = 0; k < kColBlk / 8; ++k)
-              dst[k] = make_uint4(pnx::pack_bf16x2(v[8 * k], v[8 * k + 1]), pnx::pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
-                                  pnx::pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pnx::pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+              for (int k = 0; k < kColBlk / 8; ++k)
+                dst[k] = make_uint4(pnx::pack_bf16x2(v[8 * k], v[8 * k + 1]), pnx::pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                    pnx::pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pnx::pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+            }
           }
-        }
-        if (p.stats) {
-          float a[32];
+          if (p.stats) {
+            float a[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            v[k] = active ? v[k] : 0.f;
-            a[k] = v[k];
-          }
-          const float s1 = colsum32(a);
+            for (int k = 0; k < 32; ++k) {
+              v[k] = active ? v[k] : 0.f;
+              a[k] = v[k];
+            }
+            const float s1 = colsum32(a);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] *= v[k];
-          const float s2 = colsum32(v);
-          if (lane < kColBlk) {  // lane c owns column c of this warp's accumulators: plain read-modify-write
-            st_sum[cb * kColBlk + lane] += s1;
-            st_sq[cb * kColBlk + lane] += s2;
+            for (int k = 0; k < 32; ++k) v[k] *= v[k];
+            const float s2 = colsum32(v);
+            if (lane < kColBlk) {  // lane c owns column c of this warp's accumulators: plain read-modify-write
+              atomicAdd(&st_sum[cb * kColBlk + lane], s1);
+              atomicAdd(&st_sq[cb * kColBlk + lane], s2);
+            }
           }
         }
       }
@@ -350,8 +410,8 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.stats) {
-      __syncwarp();
-      for (int c = lane; c < BN; c += 32) {
+      named_bar_sync(2, 128);  // the four epilogue warps
+      for (int c = threadIdx.x - (kThreadsTotal - 128); c < BN; c += 128) {
         const int ch = (n0 + c) % p.stats_mod;
         atomicAdd(&p.stats[ch], (double)st_sum[c]);
         atomicAdd(&p.stats[p.stats_C + ch], (double)st_sq[c]);

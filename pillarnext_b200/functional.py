@@ -393,3 +393,47 @@ class CenterLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, _g_res):
         return (None,) + tuple(d.mul_(g_total) for d in ctx.douts)
+
+
+# ------------------------------------------------------------------------------------------- head final convs
+class HeadFinalConvFn(torch.autograd.Function):
+    """The sibling heads' final Conv2d(64, c, 3) (centerhead.py:44-46) as ONE 1x1 tensor-core GEMM (N = 9 taps x 16
+    padded outputs, no gather) + a 9-point stencil sum (stencil.cu), instead of a gather-bound 3x3 implicit GEMM.
+    y bf16 [M, Cin]; wb fp32 [16, Cin, 3, 3] (block-diagonal over the heads, zero rows as padding); bias fp32 [16].
+    Returns fp32 [M, 16]."""
+    NZ = 192   # 9*16 = 144 GEMM columns, padded to a tile / K multiple
+
+    @staticmethod
+    def forward(ctx, y, wb, bias, B, H, W):
+        from ._lib import check, lib, ptr, stream
+        M, cin = y.shape
+        assert wb.shape[0] == 16 and wb.shape[2] == 3
+        with torch.no_grad():
+            wz = torch.zeros(1, HeadFinalConvFn.NZ, cin, dtype=torch.bfloat16, device=y.device)
+            wz[0, :144] = wb.permute(2, 3, 0, 1).reshape(144, cin).to(torch.bfloat16)       # row = tap*16 + j
+        Z = torch.empty(M, HeadFinalConvFn.NZ, dtype=torch.float32, device=y.device)
+        ops.igemm(y, M, wz, 1, cin, HeadFinalConvFn.NZ, Z, block_n=192)
+        out = torch.empty(M, 16, dtype=torch.float32, device=y.device)
+        ops._count(1)
+        check(lib().pnx_tap_gather_sum(ptr(Z), HeadFinalConvFn.NZ, ptr(bias.detach().float().contiguous()), B, H, W, ptr(out), stream()))
+        ctx.save_for_backward(y, wz)
+        ctx.geo = (B, H, W, cin, tuple(wb.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ._lib import check, lib, ptr, stream
+        y, wz = ctx.saved_tensors
+        B, H, W, cin, wshape = ctx.geo
+        M, NZ = y.shape[0], HeadFinalConvFn.NZ
+        dout = dout.contiguous().float()
+        dZ = torch.empty(M, NZ, dtype=torch.bfloat16, device=dout.device)
+        ops._count(1)
+        check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), NZ, stream()))
+        dbias = dout.sum(0)
+        dy = torch.empty(M, cin, dtype=torch.bfloat16, device=dout.device)
+        ops.igemm(dZ, M, wz.transpose(1, 2).contiguous(), 1, NZ, cin, dy)          # dy = dZ . Wz
+        g = torch.zeros(1, cin, NZ, dtype=torch.float32, device=dout.device)
+        ops.wgrad(y, cin, dZ, NZ, M, 1, g)                                        # [1, Cin, NZ] = y^T . dZ
+        dwb = g[0, :, :144].reshape(cin, 3, 3, 16).permute(3, 0, 1, 2).contiguous()
+        return dy, dwb, dbias, None, None, None

@@ -378,7 +378,10 @@ class SepHead(nn.Module):
             o += classes[i]
         wb = torch.cat(rows_w + ([wb[tot:]] if npad > tot else []), 0)
         bb = torch.cat(rows_b + ([bb[tot:]] if npad > tot else []), 0)
-        out, _ = Fn.conv(y, wb, bb, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), out_fp32=True)
+        if npad == 16:
+            out = Fn.HeadFinalConvFn.apply(y, wb, bb, B, H, W)       # 1x1 GEMM + stencil (gather-free)
+        else:
+            out, _ = Fn.conv(y, wb, bb, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), out_fp32=True)
         out4 = out.view(B, H, W, npad)
         ret, o, offs = dict(), 0, {}
         for i, n in enumerate(names):
