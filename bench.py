@@ -197,18 +197,8 @@ def main():
     host = [pin(synth.make_batch([rank * 1000 + b * args.frames + f for f in range(args.frames)], args.points, cfg,
                                  kind="lidar", n_boxes=40, sweeps=10)) for b in range(nb)]
     resident = [to_device(h, dev) for h in host]
-    flat = None
-
-    def allreduce_grads():
-        nonlocal flat
-        if world == 1:
-            return
-        grads = [p.grad for p in params]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat)
-        flat.div_(world)
-        for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(s)
+    from pillarnext_b200.parallel import FlatGradAllReduce
+    allreduce_grads = FlatGradAllReduce(params)
 
     def step(ex):
         loss, _ = model(ex)

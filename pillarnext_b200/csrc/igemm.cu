@@ -40,13 +40,15 @@ struct IgemmParams {
 // (small N: two producer warps per scheduler hide the gather latency), PW = 4 for the epilogue-heavy ones (wide N,
 // short K: the epilogue warps need the issue slots and the registers).
 constexpr uint32_t kABytes = 128 * 128;
-constexpr int kLag = 2;
+
 
 template <int BN>
 struct Cfg {
   static constexpr uint32_t kBBytes = BN * 128;
   static constexpr int kStagesRaw = (192 * 1024) / (int)(kABytes + kBBytes);
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStagesCap = BN <= 64 ? 6 : 8;   // gather-bound shapes: leave >= 48 KB of L1 for cross-tap row reuse
+  static constexpr int kStages = kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw;
+  static constexpr int kLag = kStages >= 6 ? 4 : (kStages >= 4 ? kStages - 2 : 1);  // cp.async groups in flight per producer thread
   static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + 128 * 9 * 8 + 256 + 4 * 4096 + 2 * BN * 4 + BN * 4;
 };
 
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
   constexpr int kProducerThreads = PW * 32;
   constexpr int kThreadsTotal = 64 + PW * 32 + 128;
   constexpr int kStages = C::kStages;
+  constexpr int kLag = C::kLag;
   constexpr uint32_t kBBytes = C::kBBytes;
   constexpr int kColBlk = BN >= 32 ? 32 : 16;
   constexpr int kNumCB = BN / kColBlk;
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < num_k; ++kc) {
-          const int t = kc / kpt, cc = kc - t * kpt;
+          const int cc = kc / p.T, t = kc - cc * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
           pnx::mbar_wait(&empty[stage], phase ^ 1);
           pnx::mbar_arrive_expect_tx(&full[stage], kBBytes);
           pnx::tma_load_2d(&wmap, &full[stage], sB + (size_t)stage * kBBytes, cc * 64, t * p.w_rows_per_tap + n0);
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kc = 0; kc < num_k; ++kc) {
           pnx::mbar_wait(&full[stage], phase);
+          pnx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           pnx::tc_fence_after();
           const uint32_t a_base = pnx::smem_u32(sA + (size_t)stage * kABytes);
           const uint32_t b_base = pnx::smem_u32(sB + (size_t)stage * kBBytes);
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
       }
       named_bar_sync(1, kProducerThreads);
       for (int kc = 0; kc < num_k; ++kc) {
-        const int t = kc / kpt, cc = kc - t * kpt;
+        const int cc = kc / p.T, t = kc - cc * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
         pnx::mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t dst = pnx::smem_u32(sA + (size_t)stage * kABytes);
         const __nv_bfloat16* col = p.A + cc * 64 + chunk * 8;
@@ -219,12 +223,11 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
         for (int j = 0; j < 128 / (kProducerThreads / 8); ++j) {
           const int r = j * (kProducerThreads / 8) + sub_row;
           const long long off = s_off[r * 9 + t];
-          pnx::cp_async16(dst + r * 128 + ((chunk ^ (r & 7)) << 4), col + (off < 0 ? 0 : off), off < 0 ? 0u : 16u);
+          pnx::cp_async16_ca(dst + r * 128 + ((chunk ^ (r & 7)) << 4), col + (off < 0 ? 0 : off), off < 0 ? 0u : 16u);
         }
         pnx::cp_async_commit();
         if (pending == kLag) {
           pnx::cp_async_wait<kLag>();
-          pnx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
           if (++arr_stage == kStages) arr_stage = 0;
@@ -235,7 +238,6 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
       }
     }
     pnx::cp_async_wait<0>();
-    pnx::fence_proxy_async_smem();
     __syncwarp();
     for (; pending > 0; --pending) {
       if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);

@@ -50,7 +50,7 @@ struct WCfg {
   static constexpr uint32_t kStageBytes = (2 + TG * kYAtoms) * kBlk;
   static constexpr int kStagesRaw = (196 * 1024) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kLag = kStages >= 4 ? kStages - 2 : (kStages == 3 ? 1 : 0);
+  static constexpr int kLag = kStages - 1;  // cp.async groups kept in flight per producer thread (must stay < kStages)
   static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + (size_t)kStages * kKS * (TG + 1) * 8;
   static_assert(NYC * TG <= 512, "TMEM budget");
   static_assert(kStages >= 2, "need at least two stages");
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
         const int total_atoms = ntaps * kYAtoms;
         for (int kc = 0; kc < num_k; ++kc) {
           pnx::mbar_wait(&full[stage], phase);
+          pnx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           pnx::tc_fence_after();
           const uint32_t sx = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
           const uint32_t sy = sx + 2 * kBlk;
@@ -197,13 +198,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
             const __nv_bfloat16* ys = ybase + (oy < 0 ? 0 : oy);
             const uint32_t nby = (oy < 0 || ox < 0) ? 0u : 16u;
 #pragma unroll
-            for (int a = 0; a < kYAtoms; ++a) pnx::cp_async16(sy + (j * kYAtoms + a) * kBlk + off, ys + a * 64, nby);
+            for (int a = 0; a < kYAtoms; ++a) pnx::cp_async16_ca(sy + (j * kYAtoms + a) * kBlk + off, ys + a * 64, nby);
           }
         }
         pnx::cp_async_commit();
         if (pending == kLag) {
           pnx::cp_async_wait<kLag>();
-          pnx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
           if (++arr_stage == kStages) arr_stage = 0;
@@ -213,7 +213,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       pnx::cp_async_wait<0>();
-      pnx::fence_proxy_async_smem();
       __syncwarp();
       for (; pending > 0; --pending) {
         if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
