@@ -186,6 +186,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (some boxes default to VERSION)
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     cfg = synth.NUSC

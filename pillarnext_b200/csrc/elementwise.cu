@@ -20,22 +20,28 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
                     pnx::pack_bf16x2(f[6], f[7]));
 }
 
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
-                                const float* __restrict__ scale, const float* __restrict__ shift,
-                                const __nv_bfloat16* __restrict__ res, long long ldr, int relu,
-                                __nv_bfloat16* __restrict__ y, long long ldy) {
+// Thread layout of the row-wise kernels: 256 threads = (256 / cg) rows x cg channel groups of 8 channels; a thread
+// keeps its channel group for the whole grid-stride loop, so per-channel coefficients live in registers and the
+// loop has no integer division.
+__global__ void __launch_bounds__(256)
+    bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const __nv_bfloat16* __restrict__ res, long long ldr, int relu,
+                    __nv_bfloat16* __restrict__ y, long long ldy) {
   const int cg = C >> 3;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = M * cg;
-  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long m = t / cg;
-    const int c0 = (int)(t - m * cg) << 3;
+  const int rpb = 256 / cg;
+  const int my_cg = threadIdx.x % cg, my_row = threadIdx.x / cg;
+  if (my_row >= rpb) return;
+  const int c0 = my_cg << 3;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = scale[c0 + k];
+    sh[k] = shift[c0 + k];
+  }
+  for (long long m = (long long)blockIdx.x * rpb + my_row; m < M; m += (long long)gridDim.x * rpb) {
     float v[8], r[8];
     unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), v);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
     if (res) unpack8(*reinterpret_cast<const uint4*>(res + m * ldr + c0), r);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -98,43 +104,40 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long 
   }
 }
 
-// dx = scale * (g - sum_g/n - xhat * sum_gx/n) ; optional dres (+)= g
-// Per-channel coefficients are staged once per block in shared memory: [A = gamma*invstd | B = sum_g/n |
-// Cc = sum_gx/n | mean | invstd] so the row loop is pure 128-bit streaming.
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
-                                    const __nv_bfloat16* __restrict__ y, long long ldy,
-                                    const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, const double* __restrict__ red, float inv_n,
-                                    int relu, __nv_bfloat16* __restrict__ dx, long long lddx,
-                                    __nv_bfloat16* __restrict__ dres, long long lddres, int dres_accumulate) {
-  extern __shared__ float coef[];  // [5][C]
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float is = invstd[c];
-    coef[c] = gamma[c] * is;
-    coef[C + c] = (float)red[c] * inv_n;
-    coef[2 * C + c] = (float)red[C + c] * inv_n;
-    coef[3 * C + c] = mean[c];
-    coef[4 * C + c] = is;
-  }
-  __syncthreads();
+// dx = gamma*invstd * (g - sum_g/n - xhat * sum_gx/n) ; optional dres (+)= g        (same thread layout as bn_apply)
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ y,
+                        long long ldy, const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ gamma, const double* __restrict__ red, float inv_n, int relu,
+                        __nv_bfloat16* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dres,
+                        long long lddres, int dres_accumulate) {
   const int cg = C >> 3;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = M * cg;
-  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long m = t / cg;
-    const int c0 = (int)(t - m * cg) << 3;
+  const int rpb = 256 / cg;
+  const int my_cg = threadIdx.x % cg, my_row = threadIdx.x / cg;
+  if (my_row >= rpb) return;
+  const int c0 = my_cg << 3;
+  float ca[8], cb[8], cc[8], mu[8], is[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    is[k] = invstd[c];
+    mu[k] = mean[c];
+    ca[k] = gamma[c] * is[k];
+    cb[k] = (float)red[c] * inv_n;
+    cc[k] = (float)red[C + c] * inv_n;
+  }
+  for (long long m = (long long)blockIdx.x * rpb + my_row; m < M; m += (long long)gridDim.x * rpb) {
     float g[8], yy[8], xx[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + m * lddy + c0), g);
     unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), xx);
     if (relu) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
       const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
       g[k] = gg;
-      const float xh = (xx[k] - coef[3 * C + c]) * coef[4 * C + c];
-      o[k] = coef[c] * (gg - coef[C + c] - xh * coef[2 * C + c]);
+      const float xh = (xx[k] - mu[k]) * is[k];
+      o[k] = ca[k] * (gg - cb[k] - xh * cc[k]);
     }
     *reinterpret_cast<uint4*>(dx + m * lddx + c0) = pack8(o);
     if (dres) {
@@ -207,6 +210,14 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long 
   }
 }
 
+// grid for the (rows x channel-group) layout: enough blocks for ~16 waves, each thread streaming >= 4 rows
+inline int row_blocks(long long M, int C) {
+  const int rpb = 256 / (C / 8);
+  long long b = (M + (long long)rpb * 4 - 1) / ((long long)rpb * 4);
+  const long long cap = 148LL * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
 inline int ew_blocks(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   long long cap = 148LL * 16;
@@ -219,7 +230,8 @@ extern "C" int pnx_bn_apply(const void* x, long long ldx, long long M, int C, co
                             const void* res, long long ldr, int relu, void* y, long long ldy, cudaStream_t stream) {
   PNX_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldr % 8 == 0, "C/ld % 8");
   if (M == 0) return PNX_OK;
-  bn_apply_kernel<<<ew_blocks(M * (C / 8), 256), 256, 0, stream>>>((const __nv_bfloat16*)x, ldx, M, C, scale, shift,
+  PNX_CHECK_ARG(C <= 2048, "C <= 2048");
+  bn_apply_kernel<<<row_blocks(M, C), 256, 0, stream>>>((const __nv_bfloat16*)x, ldx, M, C, scale, shift,
                                                                    (const __nv_bfloat16*)res, ldr, relu,
                                                                    (__nv_bfloat16*)y, ldy);
   PNX_CHECK_LAUNCH();
@@ -252,7 +264,7 @@ extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, l
   PNX_CHECK_ARG(C % 8 == 0, "C % 8");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(C <= 2048, "C <= 2048");
-  bn_bwd_apply_kernel<<<ew_blocks(M * (C / 8), 256), 256, 5 * C * sizeof(float), stream>>>(
+  bn_bwd_apply_kernel<<<row_blocks(M, C), 256, 0, stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M, C, mean, invstd,
       gamma, red, (float)(1.0 / count), relu, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddres,
       dres_accumulate);

@@ -44,15 +44,15 @@ constexpr uint32_t kBlk = kKS * 128;  // bytes of one [64 rows x 64 ch] block
 constexpr int kMaxTG = 8;
 
 // NYC = Y channels per CTA (64..256), TG = max taps per group (NYC * TG <= 512 TMEM columns)
-template <int NYC, int TG>
+template <int NYC, int TG, int XB>
 struct WCfg {
   static constexpr int kYAtoms = NYC / 64;
-  static constexpr uint32_t kStageBytes = (2 + TG * kYAtoms) * kBlk;
+  static constexpr uint32_t kStageBytes = (2 * XB + TG * kYAtoms) * kBlk;
   static constexpr int kStagesRaw = (196 * 1024) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kLag = kStages - 1;  // cp.async groups kept in flight per producer thread (must stay < kStages)
   static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + (size_t)kStages * kKS * (TG + 1) * 8;
-  static_assert(NYC * TG <= 512, "TMEM budget");
+  static_assert(NYC * TG * XB <= 512, "TMEM budget");
   static_assert(kStages >= 2, "need at least two stages");
 };
 
@@ -68,9 +68,10 @@ __device__ __forceinline__ void divmod_fast(int n, int d, float inv_d, int& q, i
   }
 }
 
-template <int NYC, int TG>
+// XB = number of 128-channel X blocks per CTA (2 halves the re-gathering of Y when the TMEM budget allows)
+template <int NYC, int TG, int XB>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
-  using C = WCfg<NYC, TG>;
+  using C = WCfg<NYC, TG, XB>;
   constexpr int kStages = C::kStages, kLag = C::kLag, kYAtoms = C::kYAtoms;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -118,15 +119,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
           pnx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           pnx::tc_fence_after();
           const uint32_t sx = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
-          const uint32_t sy = sx + 2 * kBlk;
+          const uint32_t sy = sx + 2 * XB * kBlk;
 #pragma unroll
           for (int k = 0; k < kKS / 16; ++k) {
-            const uint64_t dx = pnx::make_smem_desc_sw128(sx + k * 2048, x_lbo, 1024);
             for (int a0 = 0; a0 < total_atoms; a0 += kAtomsPerMma) {
               const int na = min(kAtomsPerMma, total_atoms - a0);
               const uint64_t dy = pnx::make_smem_desc_sw128(sy + a0 * kBlk + k * 2048, kBlk, 1024);
-              pnx::umma_f16(tmem_base + a0 * 64, dx, dy, pnx::make_idesc_bf16(128, na * 64, 1, 1),
-                            (kc > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int x2 = 0; x2 < XB; ++x2) {
+                const uint64_t dx = pnx::make_smem_desc_sw128(sx + x2 * 2 * kBlk + k * 2048, x_lbo, 1024);
+                pnx::umma_f16(tmem_base + x2 * (NYC * TG) + a0 * 64, dx, dy, pnx::make_idesc_bf16(128, na * 64, 1, 1),
+                              (kc > 0 || k > 0) ? 1u : 0u);
+              }
             }
           }
           pnx::umma_commit(&empty[stage]);
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
       // integer/address latency of the copy loop is hidden; 64-bit row offsets come from a per-chunk smem table)
       const int ptid = threadIdx.x - 64;
       const int sub_row = ptid >> 3, chunk = ptid & 7;
-      const int x_ch0 = xb * 128, y_ch0 = yc * NYC;
+      const int x_ch0 = xb * 128 * XB, y_ch0 = yc * NYC;
       const int hw = p.Hout * p.Wout;
       const __nv_bfloat16* xbase = p.X + x_ch0 + chunk * 8;
       const __nv_bfloat16* ybase = p.Y + y_ch0 + chunk * 8;
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
         pnx::mbar_wait(&empty[stage], phase ^ 1);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint32_t sx = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
-        const uint32_t sy = sx + 2 * kBlk;
+        const uint32_t sy = sx + 2 * XB * kBlk;
 #pragma unroll
         for (int j2 = 0; j2 < kKS / 32; ++j2) {
           const int r = j2 * 32 + sub_row;
@@ -192,7 +196,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
           const __nv_bfloat16* xs = xbase + (ox < 0 ? 0 : ox);
           const uint32_t nbx = ox < 0 ? 0u : 16u;
           pnx::cp_async16(sx + off, xs, nbx);
-          if (!p.x_dup) pnx::cp_async16(sx + kBlk + off, xs + 64, nbx);
+          if (!p.x_dup) {
+#pragma unroll
+            for (int b2 = 1; b2 < 2 * XB; ++b2) pnx::cp_async16(sx + b2 * kBlk + off, xs + b2 * 64, nbx);
+          }
           for (int j = 0; j < ntaps; ++j) {
             const long long oy = rows[(1 + j) * kKS + r];
             const __nv_bfloat16* ys = ybase + (oy < 0 ? 0 : oy);
@@ -224,14 +231,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
       while (!pnx::mbar_try_wait(done, 0)) __nanosleep(256);  // long wait: leave the issue slots to the producers
       pnx::tc_fence_after();
       const int xrow_local = quarter * 32 + lane;
-      const int xch = xb * 128 + xrow_local;
-      const bool ok = xch < p.X_total && !(p.x_dup && xrow_local >= 64);
+      for (int x2 = 0; x2 < XB; ++x2)
       for (int j = 0; j < ntaps; ++j) {
+        const int xch = (xb * XB + x2) * 128 + xrow_local;
+        const bool ok = xch < p.X_total && !(p.x_dup && xrow_local >= 64);
         float* dst = p.dW + ((size_t)(t0 + j) * p.X_total + (ok ? xch : 0)) * p.Y_total + yc * NYC;
 #pragma unroll
         for (int cb = 0; cb < NYC / 32; ++cb) {
           uint32_t r[32];
-          pnx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + j * NYC + cb * 32, r);
+          pnx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + x2 * (NYC * TG) + j * NYC + cb * 32, r);
           pnx::tmem_ld_wait();
           if (ok) {
 #pragma unroll
@@ -247,14 +255,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
   if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int NYC, int TG>
+template <int NYC, int TG, int XB>
 int launch_wgrad(WgradParams p, int x_blocks, int sm_count, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNX_CUDA(cudaFuncSetAttribute(wgrad_kernel<NYC, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)WCfg<NYC, TG>::kSmem));
+    PNX_CUDA(cudaFuncSetAttribute(wgrad_kernel<NYC, TG, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)WCfg<NYC, TG, XB>::kSmem));
     attr_set = true;
   }
+  x_blocks /= XB;
   p.y_chunks = p.Y_total / NYC;
   p.taps_per_group = p.T < TG ? p.T : TG;
   int groups = (p.T + p.taps_per_group - 1) / p.taps_per_group;
@@ -269,7 +278,7 @@ int launch_wgrad(WgradParams p, int x_blocks, int sm_count, cudaStream_t stream)
   p.rows_per_split = ((p.M + splits - 1) / splits + kKS - 1) / kKS * kKS;
   splits = (p.M + p.rows_per_split - 1) / p.rows_per_split;
   dim3 grid(x_blocks * p.y_chunks, groups, splits);
-  wgrad_kernel<NYC, TG><<<grid, kThreads, WCfg<NYC, TG>::kSmem, stream>>>(p);
+  wgrad_kernel<NYC, TG, XB><<<grid, kThreads, WCfg<NYC, TG, XB>::kSmem, stream>>>(p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -303,8 +312,11 @@ extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, const voi
   p.y_chunks = 1; p.taps_per_group = 1; p.rows_per_split = M;
   const int x_blocks = x_channels == 64 ? 1 : x_channels / 128;
   // Y chunk: the largest of 256/192/128/64 dividing y_channels; taps per group bounded by 512 TMEM columns
-  if (y_channels % 256 == 0) return launch_wgrad<256, 1>(p, x_blocks, sm_count, stream);
-  if (y_channels % 192 == 0) return launch_wgrad<192, 2>(p, x_blocks, sm_count, stream);
-  if (y_channels % 128 == 0) return launch_wgrad<128, 3>(p, x_blocks, sm_count, stream);
-  return launch_wgrad<64, 5>(p, x_blocks, sm_count, stream);
+  if (y_channels % 256 == 0) {
+    if (x_blocks % 2 == 0) return launch_wgrad<256, 1, 2>(p, x_blocks, sm_count, stream);  // 256 x 256 accumulators
+    return launch_wgrad<256, 1, 1>(p, x_blocks, sm_count, stream);
+  }
+  if (y_channels % 192 == 0) return launch_wgrad<192, 2, 1>(p, x_blocks, sm_count, stream);
+  if (y_channels % 128 == 0) return launch_wgrad<128, 3, 1>(p, x_blocks, sm_count, stream);
+  return launch_wgrad<64, 5, 1>(p, x_blocks, sm_count, stream);
 }
