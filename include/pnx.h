@@ -174,15 +174,17 @@ int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long 
  * conv.py:29-34; rows = active sites or pixels, C channels, ld* = row strides in elements. */
 int pnx_bn_apply(const void* x, long long ldx, long long M, int C, const float* scale, const float* shift,
                  const void* res, long long ldr, int relu, void* y, long long ldy, cudaStream_t stream);
-/* BatchNorm backward: red[0:C] += sum g, red[C:2C] += sum g*xhat with g = dy*(y>0 if relu) ... */
+/* BatchNorm backward: red[0:C] += sum g, red[C:2C] += sum g*xhat with g = dy*(y>0 if relu).  y may be NULL when
+ * there is no residual: the ReLU mask is then recomputed from x with the forward affine (fscale, fshift). */
 int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
                       long long ldx, long long M, int C, const float* mean, const float* invstd, int relu,
-                      double* red, cudaStream_t stream);
+                      const float* fscale, const float* fshift, double* red, cudaStream_t stream);
 /* ... dx = gamma*invstd*(g - red[c]/count - xhat*red[C+c]/count); optional dres (+)= g (residual branch). */
 int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
                      long long ldx, long long M, int C, const float* mean, const float* invstd,
-                     const float* gamma, const double* red, double count, int relu, void* dx, long long lddx,
-                     void* dres, long long lddres, int dres_accumulate, cudaStream_t stream);
+                     const float* gamma, const double* red, double count, int relu, const float* fscale,
+                     const float* fshift, void* dx, long long lddx, void* dres, long long lddres,
+                     int dres_accumulate, cudaStream_t stream);
 int pnx_add_rows(void* a, long long lda, const void* b, long long ldb, long long M, int C, cudaStream_t stream);
 /* y = relu(a + b) (BasicBlock tail, conv.py:48-50) and its backward g (+)= dy*(y>0). */
 int pnx_add_relu(const void* a, long long lda, const void* b, long long ldb, long long M, int C, void* y,

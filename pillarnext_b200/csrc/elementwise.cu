@@ -60,6 +60,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long 
                                      const __nv_bfloat16* __restrict__ y, long long ldy,
                                      const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                     const float* __restrict__ fscale, const float* __restrict__ fshift,
                                      double* __restrict__ red) {
   extern __shared__ float sred[];  // [kThreads][16]
   const int cg = C >> 3;
@@ -67,19 +68,27 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long 
   const int rows_per_block = kThreads / cg;
   const int my_row = threadIdx.x / cg;
   const int c0 = my_cg << 3;
-  float sg[8], sgx[8], mu[8], is[8];
+  float sg[8], sgx[8], mu[8], is[8], fs[8], fh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     sg[k] = sgx[k] = 0.f;
     mu[k] = mean[c0 + k];
     is[k] = invstd[c0 + k];
+    fs[k] = y ? 0.f : fscale[c0 + k];   // y == nullptr: the ReLU mask is recomputed from x (saves one row-matrix read)
+    fh[k] = y ? 0.f : fshift[c0 + k];
   }
   if (my_row < rows_per_block) {
     for (long long m = (long long)blockIdx.x * rows_per_block + my_row; m < M; m += (long long)gridDim.x * rows_per_block) {
       float g[8], yy[8], xx[8];
       unpack8(*reinterpret_cast<const uint4*>(dy + m * lddy + c0), g);
       unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), xx);
-      if (relu) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
+      if (relu) {
+        if (y) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
+        else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
@@ -110,6 +119,7 @@ __global__ void __launch_bounds__(256)
                         long long ldy, const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gamma, const double* __restrict__ red, float inv_n, int relu,
+                        const float* __restrict__ fscale, const float* __restrict__ fshift,
                         __nv_bfloat16* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dres,
                         long long lddres, int dres_accumulate) {
   const int cg = C >> 3;
@@ -117,10 +127,12 @@ __global__ void __launch_bounds__(256)
   const int my_cg = threadIdx.x % cg, my_row = threadIdx.x / cg;
   if (my_row >= rpb) return;
   const int c0 = my_cg << 3;
-  float ca[8], cb[8], cc[8], mu[8], is[8];
+  float ca[8], cb[8], cc[8], mu[8], is[8], fs[8], fh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = c0 + k;
+    fs[k] = y ? 0.f : fscale[c];
+    fh[k] = y ? 0.f : fshift[c];
     is[k] = invstd[c];
     mu[k] = mean[c];
     ca[k] = gamma[c] * is[k];
@@ -131,7 +143,13 @@ __global__ void __launch_bounds__(256)
     float g[8], yy[8], xx[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + m * lddy + c0), g);
     unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), xx);
-    if (relu) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
+    if (relu) {
+      if (y) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
+      }
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
@@ -240,7 +258,8 @@ extern "C" int pnx_bn_apply(const void* x, long long ldx, long long M, int C, co
 
 extern "C" int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
                                  long long ldx, long long M, int C, const float* mean, const float* invstd, int relu,
-                                 double* red, cudaStream_t stream) {
+                                 const float* fscale, const float* fshift, double* red, cudaStream_t stream) {
+  PNX_CHECK_ARG(!relu || y || (fscale && fshift), "relu backward needs y or the forward affine (scale, shift)");
   PNX_CHECK_ARG(C % 8 == 0 && C <= 2048, "C % 8 == 0 and C <= 2048");
   if (M == 0) return PNX_OK;
   constexpr int kT = 256;
@@ -251,22 +270,23 @@ extern "C" int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, 
   if (nb < 1) nb = 1;
   bn_bwd_reduce_kernel<kT><<<(int)nb, kT, kT * 16 * sizeof(float), stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M, C, mean, invstd,
-      relu, red);
+      relu, fscale, fshift, red);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
 
 extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
                                 long long ldx, long long M, int C, const float* mean, const float* invstd,
-                                const float* gamma, const double* red, double count, int relu, void* dx,
-                                long long lddx, void* dres, long long lddres, int dres_accumulate,
-                                cudaStream_t stream) {
+                                const float* gamma, const double* red, double count, int relu, const float* fscale,
+                                const float* fshift, void* dx, long long lddx, void* dres, long long lddres,
+                                int dres_accumulate, cudaStream_t stream) {
+  PNX_CHECK_ARG(!relu || y || (fscale && fshift), "relu backward needs y or the forward affine (scale, shift)");
   PNX_CHECK_ARG(C % 8 == 0, "C % 8");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(C <= 2048, "C <= 2048");
   bn_bwd_apply_kernel<<<row_blocks(M, C), 256, 0, stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M, C, mean, invstd,
-      gamma, red, (float)(1.0 / count), relu, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddres,
+      gamma, red, (float)(1.0 / count), relu, fscale, fshift, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddres,
       dres_accumulate);
   PNX_CHECK_LAUNCH();
   return PNX_OK;

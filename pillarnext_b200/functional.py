@@ -109,7 +109,7 @@ class ConvFn(torch.autograd.Function):
     x bf16 [M_in, >=Cin]; returns (out [M_out(*4 if shuffle), Cout], stats fp64 [2*Cs] or empty)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, spec, layout, want_stats, out_fp32, relu, n_valid_out):
+    def forward(ctx, x, w, bias, spec, layout, want_stats, out_fp32, relu, bias_feeds_bn):
         shape = tuple(w.shape)
         if layout.kind == "dense":
             cout, cin = shape[0], shape[1]
@@ -129,7 +129,7 @@ class ConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, w, out if relu else None)
         ctx.spec, ctx.layout, ctx.dims = spec, layout, (cin, cout, shape)
         ctx.has_bias, ctx.relu, ctx.out_fp32 = bias is not None, relu, out_fp32
-        ctx.n_valid_out = n_valid_out
+        ctx.bias_feeds_bn = bool(bias_feeds_bn)
         ctx.mark_non_differentiable(stats)
         return out, stats
 
@@ -151,7 +151,14 @@ class ConvFn(torch.autograd.Function):
             g = torch.empty_like(dy)
             ops.relu_bwd(dy, out, rows, cout, g)
             dy = g
-        dbias = torch.sum(dy[:, :cout], dim=0, dtype=torch.float32) if ctx.has_bias else None   # fp32 accumulate, no fp32 copy
+        if not ctx.has_bias:
+            dbias = None
+        elif ctx.bias_feeds_bn:
+            # conv bias in front of a training-mode BatchNorm: BN's input gradient sums to zero per channel, so the
+            # bias gradient is exactly 0 (the reference's autograd produces ~1e-7 rounding noise there)
+            dbias = torch.zeros(cout, dtype=torch.float32, device=dy.device)
+        else:
+            dbias = torch.sum(dy[:, :cout], dim=0, dtype=torch.float32)   # fp32 accumulate, no fp32 copy
         dx = None
         if ctx.needs_input_grad[0]:
             wd = packed(w, layout, "dgrad", spec.d_flip)            # [taps_d, Cin, Cout]
@@ -178,8 +185,8 @@ class ConvFn(torch.autograd.Function):
         return dx, dw, dbias, None, None, None, None, None, None
 
 
-def conv(x, w, bias, spec, layout, want_stats=False, out_fp32=False, relu=False):
-    return ConvFn.apply(x, w, bias, spec, layout, want_stats, out_fp32, relu, None)
+def conv(x, w, bias, spec, layout, want_stats=False, out_fp32=False, relu=False, bias_feeds_bn=False):
+    return ConvFn.apply(x, w, bias, spec, layout, want_stats, out_fp32, relu, bias_feeds_bn)
 
 
 # ------------------------------------------------------------------------------------------- batch norm
@@ -210,13 +217,13 @@ class BNActFn(torch.autograd.Function):
             mean = invstd = None
         y = torch.empty(M, C, dtype=torch.bfloat16, device=x_raw.device)
         ops.bn_apply(x_raw, M, C, scale, shift, y, res=residual, relu=relu)
-        ctx.save_for_backward(x_raw, y, gamma, mean, invstd, scale)
+        ctx.save_for_backward(x_raw, y, gamma, mean, invstd, scale, shift)
         ctx.relu, ctx.count, ctx.has_res, ctx.sync, ctx.training = relu, count, residual is not None, _sync_enabled(bn), bn.training
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x_raw, y, gamma, mean, invstd, scale = ctx.saved_tensors
+        x_raw, y, gamma, mean, invstd, scale, shift = ctx.saved_tensors
         M, C = x_raw.shape
         dy = dy.contiguous()
         dx = torch.empty(M, C, dtype=torch.bfloat16, device=dy.device)
@@ -227,16 +234,18 @@ class BNActFn(torch.autograd.Function):
             red = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
             from ._lib import check, lib, ptr, stream
             check(lib().pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), ptr(y), y.stride(0), ptr(x_raw), x_raw.stride(0), M, C,
-                                          ptr(mean), ptr(invstd), 1 if ctx.relu else 0, ptr(red), stream()))
+                                          ptr(mean), ptr(invstd), 1 if ctx.relu else 0, None, None, ptr(red), stream()))
             local = red.clone()
             dist.all_reduce(red)
             check(lib().pnx_bn_bwd_apply(ptr(dy), dy.stride(0), ptr(y), y.stride(0), ptr(x_raw), x_raw.stride(0), M, C,
                                          ptr(mean), ptr(invstd), ptr(gamma), ptr(red), float(max(ctx.count, 1)),
-                                         1 if ctx.relu else 0, ptr(dx), dx.stride(0), ptr(dres) if dres is not None else None,
+                                         1 if ctx.relu else 0, None, None, ptr(dx), dx.stride(0), ptr(dres) if dres is not None else None,
                                          dres.stride(0) if dres is not None else 8, 0, stream()))
             red = local
         else:
-            red = ops.bn_bwd(dy, y, x_raw, M, C, mean, invstd, gamma, ctx.count, ctx.relu, dx, dres=dres)
+            # without a residual the ReLU mask is recomputed from x_raw (one row-matrix read less per pass)
+            red = ops.bn_bwd(dy, y if ctx.has_res else None, x_raw, M, C, mean, invstd, gamma, ctx.count, ctx.relu, dx,
+                             dres=dres, affine=(scale, shift))
         r = red.float()
         return dx, None, r[C:], r[:C], dres, None, None, None
 

@@ -356,7 +356,8 @@ class SepHead(nn.Module):
         ga = torch.cat([getattr(self, n)[1].weight for n in names], 0)
         be = torch.cat([getattr(self, n)[1].bias for n in names], 0)
         bn = self._cat_bn(names)
-        raw, stats = Fn.conv(x, wa, ba, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), want_stats=True)
+        raw, stats = Fn.conv(x, wa, ba, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), want_stats=True,
+                             bias_feeds_bn=self.training)
         y = Fn.BNActFn.apply(raw, stats, ga, be, None, bn, True, raw.shape[0])
         if self.training:
             with torch.no_grad():
@@ -432,7 +433,7 @@ class CenterHead(nn.Module):
         _require_cuda(x, "CenterHead")
         rows, B, H, W = _to_rows(x)
         raw, stats = Fn.conv(rows, self.shared_conv[0].weight, self.shared_conv[0].bias, Fn.dense_spec(B, H, W, 3),
-                             Fn.WLayout("dense"), want_stats=True)
+                             Fn.WLayout("dense"), want_stats=True, bias_feeds_bn=self.training)
         y = Fn.bn_act(raw, stats, self.shared_conv[1], relu=True)
         return [task.run(y, B, H, W) for task in self.tasks]
 

@@ -354,16 +354,20 @@ def bn_apply(x, M, C, scale, shift, y, res=None, relu=True):
     return y
 
 
-def bn_bwd(dy, y, x, M, C, mean, invstd, gamma, count, relu, dx, dres=None, dres_accumulate=False):
-    """Returns red (fp64 [2C]: sum g = dbeta, sum g*xhat = dgamma); writes dx (and dres)."""
+def bn_bwd(dy, y, x, M, C, mean, invstd, gamma, count, relu, dx, dres=None, dres_accumulate=False, affine=None):
+    """Returns red (fp64 [2C]: sum g = dbeta, sum g*xhat = dgamma); writes dx (and dres).
+    y=None (no residual): the ReLU mask is recomputed from x with affine=(scale, shift) of the forward."""
     red = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
     L = lib()
-    yy = y if y is not None else dy
+    fs, fh = (affine if affine is not None else (None, None))
+    yp, ys = (ptr(y), y.stride(0)) if y is not None else (None, 8)
     _count(2)
-    check(L.pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), ptr(yy), yy.stride(0), ptr(x), x.stride(0), M, C, ptr(mean),
-                              ptr(invstd), 1 if relu else 0, ptr(red), stream()))
-    check(L.pnx_bn_bwd_apply(ptr(dy), dy.stride(0), ptr(yy), yy.stride(0), ptr(x), x.stride(0), M, C, ptr(mean),
-                             ptr(invstd), ptr(gamma), ptr(red), float(max(count, 1)), 1 if relu else 0, ptr(dx),
+    check(L.pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), yp, ys, ptr(x), x.stride(0), M, C, ptr(mean), ptr(invstd),
+                              1 if relu else 0, ptr(fs) if fs is not None else None, ptr(fh) if fh is not None else None,
+                              ptr(red), stream()))
+    check(L.pnx_bn_bwd_apply(ptr(dy), dy.stride(0), yp, ys, ptr(x), x.stride(0), M, C, ptr(mean), ptr(invstd),
+                             ptr(gamma), ptr(red), float(max(count, 1)), 1 if relu else 0,
+                             ptr(fs) if fs is not None else None, ptr(fh) if fh is not None else None, ptr(dx),
                              dx.stride(0), ptr(dres) if dres is not None else None,
                              dres.stride(0) if dres is not None else 8, 1 if dres_accumulate else 0, stream()))
     return red

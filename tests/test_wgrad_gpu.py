@@ -113,6 +113,11 @@ def test_bn_rows(M, C, relu, with_res):
     _close(red[C:].float(), gamma.grad)
     if with_res:
         assert torch.equal(dres.float(), torch.where(mask, dy.float(), torch.zeros(1, device="cuda")))
+    else:
+        # mask recomputed from x (y not read): identical result
+        dx2 = torch.empty_like(dx)
+        red2 = ops.bn_bwd(dy, None, x, M, C, mu, istd, gamma.detach(), M, relu, dx2, affine=(sc, sh))
+        assert torch.equal(dx2, dx) and torch.allclose(red2, red)
 
 
 def test_add_relu_roundtrip():
