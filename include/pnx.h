@@ -159,6 +159,16 @@ int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void
               double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
               long long ld_add, int sm_count, cudaStream_t stream);
 
+/* ---------------------------------------------------------------- dense 3x3 conv with TMA-folded im2col
+ * out[(b,y,x), n] = sum_{r,s<3} sum_c A[(b, y+r-1, x+s-1), c] * W[r*3+s, n, c] (+bias)(relu), zero padding,
+ * on a B x H x W channels-last image (A rows = pixels, row stride lda; W packed [9, Cout, Cin] like pnx_igemm).
+ * One 4-D TMA window load per (64-channel chunk, kernel row) feeds the three horizontal taps through shifted
+ * shared-memory descriptors.  bf16 output, optional BatchNorm statistics (fp64 [2*stats_C]).  Same layers as
+ * pnx_igemm's dense mode (aspp.py/conv.py/centerhead.py 3x3 convs, dilation 1) and their data gradients. */
+int pnx_conv3x3_win(const void* A, long long lda, int B, int H, int W, int Cin, const void* Wpacked, int Cout,
+                    int block_n, void* out, long long ldc, const float* bias, double* stats, int stats_C, int relu,
+                    int base_off_mode, int sm_count, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- tcgen05 weight gradient
  * dW[t, x, y] += sum_m X[m, x] * Y[g(m,t), y]   (fp32, red.global.add; zero dW first)
  * X = direct operand (output gradient; layer input for ConvTranspose2d, shuffle=1), Y = operand read through

@@ -61,3 +61,24 @@ int pnx_encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, u
   }
   return PNX_OK;
 }
+
+int pnx_encode_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                            const uint32_t box[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    pnx_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return PNX_ERR_CUDA;
+  }
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pnx_set_error("cuTensorMapEncodeTiled(4d) failed: CUresult %d", (int)r);
+    return PNX_ERR_CUDA;
+  }
+  return PNX_OK;
+}

@@ -123,9 +123,14 @@ class ConvFn(torch.autograd.Function):
         out_c = cout
         out = torch.empty(rows, out_c, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
         stats = torch.zeros(2 * cout if want_stats else 0, dtype=torch.float64, device=x.device)
-        ops.igemm(x, spec.M_out, wp, wp.shape[0], cin, n_cols, out, lda=x.stride(0), ldc=out_c, nbr=spec.nbr,
-                  dense=spec.dense, bias=bias, stats=stats if want_stats else None,
-                  stats_mod=cout if want_stats else None, shuffle=spec.shuffle, relu=relu)
+        if layout.kind == "dense" and spec.nbr is None and ops.win_eligible(spec.dense, n_cols, cin, out_fp32, spec.shuffle):
+            H_, W_ = spec.dense[0], spec.dense[1]
+            ops.conv3x3_win(x, spec.M_out // (H_ * W_), H_, W_, wp, cin, n_cols, out, bias=bias,
+                            stats=stats if want_stats else None, relu=relu)          # im2col folded into TMA
+        else:
+            ops.igemm(x, spec.M_out, wp, wp.shape[0], cin, n_cols, out, lda=x.stride(0), ldc=out_c, nbr=spec.nbr,
+                      dense=spec.dense, bias=bias, stats=stats if want_stats else None,
+                      stats_mod=cout if want_stats else None, shuffle=spec.shuffle, relu=relu)
         ctx.save_for_backward(x, w, out if relu else None)
         ctx.spec, ctx.layout, ctx.dims = spec, layout, (cin, cout, shape)
         ctx.has_bias, ctx.relu, ctx.out_fp32 = bias is not None, relu, out_fp32
@@ -165,7 +170,11 @@ class ConvFn(torch.autograd.Function):
             if cpad != cout:
                 wd = torch.nn.functional.pad(wd, (0, cpad - cout))
             dx = torch.empty(spec.M_in, cin, dtype=torch.bfloat16, device=dy.device)
-            ops.igemm(dy, spec.M_in, wd, wd.shape[0], cpad, cin, dx, nbr=spec.d_nbr, dense=spec.d_dense)
+            if layout.kind == "dense" and spec.d_nbr is None and ops.win_eligible(spec.d_dense, cin, cpad):
+                H_, W_ = spec.d_dense[0], spec.d_dense[1]
+                ops.conv3x3_win(dy, spec.M_in // (H_ * W_), H_, W_, wd, cpad, cin, dx)
+            else:
+                ops.igemm(dy, spec.M_in, wd, wd.shape[0], cpad, cin, dx, nbr=spec.d_nbr, dense=spec.d_dense)
             if x.shape[1] != cin:                                   # x was a column slice of a wider buffer
                 full = torch.zeros(x.shape[0], x.shape[1], dtype=torch.bfloat16, device=dy.device)
                 full[:, :cin] = dx

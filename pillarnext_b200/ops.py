@@ -330,6 +330,37 @@ def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None,
     return out
 
 
+WIN_BASE_OFF = 0   # measured on B200: the 128B swizzle is applied on absolute smem address bits, so row-shifted
+                   # descriptors need NO matrix base offset (tests/test_igemm_win_gpu.py checks both conventions)
+
+
+def win_eligible(dense, n_cols, k_cols, out_fp32=False, shuffle=False):
+    """Dense 3x3 stride-1 dilation-1 'same' conv whose image rows tile into 128-pixel chunks with <= 15 % waste."""
+    if dense is None or out_fp32 or shuffle:
+        return False
+    Ho, Wo, Hi, Wi, kw, mul, dil, pad = dense
+    if not (kw == 3 and mul == 1 and dil == 1 and pad == 1 and Ho == Hi and Wo == Wi):
+        return False
+    if n_cols % 64 or k_cols % 64:
+        return False
+    xc = (Wo + 127) // 128
+    return xc * 128 <= 1.15 * Wo
+
+
+def conv3x3_win(A, B, H, W, w_packed, cin, cout, out, *, bias=None, stats=None, relu=False, block_n=None, base_off=None):
+    """Dense 3x3 'same' conv with TMA-folded im2col (pnx_conv3x3_win). A bf16 rows [B*H*W, >=cin]; out bf16."""
+    assert A.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and tuple(w_packed.shape) == (9, cout, cin)
+    bn = block_n or (192 if cout % 192 == 0 else (128 if cout % 128 == 0 else 64))
+    M = B * H * W
+    _count(1)
+    with _Timed("igemm_win", 2.0 * M * 9 * cin * cout, 2.0 * M * (cin * 3 + cout), "M%d_K%d_N%d_bn%d" % (M, cin, cout, bn)):
+      check(lib().pnx_conv3x3_win(ptr(A), A.stride(0), B, H, W, cin, ptr(w_packed), cout, bn, ptr(out), out.stride(0),
+                                ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None,
+                                stats.numel() // 2 if stats is not None else 0, 1 if relu else 0,
+                                WIN_BASE_OFF if base_off is None else base_off, sm_count(), stream()))
+    return out
+
+
 def wgrad(X, x_channels, Y, y_channels, M, taps, dW, *, nbr=None, dense=None, shuffle=False, gathered=None):
     """dW[t, x, y] += sum_m X[m, x] * Y[g(m,t), y]; X direct, Y gathered; dW fp32 [taps, x_channels, y_channels]."""
     assert X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16 and dW.dtype == torch.float32

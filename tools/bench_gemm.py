@@ -48,3 +48,12 @@ run_wgrad("wgrad X384 Y64", 384, 64)
 run_wgrad("wgrad X64 Y384", 64, 384)
 run_wgrad("wgrad X256 Y256", 256, 256, m=m2, g=g2)
 run_wgrad("wgrad X64 Y64", 64, 64)
+def run_win(name, K, N, bn, m=M):
+    A = torch.randn(m, K, device="cuda").bfloat16(); Wp = (torch.randn(9, N, K, device="cuda") * 0.05).bfloat16()
+    out = torch.empty(m, N, device="cuda", dtype=torch.bfloat16)
+    st = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    ms = timeit(lambda: ops.conv3x3_win(A, B, H, W, Wp, K, N, out, stats=st, block_n=bn))
+    print("%-42s %7.3f ms %7.1f TF/s" % (name, ms, 2.0 * m * 9 * K * N / ms / 1e9), flush=True)
+run_win("WIN convA 64->384 bn192 +stats", 64, 384, 192)
+run_win("WIN convA-dgrad 384->64 bn64", 384, 64, 64)
+run_win("WIN 256->64 bn64", 256, 64, 64)
