@@ -46,9 +46,8 @@ template <int BN>
 struct Cfg {
   static constexpr uint32_t kBBytes = BN * 128;
   static constexpr int kStagesRaw = (192 * 1024) / (int)(kABytes + kBBytes);
-  static constexpr int kStagesCap = BN <= 64 ? 6 : 8;   // gather-bound shapes: leave >= 48 KB of L1 for cross-tap row reuse
+  static constexpr int kStagesCap = 8;
   static constexpr int kStages = kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw;
-  static constexpr int kLag = kStages >= 6 ? 4 : (kStages >= 4 ? kStages - 2 : 1);  // cp.async groups in flight per producer thread
   static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + 128 * 9 * 8 + 256 + 4 * 4096 + 2 * BN * 4 + BN * 4;
 };
 
@@ -72,13 +71,14 @@ __device__ __forceinline__ float colsum32(float (&v)[32]) {
 }
 
 template <int BN, int PW>
-__global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, IgemmParams p) {
+__global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
+                                                                  IgemmParams p) {
   using C = Cfg<BN>;
   constexpr int kProducerWarps = PW;
   constexpr int kProducerThreads = PW * 32;
   constexpr int kThreadsTotal = 64 + PW * 32 + 128;
   constexpr int kStages = C::kStages;
-  constexpr int kLag = C::kLag;
+  static_assert(PW <= kStages, "gather warps must not outnumber the stages (mbarrier parity)");
   constexpr uint32_t kBBytes = C::kBBytes;
   constexpr int kColBlk = BN >= 32 ? 32 : 16;
   constexpr int kNumCB = BN / kColBlk;
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)kStages * kABytes;
-  long long* s_off = reinterpret_cast<long long*>(sB + (size_t)kStages * kBBytes);  // [128 rows][T] element offsets, -1 = absent
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_off + 128 * 9);
+  int* s_idx = reinterpret_cast<int*>(sB + (size_t)kStages * kBBytes);  // [T][128 rows] gathered row index, -1 = absent
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_idx + 128 * 9 * 2);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
 
   if (warp == 0 && pnx::elect_one()) {
     pnx::tma_prefetch_desc(&wmap);
+    pnx::tma_prefetch_desc(&amap);
     for (int s = 0; s < kStages; ++s) {
-      pnx::mbar_init(&full[s], 1 + kProducerWarps);
+      pnx::mbar_init(&full[s], 2);  // weight producer + the gather warp of this stage (both arrive with expect_tx)
       pnx::mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -155,7 +156,6 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kc = 0; kc < num_k; ++kc) {
           pnx::mbar_wait(&full[stage], phase);
-          pnx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           pnx::tc_fence_after();
           const uint32_t a_base = pnx::smem_u32(sA + (size_t)stage * kABytes);
           const uint32_t b_base = pnx::smem_u32(sB + (size_t)stage * kBBytes);
@@ -174,15 +174,17 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
       }
     }
   } else if (warp < 2 + kProducerWarps) {
-    // ---------------------------------------------------------------- A gather producers
-    // Row offsets (row * lda, 64-bit) are computed once per tile into shared memory so the per-stage loop is one
-    // add + cp.async per 16 bytes.
+    // ---------------------------------------------------------------- A gather producers (TMA tile::gather4)
+    // One request = 4 arbitrary rows x 128 B of A, landed in the 128B-swizzled K-major tile; lane l of the issuing
+    // warp owns rows 4l..4l+3 of the 128-row tile, so one warp instruction fills a whole stage.  Absent neighbours
+    // are row index -1 = out of bounds = zero fill.  The (chunk, tap) stages of a tile go round-robin over the
+    // producer warps (a warp sustains ~8 B/clk of requests, the SM ~50 B/clk: tools/gather4_rate.cu).
+    // Row indices are computed once per tile into shared memory ([tap][row], one LDS.128 per request).
+    const int pw = warp - 2;
     const int ptid = threadIdx.x - 64;
-    const int sub_row = ptid >> 3, chunk = ptid & 7;
     const int hw = p.Hout * p.Wout;
     const float inv_hw = 1.0f / (float)hw, inv_w = 1.0f / (float)p.Wout;
-    int stage = 0, arr_stage = 0, pending = 0;
-    uint32_t phase = 0;
+    uint32_t g_base = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       named_bar_sync(1, kProducerThreads);
       for (int e = ptid; e < 128 * p.T; e += kProducerThreads) {
@@ -211,37 +213,23 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
             idx = m;
           }
         }
-        s_off[r * 9 + t] = idx < 0 ? -1ll : (long long)idx * p.lda;
+        s_idx[t * 128 + r] = idx;
       }
       named_bar_sync(1, kProducerThreads);
-      for (int kc = 0; kc < num_k; ++kc) {
+      // stage g (global count over tiles) belongs to warp g % PW: a warp's consecutive stages are exactly PW <= kStages
+      // apart, so it can never be two phases ahead of an `empty` barrier (the parity wait stays unambiguous)
+      for (int kc = (int)((pw + kProducerWarps - g_base % kProducerWarps) % kProducerWarps); kc < num_k; kc += kProducerWarps) {
         const int cc = kc / p.T, t = kc - cc * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
+        const uint32_t g = g_base + (uint32_t)kc;
+        const uint32_t stage = g % (uint32_t)kStages, phase = (g / (uint32_t)kStages) & 1u;
         pnx::mbar_wait(&empty[stage], phase ^ 1);
-        const uint32_t dst = pnx::smem_u32(sA + (size_t)stage * kABytes);
-        const __nv_bfloat16* col = p.A + cc * 64 + chunk * 8;
-#pragma unroll
-        for (int j = 0; j < 128 / (kProducerThreads / 8); ++j) {
-          const int r = j * (kProducerThreads / 8) + sub_row;
-          const long long off = s_off[r * 9 + t];
-          pnx::cp_async16_ca(dst + r * 128 + ((chunk ^ (r & 7)) << 4), col + (off < 0 ? 0 : off), off < 0 ? 0u : 16u);
-        }
-        pnx::cp_async_commit();
-        if (pending == kLag) {
-          pnx::cp_async_wait<kLag>();
-          __syncwarp();
-          if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
-          if (++arr_stage == kStages) arr_stage = 0;
-        } else {
-          ++pending;
-        }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (lane == 0) pnx::mbar_arrive_expect_tx(&full[stage], kABytes);
+        __syncwarp();
+        const int4 rows = *reinterpret_cast<const int4*>(s_idx + t * 128 + 4 * lane);
+        pnx::tma_gather4(&amap, &full[stage], pnx::smem_u32(sA + (size_t)stage * kABytes) + lane * 512, cc * 64, rows.x,
+                         rows.y, rows.z, rows.w);
       }
-    }
-    pnx::cp_async_wait<0>();
-    __syncwarp();
-    for (; pending > 0; --pending) {
-      if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
-      if (++arr_stage == kStages) arr_stage = 0;
+      g_base += (uint32_t)num_k;
     }
   } else {
     // ---------------------------------------------------------------- epilogue (4 warps = 128 TMEM lanes)
@@ -428,7 +416,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
 }
 
 template <int BN, int PW>
-int launch_igemm(const CUtensorMap& wmap, const IgemmParams& p, int n_blocks, int sm_count, cudaStream_t stream) {
+int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmParams& p, int n_blocks, int sm_count, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmem));
@@ -439,7 +427,7 @@ int launch_igemm(const CUtensorMap& wmap, const IgemmParams& p, int n_blocks, in
   if (gx < 1) gx = 1;
   if (gx > num_tiles) gx = num_tiles;
   dim3 grid(gx, n_blocks);
-  igemm_kernel<BN, PW><<<grid, 64 + PW * 32 + 128, Cfg<BN>::kSmem, stream>>>(wmap, p);
+  igemm_kernel<BN, PW><<<grid, 64 + PW * 32 + 128, Cfg<BN>::kSmem, stream>>>(wmap, amap, p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -482,14 +470,19 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   int rc = pnx_encode_tmap_2d_bf16(&wmap, Wpacked, (uint64_t)taps * Cout, (uint64_t)Cin, (uint64_t)Cin * 2,
                                    (uint32_t)block_n, 64);
   if (rc) return rc;
+  // A as a 2-D tensor [rows, Cin] for tile::gather4 (box = one 64-channel row).  The row count only bounds the
+  // out-of-range test of the gather (index -1 = absent neighbour = zero fill); valid indices come from the caller.
+  CUtensorMap amap;
+  rc = pnx_encode_tmap_gather_bf16(&amap, A, (uint64_t)0x7fffffff, (uint64_t)Cin, (uint64_t)lda * 2);
+  if (rc) return rc;
   const int n_blocks = Cout / block_n;
   switch (block_n) {
-    case 16: return launch_igemm<16, 8>(wmap, p, n_blocks, sm_count, stream);
-    case 32: return launch_igemm<32, 8>(wmap, p, n_blocks, sm_count, stream);
-    case 64: return launch_igemm<64, 8>(wmap, p, n_blocks, sm_count, stream);
-    case 128: return launch_igemm<128, 4>(wmap, p, n_blocks, sm_count, stream);
-    case 192: return launch_igemm<192, 4>(wmap, p, n_blocks, sm_count, stream);
-    case 256: return launch_igemm<256, 4>(wmap, p, n_blocks, sm_count, stream);
+    case 16: return launch_igemm<16, 8>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 32: return launch_igemm<32, 8>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 64: return launch_igemm<64, 8>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 128: return launch_igemm<128, 6>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 192: return launch_igemm<192, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 256: return launch_igemm<256, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     default:
       pnx_set_error("pnx_igemm: unsupported block_n %d (16/32/64/128/192/256)", block_n);
       return PNX_ERR_ARG;

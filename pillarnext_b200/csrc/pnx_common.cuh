@@ -126,6 +126,18 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// tile::gather4: four arbitrary rows (r0..r3) of a 2-D tensor, box = [box_cols x 1]; the rows land consecutively at
+// dst (128B swizzle by absolute smem address); a row index outside [0, rows) is zero-filled and still counted in
+// the mbarrier transaction bytes (measured: tools/gather4_rate.cu).
+__device__ __forceinline__ void tma_gather4(const CUtensorMap* m, uint64_t* bar, uint32_t dst, int c0, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
@@ -216,5 +228,7 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 
 // host: encode a 2-D bf16 tensor map (rows x cols, row-major), box = box_rows x box_cols, SWIZZLE_128B.
 // Resolved through cudaGetDriverEntryPoint so the library links without libcuda.
+int pnx_encode_tmap_gather_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                                uint64_t row_stride_bytes);
 int pnx_encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                             uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);

@@ -50,8 +50,7 @@ struct WCfg {
   static constexpr uint32_t kStageBytes = (2 * XB + TG * kYAtoms) * kBlk;
   static constexpr int kStagesRaw = (196 * 1024) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kLag = kStages - 1;  // cp.async groups kept in flight per producer thread (must stay < kStages)
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + (size_t)kStages * kKS * (TG + 1) * 8;
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + (size_t)kStages * kKS * TG * 4;
   static_assert(NYC * TG * XB <= 512, "TMEM budget");
   static_assert(kStages >= 2, "need at least two stages");
 };
@@ -70,16 +69,17 @@ __device__ __forceinline__ void divmod_fast(int n, int d, float inv_d, int& q, i
 
 // XB = number of 128-channel X blocks per CTA (2 halves the re-gathering of Y when the TMEM budget allows)
 template <int NYC, int TG, int XB>
-__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                            const __grid_constant__ CUtensorMap ymap, WgradParams p) {
   using C = WCfg<NYC, TG, XB>;
-  constexpr int kStages = C::kStages, kLag = C::kLag, kYAtoms = C::kYAtoms;
+  constexpr int kStages = C::kStages, kYAtoms = C::kYAtoms;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * C::kStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* done = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-  long long* s_rows = reinterpret_cast<long long*>(smem + (size_t)kStages * C::kStageBytes + 256);  // [kStages][TG+1][kKS] element offsets
+  int* s_idx = reinterpret_cast<int*>(smem + (size_t)kStages * C::kStageBytes + 256);  // [kStages][TG][kKS] gathered row index (-1 = absent)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int xb = blockIdx.x / p.y_chunks, yc = blockIdx.x - xb * p.y_chunks;
@@ -91,8 +91,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
   const int num_k = (m_end - m_begin + kKS - 1) / kKS;
 
   if (warp == 0 && pnx::elect_one()) {
+    pnx::tma_prefetch_desc(&xmap);
+    pnx::tma_prefetch_desc(&ymap);
     for (int s = 0; s < kStages; ++s) {
-      pnx::mbar_init(&full[s], kProducerWarps);
+      pnx::mbar_init(&full[s], 1 + kProducerWarps);  // X tile thread + every gather warp (arrive with expect_tx)
       pnx::mbar_init(&empty[s], 1);
     }
     pnx::mbar_init(done, 1);
@@ -116,7 +118,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
         const int total_atoms = ntaps * kYAtoms;
         for (int kc = 0; kc < num_k; ++kc) {
           pnx::mbar_wait(&full[stage], phase);
-          pnx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           pnx::tc_fence_after();
           const uint32_t sx = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
           const uint32_t sy = sx + 2 * XB * kBlk;
@@ -138,92 +139,80 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
         }
         pnx::umma_commit(done);
       }
+    } else if (warp == 0) {
+      // ---------------------------------------------------------------- X tile producer: plain 2-D TMA boxes of
+      // [64 rows x 64 channels] (rows past M are zero-filled by the tensor map bounds)
+      if (pnx::elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int nblk = p.x_dup ? 1 : 2 * XB;
+        const int x_ch0 = xb * 128 * XB;
+        for (int kc = 0; kc < num_k; ++kc) {
+          pnx::mbar_wait(&empty[stage], phase ^ 1);
+          pnx::mbar_arrive_expect_tx(&full[stage], (uint32_t)nblk * kBlk);
+          uint8_t* sx = smem + (size_t)stage * C::kStageBytes;
+          for (int b2 = 0; b2 < nblk; ++b2)
+            pnx::tma_load_2d(&xmap, &full[stage], sx + b2 * kBlk, x_ch0 + b2 * 64, m_begin + kc * kKS);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
     } else if (warp >= 2 && warp < 2 + kProducerWarps) {
-      // ---------------------------------------------------------------- producers (8 warps: two per scheduler so the
-      // integer/address latency of the copy loop is hidden; 64-bit row offsets come from a per-chunk smem table)
+      // ---------------------------------------------------------------- Y gather producers (TMA tile::gather4)
+      // One request = 4 rows x 128 B of one (tap, 64-channel atom) block; the ntaps*kYAtoms*16 requests of a chunk are
+      // dealt round-robin to the producer warps (a warp serialises its lanes' requests, ~66 clk each, so spreading
+      // them is what buys bandwidth: tools/gather4_rate.cu).  Row indices go through a per-stage smem table.
       const int ptid = threadIdx.x - 64;
-      const int sub_row = ptid >> 3, chunk = ptid & 7;
-      const int x_ch0 = xb * 128 * XB, y_ch0 = yc * NYC;
+      const int pw = warp - 2;
+      const int y_ch0 = yc * NYC;
       const int hw = p.Hout * p.Wout;
-      const __nv_bfloat16* xbase = p.X + x_ch0 + chunk * 8;
-      const __nv_bfloat16* ybase = p.Y + y_ch0 + chunk * 8;
-      int stage = 0, arr_stage = 0, pending = 0;
+      const int nreq = ntaps * kYAtoms * 16;
+      const int q = lane * kProducerWarps + pw;        // this thread's request of the chunk (if < nreq)
+      const int my_blk = q >> 4, my_l16 = q & 15;      // block = tap * kYAtoms + atom
+      const int my_tap = my_blk / kYAtoms, my_atom = my_blk - my_tap * kYAtoms;
+      const int my_cnt = nreq > pw ? (nreq - pw + kProducerWarps - 1) / kProducerWarps : 0;  // requests of this warp
+      int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < num_k; ++kc) {
-        // rows[0][r] = direct row offset (or -1), rows[1+j][r] = gathered row offset of tap t0+j
-        long long* rows = s_rows + stage * (TG + 1) * kKS;
-        for (int e = ptid; e < (ntaps + 1) * kKS; e += kProducerThreads) {
+        int* tbl = s_idx + stage * (TG * kKS);
+        for (int e = ptid; e < ntaps * kKS; e += kProducerThreads) {
           const int j = e / kKS, r = e - j * kKS;
           const int m = m_begin + kc * kKS + r;
-          long long off = -1;
+          int g = -1;
           if (m < m_end) {
-            if (j == 0) {
-              off = (long long)m * p.ldx;
+            const int t = t0 + j;
+            if (!p.gathered) {
+              g = m;
+            } else if (p.nbr) {
+              g = p.nbr[(size_t)m * p.T + t];
             } else {
-              const int t = t0 + j - 1;
-              int g;
-              if (!p.gathered) {
-                g = m;
-              } else if (p.nbr) {
-                g = p.nbr[(size_t)m * p.T + t];
+              int b, rem, y, x;
+              divmod_fast(m, hw, p.inv_hw, b, rem);
+              divmod_fast(rem, p.Wout, p.inv_w, y, x);
+              if (p.shuffle) {
+                g = (b * 2 * p.Hout + 2 * y + (t >> 1)) * (2 * p.Wout) + 2 * x + (t & 1);
               } else {
-                int b, rem, y, x;
-                divmod_fast(m, hw, p.inv_hw, b, rem);
-                divmod_fast(rem, p.Wout, p.inv_w, y, x);
-                if (p.shuffle) {
-                  g = (b * 2 * p.Hout + 2 * y + (t >> 1)) * (2 * p.Wout) + 2 * x + (t & 1);
-                } else {
-                  int rr, ss;
-                  divmod_fast(t, p.kw, p.inv_kw, rr, ss);
-                  const int yi = y * p.mul + rr * p.dil - p.pad, xi = x * p.mul + ss * p.dil - p.pad;
-                  g = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
-                }
+                int rr, ss;
+                divmod_fast(t, p.kw, p.inv_kw, rr, ss);
+                const int yi = y * p.mul + rr * p.dil - p.pad, xi = x * p.mul + ss * p.dil - p.pad;
+                g = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
               }
-              off = g < 0 ? -1ll : (long long)g * p.ldy;
             }
           }
-          rows[j * kKS + r] = off;
+          tbl[j * kKS + r] = g;
         }
-        pnx::mbar_wait(&empty[stage], phase ^ 1);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const uint32_t sx = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
-        const uint32_t sy = sx + 2 * XB * kBlk;
-#pragma unroll
-        for (int j2 = 0; j2 < kKS / 32; ++j2) {
-          const int r = j2 * 32 + sub_row;
-          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
-          const long long ox = rows[r];
-          const __nv_bfloat16* xs = xbase + (ox < 0 ? 0 : ox);
-          const uint32_t nbx = ox < 0 ? 0u : 16u;
-          pnx::cp_async16(sx + off, xs, nbx);
-          if (!p.x_dup) {
-#pragma unroll
-            for (int b2 = 1; b2 < 2 * XB; ++b2) pnx::cp_async16(sx + b2 * kBlk + off, xs + b2 * 64, nbx);
-          }
-          for (int j = 0; j < ntaps; ++j) {
-            const long long oy = rows[(1 + j) * kKS + r];
-            const __nv_bfloat16* ys = ybase + (oy < 0 ? 0 : oy);
-            const uint32_t nby = (oy < 0 || ox < 0) ? 0u : 16u;
-#pragma unroll
-            for (int a = 0; a < kYAtoms; ++a) pnx::cp_async16_ca(sy + (j * kYAtoms + a) * kBlk + off, ys + a * 64, nby);
-          }
+        pnx::mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) {
+          if (my_cnt > 0) pnx::mbar_arrive_expect_tx(&full[stage], (uint32_t)my_cnt * 512u);
+          else pnx::mbar_arrive(&full[stage]);
         }
-        pnx::cp_async_commit();
-        if (pending == kLag) {
-          pnx::cp_async_wait<kLag>();
-          __syncwarp();
-          if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
-          if (++arr_stage == kStages) arr_stage = 0;
-        } else {
-          ++pending;
+        __syncwarp();
+        if (q < nreq) {
+          const int4 rows = *reinterpret_cast<const int4*>(tbl + my_tap * kKS + 4 * my_l16);
+          const uint32_t dst = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes) + (2 * XB + my_blk) * kBlk + my_l16 * 512;
+          pnx::tma_gather4(&ymap, &full[stage], dst, y_ch0 + my_atom * 64, rows.x, rows.y, rows.z, rows.w);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-      pnx::cp_async_wait<0>();
-      __syncwarp();
-      for (; pending > 0; --pending) {
-        if (lane == 0) pnx::mbar_arrive(&full[arr_stage]);
-        if (++arr_stage == kStages) arr_stage = 0;
       }
     } else if (warp >= 2 + kProducerWarps) {
       // ---------------------------------------------------------------- epilogue: TMEM -> red.global.add
@@ -256,7 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradParams p) {
 }
 
 template <int NYC, int TG, int XB>
-int launch_wgrad(WgradParams p, int x_blocks, int sm_count, cudaStream_t stream) {
+int launch_wgrad(const CUtensorMap& xmap, const CUtensorMap& ymap, WgradParams p, int x_blocks, int sm_count,
+                 cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     PNX_CUDA(cudaFuncSetAttribute(wgrad_kernel<NYC, TG, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -278,7 +268,7 @@ int launch_wgrad(WgradParams p, int x_blocks, int sm_count, cudaStream_t stream)
   p.rows_per_split = ((p.M + splits - 1) / splits + kKS - 1) / kKS * kKS;
   splits = (p.M + p.rows_per_split - 1) / p.rows_per_split;
   dim3 grid(x_blocks * p.y_chunks, groups, splits);
-  wgrad_kernel<NYC, TG, XB><<<grid, kThreads, WCfg<NYC, TG, XB>::kSmem, stream>>>(p);
+  wgrad_kernel<NYC, TG, XB><<<grid, kThreads, WCfg<NYC, TG, XB>::kSmem, stream>>>(xmap, ymap, p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -311,12 +301,18 @@ extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, const voi
   p.inv_kw = 1.0f / (float)p.kw;
   p.y_chunks = 1; p.taps_per_group = 1; p.rows_per_split = M;
   const int x_blocks = x_channels == 64 ? 1 : x_channels / 128;
+  PNX_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "X/Y 16-byte aligned");
+  CUtensorMap xmap, ymap;
+  int rc = pnx_encode_tmap_2d_bf16(&xmap, X, (uint64_t)M, (uint64_t)x_channels, (uint64_t)ldx * 2, kKS, 64);
+  if (rc) return rc;
+  rc = pnx_encode_tmap_gather_bf16(&ymap, Y, (uint64_t)0x7fffffff, (uint64_t)y_channels, (uint64_t)ldy * 2);
+  if (rc) return rc;
   // Y chunk: the largest of 256/192/128/64 dividing y_channels; taps per group bounded by 512 TMEM columns
   if (y_channels % 256 == 0) {
-    if (x_blocks % 2 == 0) return launch_wgrad<256, 1, 2>(p, x_blocks, sm_count, stream);  // 256 x 256 accumulators
-    return launch_wgrad<256, 1, 1>(p, x_blocks, sm_count, stream);
+    if (x_blocks % 2 == 0) return launch_wgrad<256, 1, 2>(xmap, ymap, p, x_blocks, sm_count, stream);  // 256 x 256 accumulators
+    return launch_wgrad<256, 1, 1>(xmap, ymap, p, x_blocks, sm_count, stream);
   }
-  if (y_channels % 192 == 0) return launch_wgrad<192, 2, 1>(p, x_blocks, sm_count, stream);
-  if (y_channels % 128 == 0) return launch_wgrad<128, 3, 1>(p, x_blocks, sm_count, stream);
-  return launch_wgrad<64, 5, 1>(p, x_blocks, sm_count, stream);
+  if (y_channels % 192 == 0) return launch_wgrad<192, 2, 1>(xmap, ymap, p, x_blocks, sm_count, stream);
+  if (y_channels % 128 == 0) return launch_wgrad<128, 3, 1>(xmap, ymap, p, x_blocks, sm_count, stream);
+  return launch_wgrad<64, 5, 1>(xmap, ymap, p, x_blocks, sm_count, stream);
 }
