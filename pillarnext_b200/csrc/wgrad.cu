@@ -38,7 +38,9 @@ struct WgradParams {
 
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = 64 + kProducerThreads + 128;
+constexpr int kIndexWarps = 4;         // compute the gathered row indices one or more chunks ahead of the gather warps
+constexpr int kIndexThreads = kIndexWarps * 32;
+constexpr int kThreads = 64 + kProducerThreads + kIndexThreads + 128;
 constexpr int kKS = 64;               // rows (K) per stage
 constexpr uint32_t kBlk = kKS * 128;  // bytes of one [64 rows x 64 ch] block
 constexpr int kMaxTG = 8;
@@ -78,7 +80,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * C::kStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* done = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* tbl_full = done + 1;            // index warps -> gather warps (per stage)
+  uint64_t* tbl_empty = tbl_full + kStages;  // gather warps -> index warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbl_empty + kStages);
   int* s_idx = reinterpret_cast<int*>(smem + (size_t)kStages * C::kStageBytes + 256);  // [kStages][TG][kKS] gathered row index (-1 = absent)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,6 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     for (int s = 0; s < kStages; ++s) {
       pnx::mbar_init(&full[s], 1 + kProducerWarps);  // X tile thread + every gather warp (arrive with expect_tx)
       pnx::mbar_init(&empty[s], 1);
+      pnx::mbar_init(&tbl_full[s], kIndexWarps);
+      pnx::mbar_init(&tbl_empty[s], kProducerWarps);
     }
     pnx::mbar_init(done, 1);
     pnx::fence_barrier_init();
@@ -160,11 +166,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       // ---------------------------------------------------------------- Y gather producers (TMA tile::gather4)
       // One request = 4 rows x 128 B of one (tap, 64-channel atom) block; the ntaps*kYAtoms*16 requests of a chunk are
       // dealt round-robin to the producer warps (a warp serialises its lanes' requests, ~66 clk each, so spreading
-      // them is what buys bandwidth: tools/gather4_rate.cu).  Row indices go through a per-stage smem table.
-      const int ptid = threadIdx.x - 64;
+      // them is what buys bandwidth: tools/gather4_rate.cu).  Row indices come from the index warps' smem table.
       const int pw = warp - 2;
       const int y_ch0 = yc * NYC;
-      const int hw = p.Hout * p.Wout;
       const int nreq = ntaps * kYAtoms * 16;
       const int q = lane * kProducerWarps + pw;        // this thread's request of the chunk (if < nreq)
       const int my_blk = q >> 4, my_l16 = q & 15;      // block = tap * kYAtoms + atom
@@ -173,34 +177,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < num_k; ++kc) {
-        int* tbl = s_idx + stage * (TG * kKS);
-        for (int e = ptid; e < ntaps * kKS; e += kProducerThreads) {
-          const int j = e / kKS, r = e - j * kKS;
-          const int m = m_begin + kc * kKS + r;
-          int g = -1;
-          if (m < m_end) {
-            const int t = t0 + j;
-            if (!p.gathered) {
-              g = m;
-            } else if (p.nbr) {
-              g = p.nbr[(size_t)m * p.T + t];
-            } else {
-              int b, rem, y, x;
-              divmod_fast(m, hw, p.inv_hw, b, rem);
-              divmod_fast(rem, p.Wout, p.inv_w, y, x);
-              if (p.shuffle) {
-                g = (b * 2 * p.Hout + 2 * y + (t >> 1)) * (2 * p.Wout) + 2 * x + (t & 1);
-              } else {
-                int rr, ss;
-                divmod_fast(t, p.kw, p.inv_kw, rr, ss);
-                const int yi = y * p.mul + rr * p.dil - p.pad, xi = x * p.mul + ss * p.dil - p.pad;
-                g = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
-              }
-            }
-          }
-          tbl[j * kKS + r] = g;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int* tbl = s_idx + stage * (TG * kKS);
+        pnx::mbar_wait(&tbl_full[stage], phase);
+        int4 rows = make_int4(-1, -1, -1, -1);
+        if (q < nreq) rows = *reinterpret_cast<const int4*>(tbl + my_tap * kKS + 4 * my_l16);
+        __syncwarp();
+        if (lane == 0) pnx::mbar_arrive(&tbl_empty[stage]);
         pnx::mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
           if (my_cnt > 0) pnx::mbar_arrive_expect_tx(&full[stage], (uint32_t)my_cnt * 512u);
@@ -208,13 +190,79 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         }
         __syncwarp();
         if (q < nreq) {
-          const int4 rows = *reinterpret_cast<const int4*>(tbl + my_tap * kKS + 4 * my_l16);
           const uint32_t dst = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes) + (2 * XB + my_blk) * kBlk + my_l16 * 512;
           pnx::tma_gather4(&ymap, &full[stage], dst, y_ch0 + my_atom * 64, rows.x, rows.y, rows.z, rows.w);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-    } else if (warp >= 2 + kProducerWarps) {
+    } else if (warp >= 2 + kProducerWarps && warp < 2 + kProducerWarps + kIndexWarps) {
+      // ---------------------------------------------------------------- index warps: gathered row of (tap j, row r) for
+      // every chunk, written to the stage's table ahead of the gather warps.  Thread e handles row r = e & 63 of taps
+      // j = (e >> 6) + 2n; the (image, y, x) decomposition of its row advances incrementally by 64 rows per chunk, so
+      // the steady state has no division (dense geometry) / one prefetched table load per entry (sparse).
+      const int itid = threadIdx.x - 64 - kProducerThreads;
+      const int r = itid & (kKS - 1), j0 = itid >> 6;
+      constexpr int kN = (TG + 1) / 2;                 // entries per thread per chunk
+      const bool dense = p.gathered && !p.nbr;
+      int b = 0, y = 0, x = 0;
+      int m = m_begin + r;
+      if (dense) {
+        const int hw = p.Hout * p.Wout;
+        b = m / hw;
+        const int rem = m - b * hw;
+        y = rem / p.Wout;
+        x = rem - y * p.Wout;
+      }
+      int dyv[kN], dxv[kN], tv[kN], pre[kN];
+#pragma unroll
+      for (int n = 0; n < kN; ++n) {
+        const int j = j0 + 2 * n;
+        const int t = t0 + j;
+        tv[n] = j < ntaps ? t : -1;
+        const int rr = t / p.kw, ss = t - rr * p.kw;
+        dyv[n] = p.shuffle ? (t >> 1) : rr * p.dil - p.pad;
+        dxv[n] = p.shuffle ? (t & 1) : ss * p.dil - p.pad;
+        pre[n] = (p.nbr && tv[n] >= 0 && m < m_end) ? p.nbr[(size_t)m * p.T + tv[n]] : -1;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kc = 0; kc < num_k; ++kc) {
+        int* tbl = s_idx + stage * (TG * kKS);
+        int val[kN];
+        const int m_next = m + kKS;
+#pragma unroll
+        for (int n = 0; n < kN; ++n) {
+          int g = -1;
+          if (tv[n] >= 0 && m < m_end) {
+            if (!p.gathered) {
+              g = m;
+            } else if (p.nbr) {
+              g = pre[n];
+            } else if (p.shuffle) {
+              g = (b * 2 * p.Hout + 2 * y + dyv[n]) * (2 * p.Wout) + 2 * x + dxv[n];
+            } else {
+              const int yi = y * p.mul + dyv[n], xi = x * p.mul + dxv[n];
+              g = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
+            }
+          }
+          val[n] = g;
+          if (p.nbr) pre[n] = (tv[n] >= 0 && m_next < m_end) ? p.nbr[(size_t)m_next * p.T + tv[n]] : -1;  // next chunk
+        }
+        pnx::mbar_wait(&tbl_empty[stage], phase ^ 1);
+#pragma unroll
+        for (int n = 0; n < kN; ++n)
+          if (tv[n] >= 0) tbl[(j0 + 2 * n) * kKS + r] = val[n];
+        __syncwarp();
+        if (lane == 0) pnx::mbar_arrive(&tbl_full[stage]);
+        m = m_next;
+        if (dense) {
+          x += kKS;
+          while (x >= p.Wout) { x -= p.Wout; ++y; }
+          while (y >= p.Hout) { y -= p.Hout; ++b; }
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp >= 2 + kProducerWarps + kIndexWarps) {
       // ---------------------------------------------------------------- epilogue: TMEM -> red.global.add
       const int quarter = warp & 3;
       while (!pnx::mbar_try_wait(done, 0)) __nanosleep(256);  // long wait: leave the issue slots to the producers
