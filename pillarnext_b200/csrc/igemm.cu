@@ -71,12 +71,13 @@ __device__ __forceinline__ float colsum32(float (&v)[32]) {
 }
 
 template <int BN, int PW>
-__global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
+__global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
                                                                   IgemmParams p) {
   using C = Cfg<BN>;
   constexpr int kProducerWarps = PW;
   constexpr int kProducerThreads = PW * 32;
-  constexpr int kThreadsTotal = 64 + PW * 32 + 128;
+  constexpr int kIndexWarps = 2;  // compute the gathered row indices of the next tile while the gather warps issue
+  constexpr int kThreadsTotal = 64 + PW * 32 + kIndexWarps * 32 + 128;
   constexpr int kStages = C::kStages;
   static_assert(PW <= kStages, "gather warps must not outnumber the stages (mbarrier parity)");
   constexpr uint32_t kBBytes = C::kBBytes;
@@ -92,7 +93,9 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tbl_full = tempty + 2;    // index warps -> gather warps (two tile tables)
+  uint64_t* tbl_empty = tbl_full + 2;  // gather warps -> index warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbl_empty + 2);
   float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [4 warps][4 KB] store staging slabs
   float* s_stat = s_tr + 4096;                                                        // [2][BN] per-channel sum / sumsq (smem atomics)
   float* s_bias = s_stat + 2 * BN;                                                // [BN] bias of this CTA's column block
@@ -110,6 +113,8 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
     for (int a = 0; a < 2; ++a) {
       pnx::mbar_init(&tfull[a], 1);
       pnx::mbar_init(&tempty[a], 4);
+      pnx::mbar_init(&tbl_full[a], kIndexWarps);
+      pnx::mbar_init(&tbl_empty[a], kProducerWarps);
     }
     pnx::fence_barrier_init();
   }
@@ -177,59 +182,85 @@ __global__ void __launch_bounds__(64 + PW * 32 + 128, 1) igemm_kernel(const __gr
     // ---------------------------------------------------------------- A gather producers (TMA tile::gather4)
     // One request = 4 arbitrary rows x 128 B of A, landed in the 128B-swizzled K-major tile; lane l of the issuing
     // warp owns rows 4l..4l+3 of the 128-row tile, so one warp instruction fills a whole stage.  Absent neighbours
-    // are row index -1 = out of bounds = zero fill.  The (chunk, tap) stages of a tile go round-robin over the
-    // producer warps (a warp sustains ~8 B/clk of requests, the SM ~50 B/clk: tools/gather4_rate.cu).
-    // Row indices are computed once per tile into shared memory ([tap][row], one LDS.128 per request).
+    // are row index -1 = out of bounds = zero fill.  The (chunk, tap) stages go round-robin over the producer warps
+    // (a warp sustains ~8 B/clk of requests, the SM ~50 B/clk: tools/gather4_rate.cu).  Row indices come from the
+    // index warps' table of the tile ([tap][row], one LDS.128 per request).
     const int pw = warp - 2;
-    const int ptid = threadIdx.x - 64;
-    const int hw = p.Hout * p.Wout;
-    const float inv_hw = 1.0f / (float)hw, inv_w = 1.0f / (float)p.Wout;
     uint32_t g_base = 0;
+    int tb = 0;
+    uint32_t tb_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      named_bar_sync(1, kProducerThreads);
-      for (int e = ptid; e < 128 * p.T; e += kProducerThreads) {
-        const int r = e / p.T, t = e - r * p.T;
-        const int m = tile * 128 + r;
-        int idx = -1;
-        if (m < p.M) {
-          if (p.nbr) {
-            idx = p.nbr[(size_t)m * p.T + t];
-          } else if (p.dense) {
-            int b, rem, y, x;
-            if (m < (1 << 24)) {
-              b = __float2int_rz(__int2float_rn(m) * inv_hw);
-              rem = m - b * hw;
-              if (rem < 0) { --b; rem += hw; } else if (rem >= hw) { ++b; rem -= hw; }
-              y = __float2int_rz(__int2float_rn(rem) * inv_w);
-              x = rem - y * p.Wout;
-              if (x < 0) { --y; x += p.Wout; } else if (x >= p.Wout) { ++y; x -= p.Wout; }
-            } else {
-              b = m / hw; rem = m - b * hw; y = rem / p.Wout; x = rem - y * p.Wout;
-            }
-            const int rr = t / p.kw, ss = t - rr * p.kw;
-            const int yi = y * p.mul + rr * p.dil - p.pad, xi = x * p.mul + ss * p.dil - p.pad;
-            idx = (yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win) ? (b * p.Hin + yi) * p.Win + xi : -1;
-          } else {
-            idx = m;
-          }
-        }
-        s_idx[t * 128 + r] = idx;
-      }
-      named_bar_sync(1, kProducerThreads);
+      const int* tbl = s_idx + tb * (128 * 9);
+      pnx::mbar_wait(&tbl_full[tb], tb_phase);
       // stage g (global count over tiles) belongs to warp g % PW: a warp's consecutive stages are exactly PW <= kStages
       // apart, so it can never be two phases ahead of an `empty` barrier (the parity wait stays unambiguous)
       for (int kc = (int)((pw + kProducerWarps - g_base % kProducerWarps) % kProducerWarps); kc < num_k; kc += kProducerWarps) {
         const int cc = kc / p.T, t = kc - cc * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
         const uint32_t g = g_base + (uint32_t)kc;
         const uint32_t stage = g % (uint32_t)kStages, phase = (g / (uint32_t)kStages) & 1u;
+        const int4 rows = *reinterpret_cast<const int4*>(tbl + t * 128 + 4 * lane);
         pnx::mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) pnx::mbar_arrive_expect_tx(&full[stage], kABytes);
         __syncwarp();
-        const int4 rows = *reinterpret_cast<const int4*>(s_idx + t * 128 + 4 * lane);
         pnx::tma_gather4(&amap, &full[stage], pnx::smem_u32(sA + (size_t)stage * kABytes) + lane * 512, cc * 64, rows.x,
                          rows.y, rows.z, rows.w);
       }
       g_base += (uint32_t)num_k;
+      __syncwarp();
+      if (lane == 0) pnx::mbar_arrive(&tbl_empty[tb]);
+      tb ^= 1;
+      if (tb == 0) tb_phase ^= 1;
+    }
+  } else if (warp < 2 + kProducerWarps + kIndexWarps) {
+    // ---------------------------------------------------------------- index warps: gathered row of (row r, tap t) for the
+    // NEXT tile while the gather warps work on the current one (two tables).  Thread i owns rows i and i + 64.
+    const int itid = threadIdx.x - 64 - kProducerWarps * 32;
+    const int hw = p.Hout * p.Wout;
+    const float inv_hw = 1.0f / (float)hw, inv_w = 1.0f / (float)p.Wout;
+    int tb = 0;
+    uint32_t tb_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int* tbl = s_idx + tb * (128 * 9);
+      pnx::mbar_wait(&tbl_empty[tb], tb_phase ^ 1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = itid + 64 * h;
+        const int m = tile * 128 + r;
+        if (m >= p.M) {
+          for (int t = 0; t < p.T; ++t) tbl[t * 128 + r] = -1;
+        } else if (p.nbr) {
+          const int* src = p.nbr + (size_t)m * p.T;
+          for (int t = 0; t < p.T; ++t) tbl[t * 128 + r] = src[t];
+        } else if (p.dense) {
+          int b, rem, y, x;
+          if (m < (1 << 24)) {
+            b = __float2int_rz(__int2float_rn(m) * inv_hw);
+            rem = m - b * hw;
+            if (rem < 0) { --b; rem += hw; } else if (rem >= hw) { ++b; rem -= hw; }
+            y = __float2int_rz(__int2float_rn(rem) * inv_w);
+            x = rem - y * p.Wout;
+            if (x < 0) { --y; x += p.Wout; } else if (x >= p.Wout) { ++y; x -= p.Wout; }
+          } else {
+            b = m / hw; rem = m - b * hw; y = rem / p.Wout; x = rem - y * p.Wout;
+          }
+          const int base = b * p.Hin;
+          int t = 0;
+          for (int rr = 0; t < p.T; ++rr) {
+            const int yi = y * p.mul + rr * p.dil - p.pad;
+            const bool yok = yi >= 0 && yi < p.Hin;
+            for (int ss = 0; ss < p.kw && t < p.T; ++ss, ++t) {
+              const int xi = x * p.mul + ss * p.dil - p.pad;
+              tbl[t * 128 + r] = (yok && xi >= 0 && xi < p.Win) ? (base + yi) * p.Win + xi : -1;
+            }
+          }
+        } else {
+          tbl[r] = m;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) pnx::mbar_arrive(&tbl_full[tb]);
+      tb ^= 1;
+      if (tb == 0) tb_phase ^= 1;
     }
   } else {
     // ---------------------------------------------------------------- epilogue (4 warps = 128 TMEM lanes)
@@ -427,7 +458,7 @@ int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmPa
   if (gx < 1) gx = 1;
   if (gx > num_tiles) gx = num_tiles;
   dim3 grid(gx, n_blocks);
-  igemm_kernel<BN, PW><<<grid, 64 + PW * 32 + 128, Cfg<BN>::kSmem, stream>>>(wmap, amap, p);
+  igemm_kernel<BN, PW><<<grid, 64 + PW * 32 + 64 + 128, Cfg<BN>::kSmem, stream>>>(wmap, amap, p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
