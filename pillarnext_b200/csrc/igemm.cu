@@ -15,6 +15,8 @@
 //   warp 1      : single-thread tcgen05.mma issue, fp32 accumulators in TMEM (2 stages x BN columns)
 //   warps 6..9  : epilogue: tcgen05.ld -> bias/relu -> bf16|fp32 store, fused BatchNorm statistics
 //                 (per-channel sum / sum of squares, butterfly column reduce, fp64 accumulate)
+#include <stdlib.h>
+
 #include "pnx_common.cuh"
 
 namespace {
@@ -42,13 +44,19 @@ struct IgemmParams {
 constexpr uint32_t kABytes = 128 * 128;
 
 
-template <int BN>
+// MT = 128-row tiles per CTA iteration.  MT = 2 multiplies one weight stage against two A tiles (M = 256 per weight
+// byte): the wide layers are bound by L2->SM traffic (~11 TB/s chip), two thirds of which was the weight tile.
+template <int BN, int MT>
 struct Cfg {
   static constexpr uint32_t kBBytes = BN * 128;
-  static constexpr int kStagesRaw = (192 * 1024) / (int)(kABytes + kBBytes);
+  static constexpr uint32_t kAStage = MT * kABytes;
+  static constexpr int kStagesRaw = (192 * 1024) / (int)(kAStage + kBBytes);
   static constexpr int kStagesCap = 8;
   static constexpr int kStages = kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw;
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + 128 * 9 * 8 + 256 + 4 * 4096 + 2 * BN * 4 + BN * 4;
+  static constexpr int kAccSets = 512 / (MT * BN) >= 2 ? 2 : 1;  // TMEM accumulator sets (2 = epilogue overlaps the next tile)
+  static constexpr int kTblSlots = MT == 1 ? 2 : 3;  // ring of per-tile index tables [9 taps][128 rows] (smem budget: 3 for MT = 2)
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kAStage + kBBytes) + kTblSlots * 128 * 9 * 4 + 256 + 4 * 4096 + 2 * BN * 4 + BN * 4;
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
@@ -70,16 +78,21 @@ __device__ __forceinline__ float colsum32(float (&v)[32]) {
   return v[0];
 }
 
-template <int BN, int PW>
+template <int BN, int PW, int MT, int SPLIT>
 __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
                                                                   IgemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MT>;
+  constexpr uint32_t kAStage = C::kAStage;
+  constexpr int kAccSets = C::kAccSets;
+  constexpr int kTbl = 128 * 9;  // ints per tile index table
+  constexpr int kTblSlots = C::kTblSlots;
   constexpr int kProducerWarps = PW;
   constexpr int kProducerThreads = PW * 32;
   constexpr int kIndexWarps = 2;  // compute the gathered row indices of the next tile while the gather warps issue
   constexpr int kThreadsTotal = 64 + PW * 32 + kIndexWarps * 32 + 128;
   constexpr int kStages = C::kStages;
-  static_assert(PW <= kStages, "gather warps must not outnumber the stages (mbarrier parity)");
+  static_assert(PW <= MT * SPLIT * kStages, "gather warps must not outnumber the stage slots (mbarrier parity)");
+  static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "warps per 128-row gather");
   constexpr uint32_t kBBytes = C::kBBytes;
   constexpr int kColBlk = BN >= 32 ? 32 : 16;
   constexpr int kNumCB = BN / kColBlk;
@@ -87,15 +100,15 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)kStages * kABytes;
+  uint8_t* sB = smem + (size_t)kStages * kAStage;
   int* s_idx = reinterpret_cast<int*>(sB + (size_t)kStages * kBBytes);  // [T][128 rows] gathered row index, -1 = absent
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_idx + 128 * 9 * 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_idx + kTblSlots * kTbl);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
-  uint64_t* tbl_full = tempty + 2;    // index warps -> gather warps (two tile tables)
-  uint64_t* tbl_empty = tbl_full + 2;  // gather warps -> index warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbl_empty + 2);
+  uint64_t* tbl_full = tempty + 2;            // index warps -> gather warps (ring of tile tables)
+  uint64_t* tbl_empty = tbl_full + kTblSlots;  // gather warps -> index warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbl_empty + kTblSlots);
   float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [4 warps][4 KB] store staging slabs
   float* s_stat = s_tr + 4096;                                                        // [2][BN] per-channel sum / sumsq (smem atomics)
   float* s_bias = s_stat + 2 * BN;                                                // [BN] bias of this CTA's column block
@@ -107,12 +120,14 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
     pnx::tma_prefetch_desc(&wmap);
     pnx::tma_prefetch_desc(&amap);
     for (int s = 0; s < kStages; ++s) {
-      pnx::mbar_init(&full[s], 2);  // weight producer + the gather warp of this stage (both arrive with expect_tx)
+      pnx::mbar_init(&full[s], 1 + MT * SPLIT);  // weight producer + SPLIT gather warps per A tile (all arrive with expect_tx)
       pnx::mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       pnx::mbar_init(&tfull[a], 1);
       pnx::mbar_init(&tempty[a], 4);
+    }
+    for (int a = 0; a < kTblSlots; ++a) {
       pnx::mbar_init(&tbl_full[a], kIndexWarps);
       pnx::mbar_init(&tbl_empty[a], kProducerWarps);
     }
@@ -128,6 +143,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_tiles = (p.M + 127) >> 7;
+  const int num_pairs = (num_tiles + MT - 1) / MT;  // CTA iterations (groups of MT tiles)
   const int n0 = blockIdx.y * BN;
   const int kpt = p.Cin >> 6;
   const int num_k = p.T * kpt;
@@ -137,7 +153,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
     if (pnx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int pt = blockIdx.x; pt < num_pairs; pt += gridDim.x) {
         for (int kc = 0; kc < num_k; ++kc) {
           const int cc = kc / p.T, t = kc - cc * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
           pnx::mbar_wait(&empty[stage], phase ^ 1);
@@ -155,27 +171,29 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int pt = blockIdx.x; pt < num_pairs; pt += gridDim.x) {
         pnx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         pnx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int kc = 0; kc < num_k; ++kc) {
           pnx::mbar_wait(&full[stage], phase);
           pnx::tc_fence_after();
-          const uint32_t a_base = pnx::smem_u32(sA + (size_t)stage * kABytes);
+          const uint32_t a_base = pnx::smem_u32(sA + (size_t)stage * kAStage);
           const uint32_t b_base = pnx::smem_u32(sB + (size_t)stage * kBBytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = pnx::make_smem_desc_sw128(a_base + k * 32, 0, 1024);
             const uint64_t db = pnx::make_smem_desc_sw128(b_base + k * 32, 0, 1024);
-            pnx::umma_f16(d_tmem, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+              const uint64_t da = pnx::make_smem_desc_sw128(a_base + h * kABytes + k * 32, 0, 1024);
+              pnx::umma_f16(d_tmem + h * BN, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            }
           }
           pnx::umma_commit(&empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         pnx::umma_commit(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == kAccSets) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp < 2 + kProducerWarps) {
@@ -187,45 +205,58 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
     // index warps' table of the tile ([tap][row], one LDS.128 per request).
     const int pw = warp - 2;
     uint32_t g_base = 0;
-    int tb = 0;
-    uint32_t tb_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int* tbl = s_idx + tb * (128 * 9);
-      pnx::mbar_wait(&tbl_full[tb], tb_phase);
-      // stage g (global count over tiles) belongs to warp g % PW: a warp's consecutive stages are exactly PW <= kStages
-      // apart, so it can never be two phases ahead of an `empty` barrier (the parity wait stays unambiguous)
-      for (int kc = (int)((pw + kProducerWarps - g_base % kProducerWarps) % kProducerWarps); kc < num_k; kc += kProducerWarps) {
+    uint32_t tcount = 0;  // tiles consumed by this CTA so far (table ring position)
+    for (int pt = blockIdx.x; pt < num_pairs; pt += gridDim.x) {
+#pragma unroll
+      for (int h = 0; h < MT; ++h) {
+        const uint32_t c = tcount + h;
+        pnx::mbar_wait(&tbl_full[c % kTblSlots], (c / kTblSlots) & 1u);
+      }
+      // item i = (stage g, tile half h, part s of the 32 requests), global count over iterations, belongs to warp
+      // i % PW: a warp's consecutive items are PW / (MT*SPLIT) <= kStages stages apart, so it can never be two phases
+      // ahead of an `empty` barrier.  SPLIT > 1 shortens the serial request issue of one stage (32 x ~66 clk).
+      constexpr int kParts = MT * SPLIT, kLanes = 32 / SPLIT;
+      const uint32_t i_base = g_base * kParts;
+      for (int it = (int)((pw + kProducerWarps - i_base % kProducerWarps) % kProducerWarps); it < num_k * kParts; it += kProducerWarps) {
+        const int kc = it / kParts, hs = it - kc * kParts;
+        const int h = hs / SPLIT, part = hs - h * SPLIT;
         const int cc = kc / p.T, t = kc - cc * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
         const uint32_t g = g_base + (uint32_t)kc;
         const uint32_t stage = g % (uint32_t)kStages, phase = (g / (uint32_t)kStages) & 1u;
-        const int4 rows = *reinterpret_cast<const int4*>(tbl + t * 128 + 4 * lane);
+        const int* tbl = s_idx + ((tcount + h) % kTblSlots) * kTbl;
+        const int l4 = part * kLanes + lane;  // request index within the tile: rows 4*l4 .. 4*l4+3
+        int4 rows = make_int4(-1, -1, -1, -1);
+        if (lane < kLanes) rows = *reinterpret_cast<const int4*>(tbl + t * 128 + 4 * l4);
         pnx::mbar_wait(&empty[stage], phase ^ 1);
-        if (lane == 0) pnx::mbar_arrive_expect_tx(&full[stage], kABytes);
+        if (lane == 0) pnx::mbar_arrive_expect_tx(&full[stage], kABytes / SPLIT);
         __syncwarp();
-        pnx::tma_gather4(&amap, &full[stage], pnx::smem_u32(sA + (size_t)stage * kABytes) + lane * 512, cc * 64, rows.x,
-                         rows.y, rows.z, rows.w);
+        if (lane < kLanes)
+          pnx::tma_gather4(&amap, &full[stage], pnx::smem_u32(sA + (size_t)stage * kAStage) + h * kABytes + l4 * 512, cc * 64,
+                           rows.x, rows.y, rows.z, rows.w);
       }
       g_base += (uint32_t)num_k;
       __syncwarp();
-      if (lane == 0) pnx::mbar_arrive(&tbl_empty[tb]);
-      tb ^= 1;
-      if (tb == 0) tb_phase ^= 1;
+      if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < MT; ++h) pnx::mbar_arrive(&tbl_empty[(tcount + h) % kTblSlots]);
+      }
+      tcount += MT;
     }
   } else if (warp < 2 + kProducerWarps + kIndexWarps) {
     // ---------------------------------------------------------------- index warps: gathered row of (row r, tap t) for the
-    // NEXT tile while the gather warps work on the current one (two tables).  Thread i owns rows i and i + 64.
+    // NEXT tiles while the gather warps work on the current ones (ring of tile tables).  Thread i owns rows i, i + 64.
     const int itid = threadIdx.x - 64 - kProducerWarps * 32;
     const int hw = p.Hout * p.Wout;
     const float inv_hw = 1.0f / (float)hw, inv_w = 1.0f / (float)p.Wout;
-    int tb = 0;
-    uint32_t tb_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int* tbl = s_idx + tb * (128 * 9);
-      pnx::mbar_wait(&tbl_empty[tb], tb_phase ^ 1);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = itid + 64 * h;
-        const int m = tile * 128 + r;
+    uint32_t tcount = 0;
+    for (int pt = blockIdx.x; pt < num_pairs; pt += gridDim.x) {
+#pragma unroll 1
+      for (int h = 0; h < 2 * MT; ++h) {
+        const uint32_t c = tcount + (h >> 1);
+        int* tbl = s_idx + (c % kTblSlots) * kTbl;   // table of tile c: [tap][row]
+        if ((h & 1) == 0) pnx::mbar_wait(&tbl_empty[c % kTblSlots], ((c / kTblSlots) & 1u) ^ 1u);
+        const int r = itid + 64 * (h & 1);
+        const int m = (pt * MT + (h >> 1)) * 128 + r;
         if (m >= p.M) {
           for (int t = 0; t < p.T; ++t) tbl[t * 128 + r] = -1;
         } else if (p.nbr) {
@@ -256,11 +287,12 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
         } else {
           tbl[r] = m;
         }
+        if (h & 1) {
+          __syncwarp();
+          if (lane == 0) pnx::mbar_arrive(&tbl_full[c % kTblSlots]);
+        }
       }
-      __syncwarp();
-      if (lane == 0) pnx::mbar_arrive(&tbl_full[tb]);
-      tb ^= 1;
-      if (tb == 0) tb_phase ^= 1;
+      tcount += MT;
     }
   } else {
     // ---------------------------------------------------------------- epilogue (4 warps = 128 TMEM lanes)
@@ -274,9 +306,13 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
     uint8_t* slab = reinterpret_cast<uint8_t*>(s_tr) + quarter * 4096;
     const int hw = p.Hout * p.Wout;
     const bool staged = (BN % 64 == 0) && !p.shuffle;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int pt = blockIdx.x; pt < num_pairs; pt += gridDim.x) {
       while (!pnx::mbar_try_wait(&tfull[acc], acc_phase)) __nanosleep(64);  // leave the issue slots to the producers
       pnx::tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < MT; ++h) {
+      const int tile = pt * MT + h;
+      if (tile >= num_tiles) break;
       const int m = tile * 128 + quarter * 32 + lane;
       const bool active = m < p.M;
       long long out_row = m;
@@ -290,7 +326,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
 #pragma unroll 1
       for (int cb = 0; cb < kNumCB; ++cb) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb * kColBlk;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * MT + h) * BN + cb * kColBlk;
         if (kColBlk == 32) pnx::tmem_ld_32x32b_x32(taddr, r);
         else pnx::tmem_ld_32x32b_x16(taddr, r);
         pnx::tmem_ld_wait();
@@ -424,11 +460,11 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
           }
         }
       }
+      }  // h
       pnx::tc_fence_before();
       __syncwarp();
       if (lane == 0) pnx::mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == kAccSets) { acc = 0; acc_phase ^= 1; }
     }
     if (p.stats) {
       named_bar_sync(2, 128);  // the four epilogue warps
@@ -446,19 +482,22 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
   if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int BN, int PW>
-int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmParams& p, int n_blocks, int sm_count, cudaStream_t stream) {
+template <int BN, int PW, int MT, int SPLIT>
+int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmParams& p, int n_blocks, int sm_count,
+                 cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmem));
+    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, PW, MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg<BN, MT>::kSmem));
     attr_set = true;
   }
   const int num_tiles = (p.M + 127) / 128;
+  const int num_pairs = (num_tiles + MT - 1) / MT;
   int gx = sm_count / n_blocks;
   if (gx < 1) gx = 1;
-  if (gx > num_tiles) gx = num_tiles;
+  if (gx > num_pairs) gx = num_pairs;
   dim3 grid(gx, n_blocks);
-  igemm_kernel<BN, PW><<<grid, 64 + PW * 32 + 64 + 128, Cfg<BN>::kSmem, stream>>>(wmap, amap, p);
+  igemm_kernel<BN, PW, MT, SPLIT><<<grid, 64 + PW * 32 + 64 + 128, Cfg<BN, MT>::kSmem, stream>>>(wmap, amap, p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -508,12 +547,18 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   if (rc) return rc;
   const int n_blocks = Cout / block_n;
   switch (block_n) {
-    case 16: return launch_igemm<16, 8>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 32: return launch_igemm<32, 8>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 64: return launch_igemm<64, 8>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 128: return launch_igemm<128, 6>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 192: return launch_igemm<192, 4>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 256: return launch_igemm<256, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 16: return launch_igemm<16, 8, 1, 1>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 32: return launch_igemm<32, 8, 1, 1>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 64: return launch_igemm<64, 8, 1, 1>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 128: return launch_igemm<128, 8, 1, 2>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 192: return launch_igemm<192, 8, 1, 2>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 256: {
+      // MT = 2 (two tiles per weight stage) measured slower than the double-buffered single-tile form on every layer of
+      // the step (exposed epilogue, 3 stages); kept selectable for experiments only.
+      static const int mt_env = getenv("PNX_IGEMM_MT") ? atoi(getenv("PNX_IGEMM_MT")) : 0;
+      if (mt_env == 2) return launch_igemm<256, 6, 2, 1>(wmap, amap, p, n_blocks, sm_count, stream);
+      return launch_igemm<256, 8, 1, 2>(wmap, amap, p, n_blocks, sm_count, stream);
+    }
     default:
       pnx_set_error("pnx_igemm: unsupported block_n %d (16/32/64/128/192/256)", block_n);
       return PNX_ERR_ARG;

@@ -179,7 +179,7 @@ struct VoxGeom {
 // V1: cell index per point + occupancy bitmap + per-block pillar counts.  One thread per point; the block
 // stages its 256 points (6 KB) through shared memory with 128-bit coalesced loads.
 __global__ void __launch_bounds__(256) vox_mark_kernel(const float* __restrict__ points, int n, VoxGeom g,
-                                                       uint32_t* __restrict__ bitmap, int* __restrict__ blockcnt,
+                                                       uint32_t* __restrict__ bitmap,
                                                        int* __restrict__ cell_of_point) {
   __shared__ float4 stage[256 * 6 / 4];
   const long long first = (long long)blockIdx.x * 256;
@@ -213,11 +213,21 @@ __global__ void __launch_bounds__(256) vox_mark_kernel(const float* __restrict__
     const int xi = (int)cx, yi = (int)cy;  // :106 trunc
     const int word = (b * g.gx + xi) * g.vwords + (yi >> 5);
     const uint32_t bit = 1u << (yi & 31);
-    const uint32_t old = atomicOr(&bitmap[word], bit);
-    if (!(old & bit)) atomicAdd(&blockcnt[word >> 5], 1);  // first point of a new pillar
+    atomicOr(&bitmap[word], bit);  // fire-and-forget RED.OR: the per-block pillar counts come from vox_blockcnt_kernel
     cell = word * 32 + (yi & 31);
   }
   cell_of_point[first + threadIdx.x] = cell;
+}
+
+// pillars per 32-word block = popcount of the block (one warp per block, one coalesced 128-byte read)
+__global__ void __launch_bounds__(256) vox_blockcnt_kernel(const uint32_t* __restrict__ bitmap, int n_blocks,
+                                                           int* __restrict__ blockcnt) {
+  const int blk = (int)(((long long)blockIdx.x * 256 + threadIdx.x) >> 5);
+  if (blk >= n_blocks) return;
+  int c = __popc(bitmap[(size_t)blk * 32 + (threadIdx.x & 31)]);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) blockcnt[blk] = c;
 }
 
 // per-superblock (1024 blocks) totals of the block counts (only ~B*100 counters: atomics from the marking kernel
@@ -327,7 +337,9 @@ extern "C" int pnx_voxelize(const float* points, int n_points, int batch, float 
   int* supercnt = blockcnt + super_offset(n_blocks);
   if (bucket_cnt) PNX_CUDA(cudaMemsetAsync(bucket_cnt, 0, (size_t)(cap_pillars + 1) * 4 * 2, stream));  // counts + cursors
   if (n_points > 0) {
-    vox_mark_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(points, n_points, g, bitmap, blockcnt, cell_of_point);
+    vox_mark_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(points, n_points, g, bitmap, cell_of_point);
+    PNX_CHECK_LAUNCH();
+    vox_blockcnt_kernel<<<pnx_cdiv((long long)n_blocks * 32, 256), 256, 0, stream>>>(bitmap, n_blocks, blockcnt);
     PNX_CHECK_LAUNCH();
   }
   super_reduce_kernel<<<(n_blocks + 1023) / 1024, 256, 0, stream>>>(blockcnt, n_blocks, supercnt);
