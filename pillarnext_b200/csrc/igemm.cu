@@ -557,7 +557,7 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
       // the step (exposed epilogue, 3 stages); kept selectable for experiments only.
       static const int mt_env = getenv("PNX_IGEMM_MT") ? atoi(getenv("PNX_IGEMM_MT")) : 0;
       if (mt_env == 2) return launch_igemm<256, 6, 2, 1>(wmap, amap, p, n_blocks, sm_count, stream);
-      return launch_igemm<256, 8, 1, 2>(wmap, amap, p, n_blocks, sm_count, stream);
+      return launch_igemm<256, 8, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     }
     default:
       pnx_set_error("pnx_igemm: unsupported block_n %d (16/32/64/128/192/256)", block_n);
