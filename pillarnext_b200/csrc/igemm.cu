@@ -406,11 +406,22 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
               const int nrows = (int)min((long long)32, (long long)p.M - row0);  // rows past M hold bias-only garbage
               float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
               const int cpc = lane >> 2, cps = (lane & 3) * 4;
-              for (int row = 0; row < nrows; ++row) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(slab + row * 128 + ((cpc ^ (row & 7)) << 4) + cps);
-                const float2 f = __bfloat1622float2(h2);
-                s0 += f.x; s1 += f.y;
-                q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+              // full 32-row blocks (all but the ragged tile edge): unrolled so the 32 LDS are in flight together
+              if (nrows == 32) {
+#pragma unroll
+                for (int row = 0; row < 32; ++row) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(slab + row * 128 + ((cpc ^ (row & 7)) << 4) + cps);
+                  const float2 f = __bfloat1622float2(h2);
+                  s0 += f.x; s1 += f.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                }
+              } else {
+                for (int row = 0; row < nrows; ++row) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(slab + row * 128 + ((cpc ^ (row & 7)) << 4) + cps);
+                  const float2 f = __bfloat1622float2(h2);
+                  s0 += f.x; s1 += f.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                }
               }
               const int c0 = (cb - 1) * 32 + 2 * lane;  // columns of this pair of blocks owned by this lane
               atomicAdd(&st_sum[c0], s0); atomicAdd(&st_sum[c0 + 1], s1);

@@ -9,7 +9,7 @@
 // whose start address is shifted by s rows (s*128 bytes, matrix base offset = s): 3 window loads feed 9 taps,
 // cutting the activation traffic 2.9x, and there are no gather warps at all (one thread issues every load).
 //   warp 0: TMA producer (A windows, 4-D map [C, W, H, B]; weight tiles, 2-D map)   warp 1: MMA issuer
-//   warps 2..5: epilogue (bias, ReLU, bf16 coalesced store through a swizzled slab, BatchNorm statistics)
+//   warps 2..9: epilogue (bias, ReLU, bf16 coalesced store through a swizzled slab, BatchNorm statistics)
 #include "pnx_common.cuh"
 
 namespace {
@@ -30,14 +30,20 @@ constexpr uint32_t kWinRows = 130;
 constexpr uint32_t kWinBytes = kWinRows * 128;     // bytes written by one window load
 constexpr uint32_t kWinSlot = 17 * 1024;           // 1024-aligned slot
 
-template <int BN>
+// WS = weights stationary: for Cin = 64 the nine [BN x 64] weight tiles (9*BN*128 B) are loaded once per CTA and stay in
+// shared memory; a stage is then only the activation window.  Without it every 128-pixel tile re-fetches all nine
+// tiles (216 KB at BN = 192 against 50 KB of windows) and the kernel is bound by L2->SM traffic at ~50 % MMA issue.
+template <int BN, bool WS>
 struct WCfgWin {
   static constexpr uint32_t kBTap = BN * 128;
-  static constexpr uint32_t kStageBytes = kWinSlot + 3 * kBTap;
-  static constexpr int kStagesRaw = (184 * 1024) / (int)kStageBytes;
+  static constexpr uint32_t kWBytes = WS ? 9 * kBTap : 0;
+  static constexpr uint32_t kStageBytes = WS ? kWinSlot : kWinSlot + 3 * kBTap;
+  static constexpr int kFixed = 1024 + 256 + 8 * 4096 + 3 * BN * 4;
+  static constexpr int kStagesRaw = WS ? (227 * 1024 - kFixed - (int)kWBytes) / (int)kStageBytes : (180 * 1024) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + 4 * 4096 + 3 * BN * 4;
+  static constexpr size_t kSmem = kFixed + kWBytes + (size_t)kStages * kStageBytes;
   static_assert(kStages >= 2, "stages");
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
@@ -52,20 +58,22 @@ __device__ __forceinline__ uint64_t desc_sw128_off(uint32_t addr, uint32_t sbo, 
   return pnx::make_smem_desc_sw128(addr, 0, sbo) | ((uint64_t)(base_off & 7u) << 49);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant__ CUtensorMap amap,
+template <int BN, bool WS>
+__global__ void __launch_bounds__(320, 1) igemm_win_kernel(const __grid_constant__ CUtensorMap amap,
                                                            const __grid_constant__ CUtensorMap wmap, WinParams p) {
-  using C = WCfgWin<BN>;
+  using C = WCfgWin<BN, WS>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_w + C::kWBytes;  // stage ring (the stationary weight tiles, if any, come first)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * C::kStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
   uint8_t* s_slab = reinterpret_cast<uint8_t*>(full) + 256;
-  float* s_stat = reinterpret_cast<float*>(s_slab + 4 * 4096);
+  float* s_stat = reinterpret_cast<float*>(s_slab + 8 * 4096);
   float* s_bias = s_stat + 2 * BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,8 +86,9 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       pnx::mbar_init(&tfull[a], 1);
-      pnx::mbar_init(&tempty[a], 4);
+      pnx::mbar_init(&tempty[a], 8);
     }
+    pnx::mbar_init(wfull, 1);
     pnx::fence_barrier_init();
   }
   if (warp == 1) pnx::tmem_alloc<512>(tmem_slot);
@@ -99,6 +108,10 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
     if (pnx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      if (WS) {
+        pnx::mbar_arrive_expect_tx(wfull, C::kWBytes);
+        for (int t = 0; t < 9; ++t) pnx::tma_load_2d(&wmap, wfull, smem_w + t * C::kBTap, 0, t * p.Cout_total + n0);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int xc = tile % p.XC, by = tile / p.XC;
         const int y = by % p.H, b = by / p.H;
@@ -106,11 +119,11 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
           for (int r = 0; r < 3; ++r) {
             pnx::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + (size_t)stage * C::kStageBytes;
-            pnx::mbar_arrive_expect_tx(&full[stage], kWinBytes + 3 * C::kBTap);
+            pnx::mbar_arrive_expect_tx(&full[stage], WS ? kWinBytes : kWinBytes + 3 * C::kBTap);
             tma_load_4d(&amap, &full[stage], st, cc * 64, xc * 128 - 1, y + r - 1, b);
 #pragma unroll
             for (int s = 0; s < 3; ++s)
-              pnx::tma_load_2d(&wmap, &full[stage], st + kWinSlot + s * C::kBTap, cc * 64, (r * 3 + s) * p.Cout_total + n0);
+              if (!WS) pnx::tma_load_2d(&wmap, &full[stage], st + kWinSlot + s * C::kBTap, cc * 64, (r * 3 + s) * p.Cout_total + n0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -121,6 +134,7 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
       constexpr uint32_t idesc = pnx::make_idesc_bf16(128, BN, 0, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      if (WS) pnx::mbar_wait(wfull, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         pnx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         pnx::tc_fence_after();
@@ -130,7 +144,8 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
           pnx::mbar_wait(&full[stage], phase);
           pnx::tc_fence_after();
           const uint32_t a_base = pnx::smem_u32(smem + (size_t)stage * C::kStageBytes);
-          const uint32_t b_base = a_base + kWinSlot;
+          // WS: kcc == 1, so stage kc is kernel row r = kc and its taps are weight tiles 3r .. 3r+2
+          const uint32_t b_base = WS ? pnx::smem_u32(smem_w) + kc * 3 * C::kBTap : a_base + kWinSlot;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
 #pragma unroll
@@ -151,11 +166,13 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int quarter = warp & 3;
-    int acc = 0;
+    // 8 warps: two per TMEM lane quarter; the 64-column block pairs of a tile alternate between the two groups (and
+    // the alternation flips every tile, so odd pair counts balance over the two accumulator sets)
+    const int quarter = warp & 3, group = (warp - 2) >> 2;
+    int acc = 0, ti = 0;
     uint32_t acc_phase = 0;
-    uint8_t* slab = s_slab + quarter * 4096;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    uint8_t* slab = s_slab + (warp - 2) * 4096;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       const int xc = tile % p.XC, by = tile / p.XC;
       const long long row0 = (long long)by * p.W + xc * 128;          // pixel index of tile row 0 (by = b*H + y)
       const int valid = min(128, p.W - xc * 128);                       // pixels of this image row in the tile
@@ -164,6 +181,7 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
       const int nrows = max(0, min(32, valid - quarter * 32));
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
+        if ((((cb >> 1) + ti) & 1) != group) continue;
         uint32_t r[32];
         pnx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb * 32, r);
         pnx::tmem_ld_wait();
@@ -202,12 +220,23 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
           if (p.stats) {
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
             const int cpc = lane >> 2, cps = (lane & 3) * 4;
-            for (int row = 0; row < nrows; ++row) {
-              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(slab + row * 128 + ((cpc ^ (row & 7)) << 4) + cps);
-              const float2 f = __bfloat1622float2(h2);
-              s0 += f.x; s1 += f.y;
-              q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
-            }
+              // full 32-row blocks (all but the ragged tile edge): unrolled so the 32 LDS are in flight together
+              if (nrows == 32) {
+#pragma unroll
+                for (int row = 0; row < 32; ++row) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(slab + row * 128 + ((cpc ^ (row & 7)) << 4) + cps);
+                  const float2 f = __bfloat1622float2(h2);
+                  s0 += f.x; s1 += f.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                }
+              } else {
+                for (int row = 0; row < nrows; ++row) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(slab + row * 128 + ((cpc ^ (row & 7)) << 4) + cps);
+                  const float2 f = __bfloat1622float2(h2);
+                  s0 += f.x; s1 += f.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                }
+              }
             const int c0 = (cb - 1) * 32 + 2 * lane;
             atomicAdd(&s_stat[c0], s0); atomicAdd(&s_stat[c0 + 1], s1);
             atomicAdd(&s_stat[BN + c0], q0); atomicAdd(&s_stat[BN + c0 + 1], q1);
@@ -222,8 +251,8 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.stats) {
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < BN; c += 128) {
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      for (int c = threadIdx.x - 64; c < BN; c += 256) {
         atomicAdd(&p.stats[n0 + c], (double)s_stat[c]);
         atomicAdd(&p.stats[p.stats_C + n0 + c], (double)s_stat[BN + c]);
       }
@@ -235,19 +264,19 @@ __global__ void __launch_bounds__(192, 1) igemm_win_kernel(const __grid_constant
   if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int BN>
+template <int BN, bool WS>
 int launch_win(const CUtensorMap& amap, const CUtensorMap& wmap, const WinParams& p, int n_blocks, int sm_count,
                cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNX_CUDA(cudaFuncSetAttribute(igemm_win_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WCfgWin<BN>::kSmem));
+    PNX_CUDA(cudaFuncSetAttribute(igemm_win_kernel<BN, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WCfgWin<BN, WS>::kSmem));
     attr_set = true;
   }
   const int num_tiles = p.B * p.H * p.XC;
   int gx = sm_count / n_blocks;
   if (gx < 1) gx = 1;
   if (gx > num_tiles) gx = num_tiles;
-  igemm_win_kernel<BN><<<dim3(gx, n_blocks), 192, WCfgWin<BN>::kSmem, stream>>>(amap, wmap, p);
+  igemm_win_kernel<BN, WS><<<dim3(gx, n_blocks), 320, WCfgWin<BN, WS>::kSmem, stream>>>(amap, wmap, p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -281,9 +310,13 @@ extern "C" int pnx_conv3x3_win(const void* A, long long lda, int B, int H, int W
   if (rc) return rc;
   const int n_blocks = Cout / block_n;
   switch (block_n) {
-    case 64: return launch_win<64>(amap, wmap, p, n_blocks, sm_count, stream);
-    case 128: return launch_win<128>(amap, wmap, p, n_blocks, sm_count, stream);
-    case 192: return launch_win<192>(amap, wmap, p, n_blocks, sm_count, stream);
+    case 64:
+      if (Cin == 64) return launch_win<64, true>(amap, wmap, p, n_blocks, sm_count, stream);
+      return launch_win<64, false>(amap, wmap, p, n_blocks, sm_count, stream);
+    case 128:
+      if (Cin == 64) return launch_win<128, true>(amap, wmap, p, n_blocks, sm_count, stream);
+      return launch_win<128, false>(amap, wmap, p, n_blocks, sm_count, stream);
+    case 192: return launch_win<192, false>(amap, wmap, p, n_blocks, sm_count, stream);
     default:
       pnx_set_error("pnx_conv3x3_win: unsupported block_n %d (64/128/192)", block_n);
       return PNX_ERR_ARG;

@@ -350,7 +350,12 @@ def win_eligible(dense, n_cols, k_cols, out_fp32=False, shuffle=False):
 def conv3x3_win(A, B, H, W, w_packed, cin, cout, out, *, bias=None, stats=None, relu=False, block_n=None, base_off=None):
     """Dense 3x3 'same' conv with TMA-folded im2col (pnx_conv3x3_win). A bf16 rows [B*H*W, >=cin]; out bf16."""
     assert A.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and tuple(w_packed.shape) == (9, cout, cin)
-    bn = block_n or (192 if cout % 192 == 0 else (128 if cout % 128 == 0 else 64))
+    if block_n:
+        bn = block_n
+    elif cin == 64 and cout % 128 == 0:
+        bn = 128            # weights-stationary variant: the nine [128 x 64] tiles stay in shared memory
+    else:
+        bn = 192 if cout % 192 == 0 else (128 if cout % 128 == 0 else 64)
     M = B * H * W
     _count(1)
     with _Timed("igemm_win", 2.0 * M * 9 * cin * cout, 2.0 * M * (cin * 3 + cout), "M%d_K%d_N%d_bn%d" % (M, cin, cout, bn)):

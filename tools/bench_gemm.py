@@ -55,5 +55,6 @@ def run_win(name, K, N, bn, m=M):
     ms = timeit(lambda: ops.conv3x3_win(A, B, H, W, Wp, K, N, out, stats=st, block_n=bn))
     print("%-42s %7.3f ms %7.1f TF/s" % (name, ms, 2.0 * m * 9 * K * N / ms / 1e9), flush=True)
 run_win("WIN convA 64->384 bn192 +stats", 64, 384, 192)
+run_win("WIN convA 64->384 auto(ws128) +stats", 64, 384, None)
 run_win("WIN convA-dgrad 384->64 bn64", 384, 64, 64)
 run_win("WIN 256->64 bn64", 256, 64, 64)
