@@ -46,16 +46,16 @@ constexpr uint32_t kABytes = 128 * 128;
 
 // MT = 128-row tiles per CTA iteration.  MT = 2 multiplies one weight stage against two A tiles (M = 256 per weight
 // byte): the wide layers are bound by L2->SM traffic (~11 TB/s chip), two thirds of which was the weight tile.
-template <int BN, int MT>
+template <int BN, int MT, int EW>
 struct Cfg {
   static constexpr uint32_t kBBytes = BN * 128;
   static constexpr uint32_t kAStage = MT * kABytes;
-  static constexpr int kStagesRaw = (192 * 1024) / (int)(kAStage + kBBytes);
+  static constexpr int kStagesRaw = (192 * 1024 - (EW - 4) * 4096) / (int)(kAStage + kBBytes);
   static constexpr int kStagesCap = 8;
   static constexpr int kStages = kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw;
   static constexpr int kAccSets = 512 / (MT * BN) >= 2 ? 2 : 1;  // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   static constexpr int kTblSlots = MT == 1 ? 2 : 3;  // ring of per-tile index tables [9 taps][128 rows] (smem budget: 3 for MT = 2)
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kAStage + kBBytes) + kTblSlots * 128 * 9 * 4 + 256 + 4 * 4096 + 2 * BN * 4 + BN * 4;
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kAStage + kBBytes) + kTblSlots * 128 * 9 * 4 + 256 + EW * 4096 + 2 * BN * 4 + BN * 4;
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
@@ -78,10 +78,12 @@ __device__ __forceinline__ float colsum32(float (&v)[32]) {
   return v[0];
 }
 
-template <int BN, int PW, int MT, int SPLIT>
-__global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
+// EW = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating 64-column block pairs) for the
+// short-K wide-N layers whose epilogue is longer than their MMA loop
+template <int BN, int PW, int MT, int SPLIT, int EW>
+__global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
                                                                   IgemmParams p) {
-  using C = Cfg<BN, MT>;
+  using C = Cfg<BN, MT, EW>;
   constexpr uint32_t kAStage = C::kAStage;
   constexpr int kAccSets = C::kAccSets;
   constexpr int kTbl = 128 * 9;  // ints per tile index table
@@ -89,7 +91,8 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
   constexpr int kProducerWarps = PW;
   constexpr int kProducerThreads = PW * 32;
   constexpr int kIndexWarps = 2;  // compute the gathered row indices of the next tile while the gather warps issue
-  constexpr int kThreadsTotal = 64 + PW * 32 + kIndexWarps * 32 + 128;
+  constexpr int kThreadsTotal = 64 + PW * 32 + kIndexWarps * 32 + EW * 32;
+  constexpr int kEpiWarp0 = 2 + PW + kIndexWarps;
   constexpr int kStages = C::kStages;
   static_assert(PW <= MT * SPLIT * kStages, "gather warps must not outnumber the stage slots (mbarrier parity)");
   static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "warps per 128-row gather");
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
   uint64_t* tbl_empty = tbl_full + kTblSlots;  // gather warps -> index warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbl_empty + kTblSlots);
   float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [4 warps][4 KB] store staging slabs
-  float* s_stat = s_tr + 4096;                                                        // [2][BN] per-channel sum / sumsq (smem atomics)
+  float* s_stat = s_tr + EW * 1024;                                                      // [2][BN] per-channel sum / sumsq (smem atomics)
   float* s_bias = s_stat + 2 * BN;                                                // [BN] bias of this CTA's column block
 
   const int warp = threadIdx.x >> 5;
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
     }
     for (int a = 0; a < 2; ++a) {
       pnx::mbar_init(&tfull[a], 1);
-      pnx::mbar_init(&tempty[a], 4);
+      pnx::mbar_init(&tempty[a], EW);
     }
     for (int a = 0; a < kTblSlots; ++a) {
       pnx::mbar_init(&tbl_full[a], kIndexWarps);
@@ -298,12 +301,12 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
     // ---------------------------------------------------------------- epilogue (4 warps = 128 TMEM lanes)
     // The column-block loop is deliberately NOT unrolled: the unrolled form was >170 KB of SASS and the epilogue
     // ran out of the instruction cache (stall_no_inst); per-channel statistics live in shared memory.
-    const int quarter = warp & 3;
-    int acc = 0;
+    const int quarter = warp & 3, group = (warp - kEpiWarp0) >> 2;
+    int acc = 0, ti = 0;
     uint32_t acc_phase = 0;
     float* st_sum = s_stat;
     float* st_sq = s_stat + BN;
-    uint8_t* slab = reinterpret_cast<uint8_t*>(s_tr) + quarter * 4096;
+    uint8_t* slab = reinterpret_cast<uint8_t*>(s_tr) + (warp - kEpiWarp0) * 4096;
     const int hw = p.Hout * p.Wout;
     const bool staged = (BN % 64 == 0) && !p.shuffle;
     for (int pt = blockIdx.x; pt < num_pairs; pt += gridDim.x) {
@@ -325,6 +328,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
       }
 #pragma unroll 1
       for (int cb = 0; cb < kNumCB; ++cb) {
+        if (EW == 8 && (((cb >> 1) + ti) & 1) != group) continue;  // the other warp of this lane quarter takes it
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * MT + h) * BN + cb * kColBlk;
         if (kColBlk == 32) pnx::tmem_ld_32x32b_x32(taddr, r);
@@ -476,10 +480,11 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
       __syncwarp();
       if (lane == 0) pnx::mbar_arrive(&tempty[acc]);
       if (++acc == kAccSets) { acc = 0; acc_phase ^= 1; }
+      ++ti;
     }
     if (p.stats) {
-      named_bar_sync(2, 128);  // the four epilogue warps
-      for (int c = threadIdx.x - (kThreadsTotal - 128); c < BN; c += 128) {
+      named_bar_sync(2, EW * 32);  // the epilogue warps
+      for (int c = threadIdx.x - (kThreadsTotal - EW * 32); c < BN; c += EW * 32) {
         const int ch = (n0 + c) % p.stats_mod;
         atomicAdd(&p.stats[ch], (double)st_sum[c]);
         atomicAdd(&p.stats[p.stats_C + ch], (double)st_sq[c]);
@@ -493,13 +498,13 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + 128, 1) igemm_kernel(const
   if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int BN, int PW, int MT, int SPLIT>
+template <int BN, int PW, int MT, int SPLIT, int EW>
 int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmParams& p, int n_blocks, int sm_count,
                  cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, PW, MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)Cfg<BN, MT>::kSmem));
+    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, PW, MT, SPLIT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg<BN, MT, EW>::kSmem));
     attr_set = true;
   }
   const int num_tiles = (p.M + 127) / 128;
@@ -508,7 +513,7 @@ int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmPa
   if (gx < 1) gx = 1;
   if (gx > num_pairs) gx = num_pairs;
   dim3 grid(gx, n_blocks);
-  igemm_kernel<BN, PW, MT, SPLIT><<<grid, 64 + PW * 32 + 64 + 128, Cfg<BN, MT>::kSmem, stream>>>(wmap, amap, p);
+  igemm_kernel<BN, PW, MT, SPLIT, EW><<<grid, 64 + PW * 32 + 64 + EW * 32, Cfg<BN, MT, EW>::kSmem, stream>>>(wmap, amap, p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -558,17 +563,21 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   if (rc) return rc;
   const int n_blocks = Cout / block_n;
   switch (block_n) {
-    case 16: return launch_igemm<16, 8, 1, 1>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 32: return launch_igemm<32, 8, 1, 1>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 64: return launch_igemm<64, 8, 1, 1>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 128: return launch_igemm<128, 8, 1, 2>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 192: return launch_igemm<192, 8, 1, 2>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 16: return launch_igemm<16, 8, 1, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 32: return launch_igemm<32, 8, 1, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 64: return launch_igemm<64, 8, 1, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 128:
+      if (taps * (Cin / 64) <= 4) return launch_igemm<128, 4, 1, 2, 8>(wmap, amap, p, n_blocks, sm_count, stream);
+      return launch_igemm<128, 8, 1, 2, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 192:  // short K (1x1 convs of the head): the epilogue of 192 columns outlasts the MMA loop -> 8 epilogue warps
+      if (taps * (Cin / 64) <= 9) return launch_igemm<192, 4, 1, 2, 8>(wmap, amap, p, n_blocks, sm_count, stream);
+      return launch_igemm<192, 8, 1, 2, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     case 256: {
       // MT = 2 (two tiles per weight stage) measured slower than the double-buffered single-tile form on every layer of
       // the step (exposed epilogue, 3 stages); kept selectable for experiments only.
       static const int mt_env = getenv("PNX_IGEMM_MT") ? atoi(getenv("PNX_IGEMM_MT")) : 0;
-      if (mt_env == 2) return launch_igemm<256, 6, 2, 1>(wmap, amap, p, n_blocks, sm_count, stream);
-      return launch_igemm<256, 8, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+      if (mt_env == 2) return launch_igemm<256, 6, 2, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+      return launch_igemm<256, 8, 1, 4, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     }
     default:
       pnx_set_error("pnx_igemm: unsupported block_n %d (16/32/64/128/192/256)", block_n);
