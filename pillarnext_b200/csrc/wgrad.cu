@@ -309,7 +309,8 @@ int launch_wgrad(const CUtensorMap& xmap, const CUtensorMap& ymap, WgradParams p
   p.taps_per_group = (p.T + groups - 1) / groups;
   groups = (p.T + p.taps_per_group - 1) / p.taps_per_group;
   const int ctas_xy = x_blocks * p.y_chunks * groups;
-  int splits = (2 * sm_count + ctas_xy - 1) / ctas_xy;
+  // two full waves of CTAs (one CTA per SM): round DOWN -- 2*148 + a few CTAs would run a third, nearly empty wave
+  int splits = (2 * sm_count) / ctas_xy;
   const int max_splits = (p.M + 8 * kKS - 1) / (8 * kKS);  // at least 8 K-chunks per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
