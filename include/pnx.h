@@ -52,7 +52,7 @@ int pnx_scan_blocks(const int* counts, int n_blocks, int* out, int* total_out, c
  *   bitmap        pnx_voxelize_bitmap_words() u32 (padded to whole 32-word blocks), occupancy in (b, xi, yi)
  *                 order (zeroed here)
  *   inblk         [words] u16 OUT: in-block exclusive popcount prefix (also used by the rulebook)
- *   blockcnt      [pnx_blockcnt_size(words/32)] int32: pillars per 32-word block (+ per 1024 blocks), zeroed here
+ *   blockcnt      [pnx_blockcnt_size(words/32)] int32: pillars per 32-word block (+ per 1024 blocks), written here
  *   blockpref     [words/32 + 1] exclusive scan of blockcnt; rank of a cell = blockpref[block] +
  *                 popcount of the block's earlier words + popcount of the lower bits of its word
  *   cell_of_point [n_points] scratch
@@ -61,7 +61,7 @@ int pnx_scan_blocks(const int* counts, int n_blocks, int* out, int* total_out, c
  *   bucket_cnt    [2*(cap_pillars+1)] OUT (optional, may be NULL): points per pillar + zeroed cursors for
  *                 pnx_bucketize
  *   counts        [2] device ints: counts[0] = #pillars P (counts[1] = #kept points, set by pnx_bucketize)
- * cap_pillars must be >= min(n_points, batch*gx*gy).  4 kernels: mark | scan | coords | rank. */
+ * cap_pillars must be >= min(n_points, batch*gx*gy).  Kernels: mark (RED.OR) | block popcounts | scan | coords | rank. */
 size_t pnx_voxelize_bitmap_words(int batch, int gx, int gy);
 int pnx_voxelize(const float* points, int n_points, int batch, float min_x, float min_y, float vs_x,
                  float vs_y, int gx, int gy, uint32_t* bitmap, uint16_t* inblk, int* blockcnt, int* blockpref,

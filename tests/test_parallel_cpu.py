@@ -22,7 +22,7 @@ def _worker(rank, world, port, q):
     loss.backward()
     FlatGradAllReduce(net.parameters())()
     grads = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
-    q.put((rank, mine, grads))
+    q.put((rank, mine, grads.tolist()))   # plain floats: a tensor would travel as a shared fd that dies with the worker
     dist.barrier()
     dist.destroy_process_group()
 
@@ -38,7 +38,7 @@ def test_flat_grad_allreduce_matches_single_process():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    res.sort(key=lambda x: x[0])
+    res = sorted((r, m, torch.tensor(g)) for r, m, g in res)
     assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3, 5]
     assert torch.allclose(res[0][2], res[1][2])
     torch.manual_seed(0)
