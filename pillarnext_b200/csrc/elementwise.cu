@@ -2,8 +2,6 @@
 //   BatchNorm apply (+residual)(+ReLU)                     forward of sparse_conv.py:33-39,55-63, conv.py:29-34,44-51
 //   BatchNorm backward: reduce (sum g, sum g*xhat) + apply  (autograd of the same lines in the reference)
 // 128-bit loads/stores, one thread = 8 consecutive channels of one row.
-#include <stdlib.h>
-
 #include "pnx_common.cuh"
 
 namespace {
@@ -281,12 +279,8 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long 
 }
 
 // grid for the (rows x channel-group) layout: enough blocks for ~16 waves, each thread streaming >= 4 rows
-inline int tune(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 inline int row_blocks(long long M, int C) {
-  static const int waves = tune("PNX_EW_WAVES", 16);
+  constexpr int waves = 16;
   const int rpb = 256 / (C / 8);
   long long b = (M + (long long)rpb * 4 - 1) / ((long long)rpb * 4);
   const long long cap = 148LL * waves;
@@ -312,7 +306,7 @@ extern "C" int pnx_bn_apply(const void* x, long long ldx, long long M, int C, co
   PNX_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldr % 8 == 0, "C/ld % 8");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(C <= 2048, "C <= 2048");
-  static const int u = tune("PNX_EW_U_APPLY", 1);  // measured: 6.2 TB/s at U=1, slower unrolled
+  constexpr int u = 1;  // rows in flight per thread; measured (tools/bench_ew.py): 6.2 TB/s at U=1, slower unrolled
   PNX_DISPATCH_U(u, bn_apply_kernel<U><<<row_blocks(M, C), 256, 0, stream>>>(
                         (const __nv_bfloat16*)x, ldx, M, C, scale, shift, (const __nv_bfloat16*)res, ldr, relu,
                         (__nv_bfloat16*)y, ldy));
@@ -330,10 +324,10 @@ extern "C" int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, 
   PNX_CHECK_ARG(C / 8 <= kT, "C <= 2048");
   const int rows_per_block = kT / (C / 8);
   long long nb = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
-  static const int rw = tune("PNX_EW_RWAVES", 4);
+  constexpr int rw = 4;
   if (nb > 148 * rw) nb = 148 * rw;
   if (nb < 1) nb = 1;
-  static const int u = tune("PNX_EW_U_REDUCE", 4);
+  constexpr int u = 4;  // measured best (tools/bench_ew.py)
   PNX_DISPATCH_U(u, bn_bwd_reduce_kernel<kT, U><<<(int)nb, kT, kT * 16 * sizeof(float), stream>>>(
                         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M,
                         C, mean, invstd, relu, fscale, fshift, red));
@@ -350,7 +344,7 @@ extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, l
   PNX_CHECK_ARG(C % 8 == 0, "C % 8");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(C <= 2048, "C <= 2048");
-  static const int u = tune("PNX_EW_U_BWD", 2);
+  constexpr int u = 2;  // measured best: 4 rows in flight costs occupancy (161 registers)
   PNX_DISPATCH_U(u, bn_bwd_apply_kernel<U><<<row_blocks(M, C), 256, 0, stream>>>(
                         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M,
                         C, mean, invstd, gamma, red, (float)(1.0 / count), relu, fscale, fshift, (__nv_bfloat16*)dx,

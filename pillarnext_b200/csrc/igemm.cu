@@ -9,14 +9,13 @@
 //     (zero padding = absent neighbour), ConvTranspose2d k2 s2 (centerhead.py:26-27) = one GEMM with
 //     N = 4*Cout and a pixel-shuffle store.
 // Pipeline per CTA (persistent over 128-row tiles, one CTA per SM):
-//   warp 0      : TMA (cp.async.bulk.tensor) producer of the weight tile  B[BN x 64]  (SWIZZLE_128B)
-//   warps 2..5  : gather producers: cp.async 16 B row chunks of A into the same 128B-swizzled K-major
-//                 layout (zero-fill for absent neighbours), generic->async proxy fence, mbarrier arrive
-//   warp 1      : single-thread tcgen05.mma issue, fp32 accumulators in TMEM (2 stages x BN columns)
-//   warps 6..9  : epilogue: tcgen05.ld -> bias/relu -> bf16|fp32 store, fused BatchNorm statistics
-//                 (per-channel sum / sum of squares, butterfly column reduce, fp64 accumulate)
-#include <stdlib.h>
-
+//   warp 0        : TMA (cp.async.bulk.tensor) producer of the weight tile  B[BN x 64]  (SWIZZLE_128B)
+//   warp 1        : single-thread tcgen05.mma issue, fp32 accumulators in TMEM (2 sets x BN columns)
+//   PW warps      : gather producers: TMA tile::gather4 requests (4 arbitrary rows x 128 B each) into the same
+//                   128B-swizzled K-major layout; row index -1 (absent neighbour) = out of bounds = zero fill
+//   2 warps       : index warps: row indices of the next tile ([tap][row] table in shared memory)
+//   4 or 8 warps  : epilogue: tcgen05.ld -> bias/relu/addend -> bf16|fp32 coalesced store through a swizzled slab,
+//                   fused BatchNorm statistics (per-channel sum / sum of squares, fp64 accumulate)
 #include "pnx_common.cuh"
 
 namespace {
@@ -38,14 +37,11 @@ struct IgemmParams {
   long long ld_add;
 };
 
-// threads = TMA warp + MMA warp + PW gather-producer warps + 4 epilogue warps.  PW = 8 for the A-bound shapes
-// (small N: two producer warps per scheduler hide the gather latency), PW = 4 for the epilogue-heavy ones (wide N,
-// short K: the epilogue warps need the issue slots and the registers).
+// threads = TMA warp + MMA warp + PW gather warps + 2 index warps + EW epilogue warps.
 constexpr uint32_t kABytes = 128 * 128;
 
-
-// MT = 128-row tiles per CTA iteration.  MT = 2 multiplies one weight stage against two A tiles (M = 256 per weight
-// byte): the wide layers are bound by L2->SM traffic (~11 TB/s chip), two thirds of which was the weight tile.
+// MT = 128-row tiles per CTA iteration (1 everywhere: MT = 2, one weight stage against two A tiles, was measured
+// slower -- the single accumulator set exposes the epilogue and only 3 stages fit).
 template <int BN, int MT, int EW>
 struct Cfg {
   static constexpr uint32_t kBBytes = BN * 128;
@@ -89,7 +85,6 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
   constexpr int kTbl = 128 * 9;  // ints per tile index table
   constexpr int kTblSlots = C::kTblSlots;
   constexpr int kProducerWarps = PW;
-  constexpr int kProducerThreads = PW * 32;
   constexpr int kIndexWarps = 2;  // compute the gathered row indices of the next tile while the gather warps issue
   constexpr int kThreadsTotal = 64 + PW * 32 + kIndexWarps * 32 + EW * 32;
   constexpr int kEpiWarp0 = 2 + PW + kIndexWarps;
@@ -572,13 +567,10 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
     case 192:  // short K (1x1 convs of the head): the epilogue of 192 columns outlasts the MMA loop -> 8 epilogue warps
       if (taps * (Cin / 64) <= 9) return launch_igemm<192, 4, 1, 2, 8>(wmap, amap, p, n_blocks, sm_count, stream);
       return launch_igemm<192, 8, 1, 2, 4>(wmap, amap, p, n_blocks, sm_count, stream);
-    case 256: {
-      // MT = 2 (two tiles per weight stage) measured slower than the double-buffered single-tile form on every layer of
-      // the step (exposed epilogue, 3 stages); kept selectable for experiments only.
-      static const int mt_env = getenv("PNX_IGEMM_MT") ? atoi(getenv("PNX_IGEMM_MT")) : 0;
-      if (mt_env == 2) return launch_igemm<256, 6, 2, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
+    case 256:
+      // (MT = 2, two tiles per weight stage, measured slower on every layer of the step: exposed epilogue of the single
+      // accumulator set and only 3 stages -- not instantiated)
       return launch_igemm<256, 8, 1, 4, 4>(wmap, amap, p, n_blocks, sm_count, stream);
-    }
     default:
       pnx_set_error("pnx_igemm: unsupported block_n %d (16/32/64/128/192/256)", block_n);
       return PNX_ERR_ARG;

@@ -10,7 +10,9 @@
 // One CTA owns a 128-channel block of X, a <=256-channel chunk of Y and a GROUP of taps: the X tile of a
 // 64-row chunk is staged ONCE and multiplied against the gathered Y tile of every tap of the group (taps are
 // extra N columns of the accumulator, up to 512 TMEM columns), so the direct operand is not re-read per tap.
-// Grid = (x blocks * y chunks, tap groups, K splits).
+// Grid = (x blocks * y chunks, tap groups, K splits), sized to two full waves of one CTA per SM.
+// Warp roles: 0 = X tiles by 2-D TMA, 1 = MMA issue, 2..9 = Y rows by TMA tile::gather4 (requests dealt round-robin
+// over the warps), 10..13 = index warps (gathered row of every (tap, row) one or more chunks ahead), 14..17 = epilogue.
 // This is the backward of: spconv SparseConv2d/SubMConv2d (reference sparse_conv.py:25-29,50-51),
 // nn.Conv2d/F.conv2d (aspp.py:19-32, conv.py:9-10, centerhead.py:35-46,108-114), nn.ConvTranspose2d
 // (centerhead.py:26-27) -- autograd derives these in the reference (trainer.py:94-108 loss.backward()).
@@ -43,7 +45,6 @@ constexpr int kIndexThreads = kIndexWarps * 32;
 constexpr int kThreads = 64 + kProducerThreads + kIndexThreads + 128;
 constexpr int kKS = 64;               // rows (K) per stage
 constexpr uint32_t kBlk = kKS * 128;  // bytes of one [64 rows x 64 ch] block
-constexpr int kMaxTG = 8;
 
 // NYC = Y channels per CTA (64..256), TG = max taps per group (NYC * TG <= 512 TMEM columns)
 template <int NYC, int TG, int XB>
@@ -56,18 +57,6 @@ struct WCfg {
   static_assert(NYC * TG * XB <= 512, "TMEM budget");
   static_assert(kStages >= 2, "need at least two stages");
 };
-
-// exact n / d for 0 <= n via one float multiply + correction (n < 2^24), integer divide otherwise
-__device__ __forceinline__ void divmod_fast(int n, int d, float inv_d, int& q, int& r) {
-  if (n < (1 << 24)) {
-    q = __float2int_rz(__int2float_rn(n) * inv_d);
-    r = n - q * d;
-    if (r < 0) { --q; r += d; } else if (r >= d) { ++q; r -= d; }
-  } else {
-    q = n / d;
-    r = n - q * d;
-  }
-}
 
 // XB = number of 128-channel X blocks per CTA (2 halves the re-gathering of Y when the TMEM budget allows)
 template <int NYC, int TG, int XB>

@@ -1,4 +1,5 @@
-"""GB/s of the BatchNorm row kernels at the shapes of the training step (tuning aid)."""
+"""GB/s of the BatchNorm row kernels at the shapes of the training step (tuning aid; the rows-in-flight factors it
+was used to choose are now compile-time constants in csrc/elementwise.cu)."""
 import sys, torch
 sys.path.insert(0, '.')
 from pillarnext_b200 import ops
