@@ -41,7 +41,9 @@ def test_descriptor_base_offset_convention():
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,bn", [(2, 9, 336, 64, 384, 192), (1, 5, 130, 384, 64, 64), (2, 7, 128, 128, 128, 128),
-                                               (1, 12, 40, 256, 64, 64), (1, 3, 257, 64, 192, 192)])
+                                               (1, 12, 40, 256, 64, 64), (1, 3, 257, 64, 192, 192),
+                                               # Cin = 64 with block_n <= 128: weights-stationary variant
+                                               (2, 9, 336, 64, 384, 128), (1, 3, 257, 64, 128, 64)])
 def test_conv3x3_win(B, H, W, Cin, Cout, bn):
     err, stats_ok = run(B, H, W, Cin, Cout, bn, None)
     assert err < 1.2e-2, err
