@@ -176,3 +176,38 @@ def test_detector_matches_oracle(grid, npts, kind):
     model.zero_grad()
     out = model(exg)
     assert isinstance(out, tuple) and out[0].dim() == 0 and len(out[1]) == len(cfg["tasks"])
+
+
+def test_full_size_frame_independence_and_point_order():
+    """BASELINE.json configs[1] size (1344^2 pillar grid, 30k points per frame), size-independent properties:
+    (1) in eval mode a frame's head outputs do not depend on which other frames share the batch -- bit-exact, because
+        sites/pixels are ordered frame-major and every kernel computes a row from that row's neighbours only;
+    (2) shuffling the points of a frame leaves the pillar set and its order unchanged (bit-exact) and the pillar
+        features equal up to the fp32 summation order of the mean."""
+    cfg = synth.NUSC
+    model, _ = build(cfg, seed=5)
+    model.eval()
+    frames = [synth.make_frame(100 + s, 30000, cfg, "lidar", sweeps=10) for s in range(2)]
+
+    def run(fr):
+        ex = {"points": synth.collate_points(fr).cuda(), "token": ["t%d" % i for i in range(len(fr))]}
+        with torch.no_grad():
+            return model._forward(ex)
+
+    both, solo = run(frames), run(frames[:1])
+    assert len(both) == len(solo) == len(cfg["tasks"])
+    for pb, ps in zip(both, solo):
+        assert list(pb.keys()) == list(ps.keys())
+        for k in pb:
+            a, b = pb[k][0:1], ps[k]
+            assert a.shape == b.shape and torch.isfinite(a).all(), k
+            assert torch.equal(a, b), (k, (a - b).abs().max().item())
+
+    pts = synth.collate_points(frames[:1])
+    perm = torch.randperm(pts.shape[0], generator=torch.Generator().manual_seed(9))
+    model.reader.batch_size = 1
+    with torch.no_grad():
+        f0, c0, _ = model.reader(pts.cuda())
+        f1, c1, _ = model.reader(pts[perm].cuda())
+    assert torch.equal(c0, c1)
+    assert (f0 - f1).abs().max().item() < 1e-4
