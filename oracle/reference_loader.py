@@ -52,6 +52,7 @@ def load_reference():
         ns.ASPPNeck = importlib.import_module("det3d.models.necks.aspp").ASPPNeck
         ch = importlib.import_module("det3d.models.heads.centerhead")
         ns.CenterHead, ns.SepHead = ch.CenterHead, ch.SepHead
+        ns.box_torch_ops = ch.box_torch_ops      # module object whose rotate_nms_pcdet the predict pin replaces
         cl = importlib.import_module("det3d.models.loss.centerloss")
         ns.FastFocalLoss, ns.RegLoss, ns.IouRegLoss = cl.FastFocalLoss, cl.RegLoss, cl.IouRegLoss
         ns.bbox3d_overlaps_diou = cl.bbox3d_overlaps_diou
