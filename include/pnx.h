@@ -227,6 +227,35 @@ int pnx_center_loss_task(const float* out, float* dout, const float* hm_gt, cons
 int pnx_center_loss_finalize(const double* acc, int n_tasks, const float* weights_dev, const float* code_w_dev,
                              const int* with_iou_dev, float* res, float* total, cudaStream_t stream);
 
+/* ---------------------------------------------------------------- F1 detection decode + rotated NMS (one task)
+ * Replaces CenterHead.predict / post_processing (centerhead.py:231-384), rotate_nms_pcdet (box_torch_ops.py:5-31) and
+ * the native nms_gpu (iou3d_nms_kernel.cu:280-324, iou3d_nms.cpp:113-159).  `out` is the task's channels-last head
+ * output [B*H*W, ld] fp32; offs = HOST ints {reg, height, dim, rot, vel, hm, iou} column offsets (iou < 0: no iou head);
+ * range6 (post_center_limit_range), rect (rectifier per class), nms_thr (per class) are HOST float arrays.
+ *   pnx_det_keys  : keys [B*H*W] int64 (INT64_MAX = filtered out; else (frame*C + class) << 32 | ~score bits, so an
+ *                   ascending sort is segment-major and score-descending), seg_count [B*C] (zeroed here).
+ *   pnx_det_nms   : order = argsort(keys) (the caller sorts), seg_start = exclusive prefix of seg_count; for each
+ *                   segment the first min(count, pre_max) candidates: suppression mask (scratch [B*C, pre_max,
+ *                   ceil(pre_max/64)] u64) and greedy sweep on the device -> keep [B*C, post_max] (positions in the
+ *                   segment's sorted run), keep_count [B*C].  pre_max <= 2048; mask row stride = ceil(pre_max/64).
+ *   pnx_det_gather: det_box [B*C, post_max, 9] (x,y,z,dx,dy,dz,vx,vy,yaw), det_score, det_label (+label_offset, i64).
+ * The two *_host entry points evaluate the same inline decode / IoU code on HOST memory (CPU test hooks, no GPU). */
+int pnx_det_keys(const float* out, long long ld, int B, int H, int W, int C, const int* offs, float osf, float vs_x,
+                 float vs_y, float pc_x, float pc_y, float score_thr, const float* range6, const float* rect,
+                 long long* keys, int* seg_count, cudaStream_t stream);
+int pnx_det_nms(const float* out, long long ld, int B, int H, int W, int C, const int* offs, float osf, float vs_x,
+                float vs_y, float pc_x, float pc_y, float score_thr, const float* range6, const float* rect,
+                const float* nms_thr, const long long* order, const int* seg_start, const int* seg_count, int pre_max,
+                int post_max, unsigned long long* mask, int* keep, int* keep_count, cudaStream_t stream);
+int pnx_det_gather(const float* out, long long ld, int B, int H, int W, int C, const int* offs, float osf, float vs_x,
+                   float vs_y, float pc_x, float pc_y, float score_thr, const float* range6, const float* rect,
+                   const long long* order, const int* seg_start, const int* keep, const int* keep_count, int post_max,
+                   int label_offset, float* det_box, float* det_score, long long* det_label, cudaStream_t stream);
+float pnx_det_iou_bev_host(const float* box7_a, const float* box7_b);
+int pnx_det_decode_host(const float* out, long long ld, int B, int H, int W, int C, const int* offs, float osf,
+                        float vs_x, float vs_y, float pc_x, float pc_y, float score_thr, const float* range6,
+                        const float* rect, long long m, float* box9, float* score, int* label);
+
 #ifdef __cplusplus
 }
 #endif

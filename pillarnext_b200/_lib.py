@@ -55,8 +55,15 @@ _SIGS = {
     "pnx_add_rows": [P, L, P, L, L, I, P],
     "pnx_add_relu": [P, L, P, L, L, I, P, L, P],
     "pnx_relu_bwd": [P, L, P, L, L, I, P, L, I, P],
+    # F1: decode + rotated NMS.  common prefix = out, ld, B, H, W, C, offs, osf, vs_x, vs_y, pc_x, pc_y, score_thr, range6, rect
+    "pnx_det_keys": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P],
+    "pnx_det_nms": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P, P, I, I, P, P, P, P],
+    "pnx_det_gather": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P, P, I, I, P, P, P, P],
+    "pnx_det_iou_bev_host": [P, P],
+    "pnx_det_decode_host": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, L, P, P, P],
 }
-_RESTYPE = {"pnx_last_error": ctypes.c_char_p, "pnx_voxelize_bitmap_words": ctypes.c_size_t}
+_RESTYPE = {"pnx_last_error": ctypes.c_char_p, "pnx_voxelize_bitmap_words": ctypes.c_size_t,
+            "pnx_det_iou_bev_host": ctypes.c_float}
 
 
 def exported_symbols():

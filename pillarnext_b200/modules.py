@@ -479,7 +479,52 @@ class CenterHead(nn.Module):
 
     @torch.no_grad()
     def predict(self, example, preds_dicts, test_cfg):
-        raise NotImplementedError("decode + rotated NMS is SURVEY.md section 8f row F1 (not built yet)")
+        """centerhead.py:231-330: decode, score/range filter, per-class rotated NMS, merge tasks.  test_cfg is the
+        reference's `post_processing` config (attribute or mapping access): post_center_limit_range, score_threshold,
+        out_size_factor (per task), voxel_size, pc_range, nms.{nms_iou_threshold (per task, per class),
+        nms_pre_max_size, nms_post_max_size}.  Returns a list (one per frame) of dicts box3d_lidar [K, 9]
+        (x, y, z, dx, dy, dz, vx, vy, yaw), scores [K], label_preds [K] (int64), token.  One host sync (the kept counts)."""
+        def get(cfg, name):
+            return cfg[name] if isinstance(cfg, dict) or hasattr(cfg, "keys") else getattr(cfg, name)
+
+        raws = [getattr(pd.get("hm"), "_pnx_raw", None) for pd in preds_dicts]
+        if any(r is None for r in raws):
+            raise NotImplementedError("predict needs the fused head output (PillarNeXt-B heads: reg/height/dim/rot/vel/hm)")
+        nms = get(test_cfg, "nms")
+        pre_max, post_max = int(get(nms, "nms_pre_max_size")), int(get(nms, "nms_post_max_size"))
+        thr_all = get(nms, "nms_iou_threshold")
+        pcr = [float(v) for v in get(test_cfg, "post_center_limit_range")]
+        if len(pcr) != 6:
+            raise NotImplementedError("predict needs a 6-value post_center_limit_range")
+        vs, pr = get(test_cfg, "voxel_size"), get(test_cfg, "pc_range")
+        osf_all = get(test_cfg, "out_size_factor")
+        tokens = example.get("token") if isinstance(example, dict) else None
+        results, flag = [], 0
+        for t, r in enumerate(raws):
+            off = r["off"]
+            offs = [off["reg"], off["height"], off["dim"], off["rot"], off["vel"], off["hm"], off.get("iou", -1)]
+            rect = [float(v) for v in self.rectifier[t]]
+            results.append(ops.det_postprocess(r["out"], r["B"], r["H"], r["W"], r["C"], offs, float(osf_all[t]), vs, pr,
+                                               float(get(test_cfg, "score_threshold")), pcr, rect,
+                                               [float(v) for v in thr_all[t]], pre_max, post_max, label_offset=flag))
+            flag += self.num_classes[t]
+        counts = torch.cat([res[3] for res in results]).cpu().tolist()       # the one host synchronisation
+        B = raws[0]["B"]
+        out, base = [], 0
+        bases = []
+        for r in raws:
+            bases.append(base)
+            base += r["B"] * r["C"]
+        for b in range(B):
+            boxes, scores, labels = [], [], []
+            for t, (r, res) in enumerate(zip(raws, results)):
+                for c in range(r["C"]):
+                    s = b * r["C"] + c
+                    k = counts[bases[t] + s]
+                    boxes.append(res[0][s, :k]); scores.append(res[1][s, :k]); labels.append(res[2][s, :k])
+            out.append(dict(box3d_lidar=torch.cat(boxes), scores=torch.cat(scores), label_preds=torch.cat(labels),
+                            token=tokens[b] if tokens is not None and len(tokens) > b else None))
+        return out
 
 
 # =========================================================================================== detector

@@ -426,3 +426,50 @@ def relu_bwd(dy, y, M, C, g, accumulate=False):
     check(lib().pnx_relu_bwd(ptr(dy), dy.stride(0), ptr(y), y.stride(0), M, C, ptr(g), g.stride(0),
                              1 if accumulate else 0, stream()))
     return g
+
+
+# --------------------------------------------------------------------------------- F1: decode + rotated NMS
+def _host_floats(vals, n):
+    import ctypes
+    a = (ctypes.c_float * n)(*([float(v) for v in vals] + [0.0] * (n - len(vals))))
+    return a, ctypes.addressof(a)
+
+
+def det_postprocess(out, B, H, W, C, offs, osf, voxel_size, pc_range, score_thr, post_center_range, rectifier, nms_thr,
+                    pre_max, post_max, label_offset=0):
+    """One task of CenterHead.predict (centerhead.py:231-384): `out` = channels-last head output [B*H*W, ld] fp32,
+    offs = column offsets (reg, height, dim, rot, vel, hm, iou or -1).  Returns det_box [B*C, post_max, 9], det_score
+    [B*C, post_max], det_label [B*C, post_max] (int64, + label_offset) and keep_count [B*C] -- all on the device, no
+    host synchronisation.  Segment s = frame * C + class.  The candidate ordering is one device sort (torch.sort of
+    the 64-bit keys the decode kernel builds); decode, IoU mask, greedy sweep and gather are libpnx kernels."""
+    import ctypes
+    assert out.dtype == torch.float32 and out.is_cuda and out.dim() == 2 and out.shape[0] == B * H * W
+    dev = out.device
+    M, nseg = B * H * W, B * C
+    offs_a = (ctypes.c_int * 7)(*[int(o) for o in offs])
+    r6, r6p = _host_floats(post_center_range, 6)
+    rc, rcp = _host_floats(rectifier, 8)
+    nt, ntp = _host_floats(nms_thr, 8)
+    common = (ptr(out), out.stride(0), B, H, W, C, ctypes.addressof(offs_a), float(osf), float(voxel_size[0]),
+              float(voxel_size[1]), float(pc_range[0]), float(pc_range[1]), float(score_thr), r6p, rcp)
+    keys = torch.empty(M, dtype=torch.int64, device=dev)
+    seg_count = torch.empty(nseg, dtype=torch.int32, device=dev)
+    L = lib()
+    _count(1)
+    check(L.pnx_det_keys(*common, ptr(keys), ptr(seg_count), stream()))
+    order = torch.sort(keys)[1]
+    seg_start = (torch.cumsum(seg_count, 0, dtype=torch.int32) - seg_count).contiguous()
+    col_blocks = (pre_max + 63) // 64
+    mask = torch.empty(nseg * pre_max * col_blocks, dtype=torch.int64, device=dev)
+    keep = torch.empty(nseg * post_max, dtype=torch.int32, device=dev)
+    keep_count = torch.empty(nseg, dtype=torch.int32, device=dev)
+    _count(2)
+    check(L.pnx_det_nms(*common, ntp, ptr(order), ptr(seg_start), ptr(seg_count), int(pre_max), int(post_max), ptr(mask),
+                        ptr(keep), ptr(keep_count), stream()))
+    det_box = torch.empty(nseg, post_max, 9, dtype=torch.float32, device=dev)
+    det_score = torch.empty(nseg, post_max, dtype=torch.float32, device=dev)
+    det_label = torch.empty(nseg, post_max, dtype=torch.int64, device=dev)
+    _count(1)
+    check(L.pnx_det_gather(*common, ptr(order), ptr(seg_start), ptr(keep), ptr(keep_count), int(post_max), int(label_offset),
+                           ptr(det_box), ptr(det_score), ptr(det_label), stream()))
+    return det_box, det_score, det_label, keep_count

@@ -14,6 +14,7 @@ import pytest
 import torch
 
 from oracle import build_ref_iou, predict_oracle as P, reference_loader
+from oracle.predict_fixtures import fake_preds as _fake_preds, test_cfg as _test_cfg, to_rows
 
 
 def rand_boxes(n, seed, spread=6.0):
@@ -62,27 +63,6 @@ def test_nms_invariants():
     assert P.nms_rotated(boxes, 1.1) == list(range(60))
 
 
-def _test_cfg():
-    return dict(post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], score_threshold=0.1,
-                out_size_factor=[4, 4], voxel_size=[0.075, 0.075], pc_range=[-50.4, -50.4],
-                nms=dict(nms_iou_threshold=[[0.2], [0.2, 0.2]], nms_pre_max_size=1000, nms_post_max_size=83))
-
-
-def _fake_preds(B, H, W, classes, seed):
-    """Head outputs with a sparse set of confident, separated peaks (so the NMS input is small and not degenerate)."""
-    g = torch.Generator().manual_seed(seed)
-    pd = dict(reg=torch.rand(B, 2, H, W, generator=g), height=torch.randn(B, 1, H, W, generator=g),
-              dim=torch.randn(B, 3, H, W, generator=g) * 0.3 + 0.5, rot=torch.randn(B, 2, H, W, generator=g),
-              vel=torch.randn(B, 2, H, W, generator=g), hm=torch.full((B, classes, H, W), -6.0))
-    n = 60
-    for b in range(B):
-        ys = torch.randint(0, H, (n,), generator=g)
-        xs = torch.randint(0, W, (n,), generator=g)
-        cs = torch.randint(0, classes, (n,), generator=g)
-        pd["hm"][b, cs, ys, xs] = torch.randn(n, generator=g) * 1.5 + 0.5
-    return pd
-
-
 def test_predict_matches_reference_predict():
     if not reference_loader.available():
         pytest.skip("reference tree not present (build container only)")
@@ -108,3 +88,41 @@ def test_predict_matches_reference_predict():
         assert torch.equal(g["label_preds"], w["label_preds"])
         assert torch.allclose(g["scores"], w["scores"], atol=1e-6)
         assert torch.allclose(g["box3d_lidar"], w["box3d_lidar"], atol=1e-5)
+
+
+# ---------------------------------------------------------------------- product math compiled for the host (no GPU needed)
+
+
+def test_host_compiled_decode_and_iou_match_oracle():
+    import ctypes
+    from pillarnext_b200 import _lib
+    L = _lib.lib()
+    cfg = _test_cfg()
+    pd = _fake_preds(2, 12, 10, 2, 3)
+    pd["reg"][0, :, 0, 0] = torch.tensor([-900.0, 0.3])                  # pushed outside post_center_limit_range
+    out = to_rows(pd)
+    boxes, hm, iou = P.decode(pd, 4, cfg["voxel_size"], cfg["pc_range"])
+    scores, labels = hm.max(-1)
+    pcr = torch.tensor(cfg["post_center_limit_range"])
+    keep = (scores > cfg["score_threshold"]) & (boxes[..., :3] >= pcr[:3]).all(-1) & (boxes[..., :3] <= pcr[3:]).all(-1)
+    offs = (ctypes.c_int * 7)(0, 2, 3, 6, 8, 10, -1)
+    r6 = (ctypes.c_float * 6)(*cfg["post_center_limit_range"])
+    rect = (ctypes.c_float * 8)(*([0.0] * 8))
+    b9, sc, lb = (ctypes.c_float * 9)(), ctypes.c_float(), ctypes.c_int()
+    A = ctypes.addressof
+    n_kept = 0
+    for m in range(out.shape[0]):
+        rc = L.pnx_det_decode_host(out.data_ptr(), out.stride(0), 2, 12, 10, 2, A(offs), 4.0, 0.075, 0.075, -50.4, -50.4,
+                                   cfg["score_threshold"], A(r6), A(rect), m, A(b9), A(sc), A(lb))
+        b, i = divmod(m, 120)
+        assert rc == int(keep[b, i]), (m, rc)
+        if rc:
+            n_kept += 1
+            assert lb.value == int(labels[b, i])
+            assert abs(sc.value - float(scores[b, i])) < 1e-6
+            assert torch.allclose(torch.tensor(list(b9)), boxes[b, i], atol=1e-5, rtol=1e-6)
+    assert 20 < n_kept < out.shape[0] and not keep[0, 0]
+    bx = rand_boxes(40, 8).numpy()
+    for i in range(0, 40, 2):
+        got = L.pnx_det_iou_bev_host(bx[i].ctypes.data, bx[i + 1].ctypes.data)
+        assert abs(got - float(P.iou_bev(bx[i], bx[i + 1]))) < 2e-6
