@@ -126,3 +126,18 @@ def test_host_compiled_decode_and_iou_match_oracle():
     for i in range(0, 40, 2):
         got = L.pnx_det_iou_bev_host(bx[i].ctypes.data, bx[i + 1].ctypes.data)
         assert abs(got - float(P.iou_bev(bx[i], bx[i + 1]))) < 2e-6
+
+
+def test_oracle_predict_matches_golden_reference_outputs():
+    """Runs anywhere: tests/golden/ref_predict.npz holds the reference's own predict outputs (oracle/make_golden_predict.py)."""
+    import os
+    from oracle.make_golden_predict import SEEDS, SHAPE, TASKS
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_predict.npz")
+    gold = np.load(path)
+    preds = [_fake_preds(*SHAPE, len(t), SEEDS[i]) for i, t in enumerate(TASKS)]
+    got = P.predict(preds, [len(t) for t in TASKS], _test_cfg(), [[0.0], [0.0, 0.0]], tokens=["a", "b"])
+    for i, g in enumerate(got):
+        assert gold["box3d_lidar_%d" % i].shape[0] > 5
+        assert np.array_equal(g["label_preds"].numpy(), gold["label_preds_%d" % i])
+        assert np.allclose(g["scores"].numpy(), gold["scores_%d" % i], atol=1e-6)
+        assert np.allclose(g["box3d_lidar"].numpy(), gold["box3d_lidar_%d" % i], atol=1e-5)
