@@ -141,3 +141,45 @@ def test_oracle_predict_matches_golden_reference_outputs():
         assert np.array_equal(g["label_preds"].numpy(), gold["label_preds_%d" % i])
         assert np.allclose(g["scores"].numpy(), gold["scores_%d" % i], atol=1e-6)
         assert np.allclose(g["box3d_lidar"].numpy(), gold["box3d_lidar_%d" % i], atol=1e-5)
+
+
+def test_host_compiled_decode_with_rectifier_and_iou_head():
+    """Waymo-style task: `iou` head present and rectifier != 0 (waymo_det_pp18_aspp_iou_car_sp.yaml: [[0.68],[0.71,0.65]]);
+    nuScenes uses rectifier 0.5 without an iou head (score -> sqrt(score))."""
+    import ctypes
+    from pillarnext_b200 import _lib
+    L = _lib.lib()
+    cfg = _test_cfg()
+    A = ctypes.addressof
+    for with_iou, rect_v in ((True, [0.71, 0.65]), (False, [0.5, 0.5])):
+        pd = _fake_preds(1, 10, 12, 2, 17)
+        g = torch.Generator().manual_seed(3)
+        if with_iou:
+            pd["iou"] = torch.randn(1, 1, 10, 12, generator=g) * 0.8          # raw head output in [-inf, inf] -> clamp((x+1)/2)
+        B, H, W = 1, 10, 12
+        cols = dict(reg=0, height=2, dim=3, rot=6, vel=8)
+        cols.update(dict(iou=10, hm=11) if with_iou else dict(hm=10))
+        out = torch.zeros(B * H * W, 16)
+        for k, o in cols.items():
+            v = pd[k].permute(0, 2, 3, 1).reshape(B * H * W, -1)
+            out[:, o:o + v.shape[1]] = v
+        boxes, hm, iou = P.decode(pd, 4, cfg["voxel_size"], cfg["pc_range"])
+        want = P.post_processing(boxes, hm, iou, rect_v, cfg["score_threshold"], cfg["post_center_limit_range"],
+                                 [1.1, 1.1], 10000, 10000)[0]            # threshold > 1: NMS keeps everything
+        offs = (ctypes.c_int * 7)(0, 2, 3, 6, 8, cols["hm"], cols.get("iou", -1))
+        r6 = (ctypes.c_float * 6)(*cfg["post_center_limit_range"])
+        rect = (ctypes.c_float * 8)(*(rect_v + [0.0] * 6))
+        b9, sc, lb = (ctypes.c_float * 9)(), ctypes.c_float(), ctypes.c_int()
+        got = []
+        for m in range(out.shape[0]):
+            if L.pnx_det_decode_host(out.data_ptr(), out.stride(0), B, H, W, 2, A(offs), 4.0, 0.075, 0.075, -50.4, -50.4,
+                                     cfg["score_threshold"], A(r6), A(rect), m, A(b9), A(sc), A(lb)):
+                got.append((lb.value, sc.value, list(b9)))
+        assert len(got) == want["scores"].numel() > 10
+        # same multiset of detections (several candidates can tie at score 0 when the clamped iou is 0: order by box too)
+        key = lambda t: (t[0], -round(t[1], 5), round(t[2][0], 3), round(t[2][1], 3))
+        got.sort(key=key)
+        ref = sorted(zip(want["label_preds"].tolist(), want["scores"].tolist(), want["box3d_lidar"].tolist()), key=key)
+        assert [t[0] for t in got] == [t[0] for t in ref]
+        assert torch.allclose(torch.tensor([t[1] for t in got]), torch.tensor([t[1] for t in ref]), atol=2e-6)
+        assert torch.allclose(torch.tensor([t[2] for t in got]), torch.tensor([t[2] for t in ref]), atol=1e-5, rtol=1e-6)
