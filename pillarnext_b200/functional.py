@@ -199,8 +199,15 @@ def conv(x, w, bias, spec, layout, want_stats=False, out_fp32=False, relu=False,
 
 
 # ------------------------------------------------------------------------------------------- batch norm
+def wants_sync(bn):
+    """SyncBatchNorm semantics requested for this BN holder: either through enable_sync_batchnorm() (`pnx_sync`) or
+    because tools/train.py:55-56 replaced it with torch.nn.SyncBatchNorm (`convert_sync_batchnorm` copies parameters
+    and buffers into a new module whose forward this package never calls -- only its type carries the request)."""
+    return bool(getattr(bn, "pnx_sync", False)) or isinstance(bn, torch.nn.SyncBatchNorm)
+
+
 def _sync_enabled(bn):
-    return getattr(bn, "pnx_sync", False) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return wants_sync(bn) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
 class BNActFn(torch.autograd.Function):

@@ -339,7 +339,7 @@ class SepHead(nn.Module):
         bn.training = self.training
         ref = getattr(self, names[0])[1]
         bn.eps, bn.momentum = ref.eps, ref.momentum
-        bn.pnx_sync = getattr(ref, "pnx_sync", False)
+        bn.pnx_sync = Fn.wants_sync(ref)
         with torch.no_grad():
             bn.running_mean.copy_(torch.cat([getattr(self, n)[1].running_mean for n in names]))
             bn.running_var.copy_(torch.cat([getattr(self, n)[1].running_var for n in names]))

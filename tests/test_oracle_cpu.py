@@ -176,3 +176,20 @@ def test_oracle_and_synth_vs_live_reference(setup):
     f, c, _ = r(pts)
     f2, c2, _ = O.reader_forward(pts, sd, synth.NUSC["voxel_size"], synth.NUSC["pc_range"], train=True)
     assert torch.equal(c, c2) and (f - f2).abs().max().item() < 2e-5
+
+
+def test_convert_sync_batchnorm_is_honoured():
+    """tools/train.py:55-56 wraps the model with torch.nn.SyncBatchNorm.convert_sync_batchnorm: state-dict keys must
+    survive and every BN holder must then ask for synchronised statistics."""
+    from pillarnext_b200 import functional as Fn, modules, synth
+    cfg = synth.tiny_config(64, [["car"], ["truck", "construction_vehicle"]])
+    model = modules.build_pillarnext_b(cfg)
+    keys = list(model.state_dict().keys())
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+    assert bns and not any(Fn.wants_sync(m) for m in bns)
+    conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    assert list(conv.state_dict().keys()) == keys
+    bns = [m for m in conv.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+    assert bns and all(isinstance(m, torch.nn.SyncBatchNorm) and Fn.wants_sync(m) for m in bns)
+    model2 = modules.enable_sync_batchnorm(modules.build_pillarnext_b(cfg))
+    assert all(Fn.wants_sync(m) for m in model2.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
