@@ -251,6 +251,11 @@ int pnx_det_gather(const float* out, long long ld, int B, int H, int W, int C, c
                    float vs_y, float pc_x, float pc_y, float score_thr, const float* range6, const float* rect,
                    const long long* order, const int* seg_start, const int* keep, const int* keep_count, int post_max,
                    int label_offset, float* det_box, float* det_score, long long* det_label, cudaStream_t stream);
+/* F2 helper: out[i] = aligned 3-D IoU (BEV polygon overlap x height overlap / union volume) of a[i], b[i] ([n,7] fp32
+ * (x,y,z,dx,dy,dz,heading)); replaces boxes_aligned_iou3d_gpu (det3d/core/iou3d_nms/iou3d_nms_utils.py:45-87 +
+ * iou3d_nms_kernel.cu:251-262), the training target of the Waymo `iou` head (centerloss.py:76-87). */
+int pnx_aligned_iou3d(const float* a, const float* b, int n, float* out, cudaStream_t stream);
+float pnx_aligned_iou3d_host(const float* box7_a, const float* box7_b);
 float pnx_det_iou_bev_host(const float* box7_a, const float* box7_b);
 int pnx_det_decode_host(const float* out, long long ld, int B, int H, int W, int C, const int* offs, float osf,
                         float vs_x, float vs_y, float pc_x, float pc_y, float score_thr, const float* range6,

@@ -369,8 +369,23 @@ def iou_reg_loss(box_pred, mask, ind, box_gt):
     return (1.0 - iou).sum() / (m.sum() + 1e-4)
 
 
-def center_loss(example, preds, weight, code_weights, with_reg_iou, voxel_size, pc_range, out_size_factor):
-    """CenterHead.loss, centerhead.py:142-229 (nuScenes branch: no `iou` head).
+def iou_loss(iou_pred, mask, ind, box_pred, box_gt):
+    """IouLoss, centerloss.py:64-87: L1 between the `iou` head at the object centres and 2*IoU3d(decoded box, gt) - 1
+    (the target carries no gradient: the boxes are detached by the caller, centerhead.py:211-212)."""
+    from oracle import predict_oracle as PO
+    if mask.sum() == 0:
+        return iou_pred.sum() * 0
+    m = mask.bool()
+    pred = _gather_feat(iou_pred, ind)[m]          # [B, 1, H, W] -> [K, 1]
+    pb = _gather_feat(box_pred, ind)[m]            # [B, 7, H, W] -> [K, 7]
+    gt = box_gt[m]
+    tgt = torch.tensor([[float(PO.aligned_iou3d(a.numpy(), b.numpy()))] for a, b in zip(pb.detach(), gt)], dtype=pred.dtype)
+    tgt = 2 * tgt - 1
+    return F.l1_loss(pred, tgt.reshape(pred.shape), reduction="sum") / (mask.sum() + 1e-4)
+
+
+def center_loss(example, preds, weight, code_weights, with_reg_iou, voxel_size, pc_range, out_size_factor, with_iou=False):
+    """CenterHead.loss, centerhead.py:142-229 (`with_iou`: the Waymo `iou` head branch, :210-215).
     NOTE: like the reference (:146, :138-140) this REPLACES preds[t]['hm'] by its clamped sigmoid
     (out of place here so autograd stays valid)."""
     total = None
@@ -384,7 +399,7 @@ def center_loss(example, preds, weight, code_weights, with_reg_iou, voxel_size, 
         loss = hm_loss + weight * loc_loss                                   # :163
         ret = dict(hm_loss=hm_loss.detach(), loc_loss=loc_loss.detach(), loc_loss_elem=box_loss.detach(),
                    num_positive=example["mask"][t].float().sum())
-        if with_reg_iou:
+        if with_reg_iou or with_iou:
             bdim = torch.exp(torch.clamp(pd["dim"], min=-5, max=5)).permute(0, 2, 3, 1)      # :172-174
             brot = pd["rot"].permute(0, 2, 3, 1)
             brot = torch.atan2(brot[..., 0:1], brot[..., 1:2])               # :177-179
@@ -397,9 +412,14 @@ def center_loss(example, preds, weight, code_weights, with_reg_iou, voxel_size, 
             xs = xs * out_size_factor[t] * voxel_size[0] + pc_range[0]       # :201-204
             ys = ys * out_size_factor[t] * voxel_size[1] + pc_range[1]
             boxes = torch.cat([xs, ys, bhei, bdim, brot], dim=3).permute(0, 3, 1, 2)          # :206-209
-            irl = iou_reg_loss(boxes, example["mask"][t], example["ind"][t], example["gt_boxes"][t])
-            loss = loss + weight * irl                                       # :221
-            ret["iou_reg_loss"] = irl.detach()
+            if with_iou:
+                il = iou_loss(pd["iou"], example["mask"][t], example["ind"][t], boxes.detach(), example["gt_boxes"][t])
+                loss = loss + il                                             # :214
+                ret["iou_loss"] = il.detach()
+            if with_reg_iou:
+                irl = iou_reg_loss(boxes, example["mask"][t], example["ind"][t], example["gt_boxes"][t])
+                loss = loss + weight * irl                                   # :221
+                ret["iou_reg_loss"] = irl.detach()
         ret["loss"] = loss
         rets.append(ret)
         total = loss if total is None else total + loss

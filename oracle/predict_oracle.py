@@ -128,6 +128,18 @@ def iou_bev(box_a, box_b):
     return F(so / max(F(F(sa + sb) - so), EPS))
 
 
+def aligned_iou3d(box_a, box_b):
+    """iou3d_nms_utils.py:45-87 (boxes_aligned_iou3d_gpu) for one pair of (x, y, z, dx, dy, dz, heading) boxes."""
+    a = [F(v) for v in box_a]
+    b = [F(v) for v in box_b]
+    a_max, a_min = F(a[2] + F(a[5] / F(2))), F(a[2] - F(a[5] / F(2)))
+    b_max, b_min = F(b[2] + F(b[5] / F(2))), F(b[2] - F(b[5] / F(2)))
+    oh = max(F(min(a_max, b_max) - max(a_min, b_min)), F(0))
+    o3 = F(box_overlap(a, b) * oh)
+    va, vb = F(F(a[3] * a[4]) * a[5]), F(F(b[3] * b[4]) * b[5])
+    return F(o3 / max(F(F(va + vb) - o3), F(1e-6)))
+
+
 def nms_rotated(boxes, thresh):
     """Greedy NMS over boxes already sorted by descending score (iou3d_nms_kernel.cu:280-324 mask + iou3d_nms.cpp:138-154
     sweep): box i, if not removed, removes every later box j with iou_bev(i, j) > thresh.  Returns kept indices."""

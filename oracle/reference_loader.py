@@ -56,6 +56,7 @@ def load_reference():
         cl = importlib.import_module("det3d.models.loss.centerloss")
         ns.FastFocalLoss, ns.RegLoss, ns.IouRegLoss = cl.FastFocalLoss, cl.RegLoss, cl.IouRegLoss
         ns.bbox3d_overlaps_diou = cl.bbox3d_overlaps_diou
+        ns.centerloss = cl                       # module object (its boxes_aligned_iou3d_gpu is CUDA-only: the pin swaps it)
         ns.AssignLabel = importlib.import_module("det3d.datasets.pipelines.assign").AssignLabel
         ns.collate = importlib.import_module("det3d.datasets.loader.collate").collate
     finally:

@@ -60,10 +60,12 @@ _SIGS = {
     "pnx_det_nms": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P, P, I, I, P, P, P, P],
     "pnx_det_gather": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P, P, I, I, P, P, P, P],
     "pnx_det_iou_bev_host": [P, P],
+    "pnx_aligned_iou3d": [P, P, I, P, P],
+    "pnx_aligned_iou3d_host": [P, P],
     "pnx_det_decode_host": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, L, P, P, P],
 }
 _RESTYPE = {"pnx_last_error": ctypes.c_char_p, "pnx_voxelize_bitmap_words": ctypes.c_size_t,
-            "pnx_det_iou_bev_host": ctypes.c_float}
+            "pnx_det_iou_bev_host": ctypes.c_float, "pnx_aligned_iou3d_host": ctypes.c_float}
 
 
 def exported_symbols():

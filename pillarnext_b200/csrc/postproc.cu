@@ -169,6 +169,17 @@ __host__ __device__ inline float det_iou_bev(const float* a, const float* b) {
   return so / fmaxf(sa + sb - so, 1e-8f);
 }
 
+// aligned 3-D IoU of two (x, y, z, dx, dy, dz, heading) boxes: BEV overlap x height overlap over the union volume
+// (reference det3d/core/iou3d_nms/iou3d_nms_utils.py:45-87 boxes_aligned_iou3d_gpu; training target of the `iou` head)
+__host__ __device__ inline float det_aligned_iou3d(const float* a, const float* b) {
+  const float a_max = a[2] + a[5] / 2, a_min = a[2] - a[5] / 2;
+  const float b_max = b[2] + b[5] / 2, b_min = b[2] - b[5] / 2;
+  const float oh = fmaxf(fminf(a_max, b_max) - fmaxf(a_min, b_min), 0.f);
+  const float o3 = det_box_overlap(a, b) * oh;
+  const float va = a[3] * a[4] * a[5], vb = b[3] * b[4] * b[5];
+  return o3 / fmaxf(va + vb - o3, 1e-6f);
+}
+
 // (x, y, z, dx, dy, dz, vx, vy, yaw) -> (x, y, z, dx, dy, dz, yaw): boxes_for_nms = box[:, [0,1,2,3,4,5,-1]]
 __host__ __device__ inline void box9_to_box7(const float* b9, float* b7) {
   for (int k = 0; k < 6; ++k) b7[k] = b9[k];
@@ -267,6 +278,16 @@ __global__ void __launch_bounds__(128) det_gather_kernel(DetParams p, const long
   }
 }
 
+__global__ void __launch_bounds__(128) aligned_iou3d_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
+                                                            float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float ba[7], bb[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { ba[k] = a[(size_t)i * 7 + k]; bb[k] = b[(size_t)i * 7 + k]; }
+  out[i] = det_aligned_iou3d(ba, bb);
+}
+
 int fill_params(DetParams* p, const float* out, long long ld, int B, int H, int W, int C, const int* offs, float osf,
                 float vs_x, float vs_y, float pc_x, float pc_y, float score_thr, const float* range6, const float* rect,
                 const float* nms_thr) {
@@ -337,6 +358,18 @@ extern "C" int pnx_det_gather(const float* out, long long ld, int B, int H, int 
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
+
+// F2 helper: out[i] = aligned 3-D IoU of boxes a[i], b[i] ([n, 7] fp32 each), the target of the Waymo `iou` head loss.
+extern "C" int pnx_aligned_iou3d(const float* a, const float* b, int n, float* out, cudaStream_t stream) {
+  PNX_CHECK_ARG(n >= 0, "n");
+  if (n == 0) return PNX_OK;
+  PNX_CHECK_ARG(a && b && out, "null pointer");
+  aligned_iou3d_kernel<<<pnx_cdiv(n, 128), 128, 0, stream>>>(a, b, n, out);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
+}
+
+extern "C" float pnx_aligned_iou3d_host(const float* box7_a, const float* box7_b) { return det_aligned_iou3d(box7_a, box7_b); }
 
 // Host-side evaluation of the same inline math (no GPU): lets the CPU test-suite pin the decode and the rotated IoU
 // against the oracle.  `out` is HOST memory here.

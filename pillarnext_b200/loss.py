@@ -108,3 +108,27 @@ def center_loss(example, preds_dicts, class_names, weight, code_weights, with_re
         rets.append(ret)
         total = loss if total is None else total + loss
     return total, rets
+
+
+def iou_head_loss(out, off, B, H, W, ind, mask, gt_boxes, out_size_factor, voxel_size, pc_range):
+    """IouLoss of the Waymo `iou` head (centerloss.py:64-87, called from centerhead.py:210-215) on the fused head's
+    channels-last output `out` [B*H*W, npad] (column offsets `off`).  Sync-free: the object rows are gathered with
+    torch (differentiable w.r.t. `out`), the detached target 2*IoU3d(decoded box, gt)-1 comes from the libpnx
+    aligned rotated-IoU kernel, absent objects are masked instead of compacted (0 / 1e-4 = 0 when a frame set has none)."""
+    from . import ops
+    npad = out.shape[1]
+    rows = out.view(B, H * W, npad)
+    g = torch.gather(rows, 1, ind.unsqueeze(-1).expand(-1, -1, npad))                  # [B, M, npad]
+    pred = g[..., off["iou"]]
+    with torch.no_grad():
+        x = (ind % W).to(g.dtype) + g[..., off["reg"]]
+        y = torch.div(ind, W, rounding_mode="floor").to(g.dtype) + g[..., off["reg"] + 1]
+        x = x * out_size_factor * voxel_size[0] + pc_range[0]                          # centerhead.py:201-204
+        y = y * out_size_factor * voxel_size[1] + pc_range[1]
+        dim = torch.exp(torch.clamp(g[..., off["dim"]:off["dim"] + 3], min=-5, max=5))
+        rot = torch.atan2(g[..., off["rot"]], g[..., off["rot"] + 1])
+        boxes = torch.cat([x.unsqueeze(-1), y.unsqueeze(-1), g[..., off["height"]:off["height"] + 1], dim, rot.unsqueeze(-1)], -1)
+        target = 2 * ops.aligned_iou3d(boxes.reshape(-1, 7), gt_boxes.reshape(-1, 7).to(boxes.dtype)).view(pred.shape) - 1
+    m = mask.bool()
+    l1 = torch.where(m, (pred - target).abs(), torch.zeros_like(pred))
+    return l1.sum() / (m.sum().to(pred.dtype) + 1e-4)

@@ -438,12 +438,20 @@ class CenterHead(nn.Module):
         return [task.run(y, B, H, W) for task in self.tasks]
 
     def loss(self, example, preds_dicts, **kwargs):
-        """centerhead.py:142-229 (nuScenes / Waymo without the `iou` head)."""
-        if self.with_iou:
-            raise NotImplementedError("the Waymo `iou` head loss (rotated aligned IoU target) is a 'next' row (F2)")
+        """centerhead.py:142-229, including the Waymo `iou` head branch (:210-215) on the fused-head path."""
         raws = [getattr(pd.get("hm"), "_pnx_raw", None) for pd in preds_dicts]
         if all(r is not None for r in raws) and all(set(r["off"]) >= {"reg", "height", "dim", "rot", "vel", "hm"} for r in raws):
-            return self._fused_loss(example, preds_dicts, raws)
+            total, rets = self._fused_loss(example, preds_dicts, raws)
+            if self.with_iou:
+                for t, r in enumerate(raws):
+                    il = L.iou_head_loss(r["out"], r["off"], r["B"], r["H"], r["W"], example["ind"][t], example["mask"][t],
+                                         example["gt_boxes"][t], self.out_size_factor[t], self.voxel_size, self.pc_range)
+                    total = total + il
+                    rets[t]["iou_loss"] = il.detach()
+                    rets[t]["loss"] = rets[t]["loss"] + il.detach()
+            return total, rets
+        if self.with_iou:
+            raise NotImplementedError("the `iou` head loss needs the fused head output (reg/height/dim/rot/vel/iou/hm)")
         return L.center_loss(example, preds_dicts, self.class_names, self.weight, self.code_weights, self.with_reg_iou,
                              getattr(self, "voxel_size", None), getattr(self, "pc_range", None),
                              getattr(self, "out_size_factor", None))

@@ -370,6 +370,16 @@ def wgrad(X, x_channels, Y, y_channels, M, taps, dW, *, nbr=None, dense=None, sh
     """dW[t, x, y] += sum_m X[m, x] * Y[g(m,t), y]; X direct, Y gathered; dW fp32 [taps, x_channels, y_channels]."""
     assert X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16 and dW.dtype == torch.float32
     assert tuple(dW.shape) == (taps, x_channels, y_channels) and dW.is_contiguous()
+    if x_channels != 64 and x_channels % 128 != 0:
+        # the kernel tiles X in 128-channel blocks (or one 64-channel block): split e.g. 448 = 384 + 64 column slices of X
+        # (seven sibling heads of a Waymo task); each part accumulates into its own zeroed buffer, added to its dW rows
+        assert x_channels % 64 == 0 and x_channels > 64, "x_channels must be a multiple of 64"
+        main = x_channels // 128 * 128
+        for x0, x1 in ((0, main), (main, x_channels)):
+            part = torch.zeros(taps, x1 - x0, y_channels, dtype=torch.float32, device=dW.device)
+            wgrad(X[:, x0:x1], x1 - x0, Y, y_channels, M, taps, part, nbr=nbr, dense=dense, shuffle=shuffle, gathered=gathered)
+            dW[:, x0:x1] += part
+        return dW
     d = dense or (0, 0, 0, 0, 1, 1, 1, 0)
     if gathered is None:
         gathered = nbr is not None or dense is not None or shuffle
@@ -473,3 +483,13 @@ def det_postprocess(out, B, H, W, C, offs, osf, voxel_size, pc_range, score_thr,
     check(L.pnx_det_gather(*common, ptr(order), ptr(seg_start), ptr(keep), ptr(keep_count), int(post_max), int(label_offset),
                            ptr(det_box), ptr(det_score), ptr(det_label), stream()))
     return det_box, det_score, det_label, keep_count
+
+
+def aligned_iou3d(boxes_a, boxes_b):
+    """[n, 7] x [n, 7] fp32 (x, y, z, dx, dy, dz, heading) -> [n] aligned 3-D IoU (iou3d_nms_utils.py:45-87)."""
+    assert boxes_a.shape == boxes_b.shape and boxes_a.shape[-1] == 7 and boxes_a.is_cuda
+    a, b = boxes_a.contiguous().float(), boxes_b.contiguous().float()
+    out = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+    _count(1)
+    check(lib().pnx_aligned_iou3d(ptr(a), ptr(b), a.shape[0], ptr(out), stream()))
+    return out

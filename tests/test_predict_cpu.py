@@ -183,3 +183,42 @@ def test_host_compiled_decode_with_rectifier_and_iou_head():
         assert [t[0] for t in got] == [t[0] for t in ref]
         assert torch.allclose(torch.tensor([t[1] for t in got]), torch.tensor([t[1] for t in ref]), atol=2e-6)
         assert torch.allclose(torch.tensor([t[2] for t in got]), torch.tensor([t[2] for t in ref]), atol=1e-5, rtol=1e-6)
+
+
+def test_iou_head_loss_oracle_matches_reference_loss():
+    """Waymo-style head (extra `iou` head, with_reg_iou): the reference's own CenterHead.loss on CPU, with only the
+    CUDA-only boxes_aligned_iou3d_gpu swapped for the oracle's aligned IoU, against the oracle's center_loss(with_iou)."""
+    if not reference_loader.available():
+        pytest.skip("reference tree not present (build container only)")
+    from oracle import pillarnext_oracle as O
+    from pillarnext_b200 import synth
+    ref = reference_loader.load_reference()
+    tasks = [["vehicle"], ["pedestrian", "cyclist"]]
+    cfg = synth.tiny_config(64, tasks)
+    heads = dict(reg=[2, 2], height=[1, 2], dim=[3, 2], rot=[2, 2], vel=[2, 2], iou=[1, 2])
+    head = ref.CenterHead(in_channels=256, tasks=tasks, weight=1.0, code_weights=cfg["code_weights"], common_heads=heads,
+                          strides=[2, 2], with_reg_iou=True, voxel_size=cfg["voxel_size"], pc_range=cfg["pc_range"],
+                          out_size_factor=[4, 4], rectifier=[[0.68], [0.71, 0.65]])
+    ex = synth.make_batch([3, 4], 1500, cfg, n_boxes=12, sweeps=1)
+    H = W = 64 // 8 * 2
+    g = torch.Generator().manual_seed(5)
+    preds = []
+    for t, names in enumerate(tasks):
+        pd = {k: torch.randn(2, c, H, W, generator=g) * 0.5 for k, (c, _) in heads.items()}
+        pd["hm"] = torch.randn(2, len(names), H, W, generator=g) - 2.0
+        preds.append(pd)
+    fake = lambda a, b: torch.tensor([[float(P.aligned_iou3d(x.numpy(), y.numpy()))] for x, y in zip(a, b)],
+                                     dtype=a.dtype).reshape(-1, 1)
+    saved = ref.centerloss.boxes_aligned_iou3d_gpu
+    ref.centerloss.boxes_aligned_iou3d_gpu = fake
+    try:
+        want, want_logs = head.loss(ex, [{k: v.clone() for k, v in pd.items()} for pd in preds])
+    finally:
+        ref.centerloss.boxes_aligned_iou3d_gpu = saved
+    got, logs = O.center_loss(ex, preds, 1.0, cfg["code_weights"], True, cfg["voxel_size"], cfg["pc_range"], [4, 4],
+                              with_iou=True)
+    assert abs(float(got) - float(want)) < 1e-5 * max(1.0, abs(float(want)))
+    for t in range(2):
+        assert float(ex["mask"][t].sum()) > 0
+        assert abs(float(logs[t]["iou_loss"]) - float(want_logs[t]["iou_loss"])) < 1e-6
+        assert 0.0 < float(logs[t]["iou_loss"]) < 2.0
