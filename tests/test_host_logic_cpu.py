@@ -1,0 +1,42 @@
+"""Host-side (Python) logic of the ops layer that needs no GPU: operand splitting, eligibility rules, config helpers."""
+import torch
+
+from pillarnext_b200 import ops
+
+
+def test_wgrad_splits_channel_counts_the_kernel_does_not_tile(monkeypatch):
+    """448 = 7 sibling heads x 64: the weight-gradient kernel tiles X in 128-channel blocks (or one 64 block), the
+    wrapper issues 384 + 64 column slices of the SAME row matrix and accumulates each into its rows of dW."""
+    calls = []
+
+    class FakeLib:
+        def pnx_wgrad(self, X, ldx, xc, Y, ldy, yc, gathered, M, taps, nbr, *rest):
+            dW_ptr = rest[9]
+            calls.append(dict(x_off=X, ldx=ldx, xc=xc, yc=yc, taps=taps, dW=dW_ptr))
+            return 0
+
+    monkeypatch.setattr(ops, "lib", lambda: FakeLib())
+    monkeypatch.setattr(ops, "ptr", lambda t: None if t is None else t.data_ptr())
+    monkeypatch.setattr(ops, "stream", lambda: 0)
+    monkeypatch.setattr(ops, "sm_count", lambda: 148)
+    X = torch.zeros(10, 448, dtype=torch.bfloat16)
+    Y = torch.zeros(10, 192, dtype=torch.bfloat16)
+    dW = torch.ones(9, 448, 192)
+    out = ops.wgrad(X, 448, Y, 192, 10, 9, dW, dense=(4, 4, 4, 4, 3, 1, 1, 1))
+    assert out is dW and torch.equal(dW, torch.ones_like(dW))                 # parts were zero: dW untouched
+    assert [(c["xc"], c["ldx"], c["x_off"] - X.data_ptr(), c["taps"]) for c in calls] == [(384, 448, 0, 9), (64, 448, 768, 9)]
+    assert all(c["dW"] != dW.data_ptr() for c in calls)                       # each part accumulates into its own buffer
+    calls.clear()
+    ops.wgrad(X[:, :384], 384, Y, 192, 10, 9, torch.zeros(9, 384, 192), dense=(4, 4, 4, 4, 3, 1, 1, 1))
+    assert len(calls) == 1 and calls[0]["xc"] == 384                          # supported widths go straight through
+
+
+def test_window_conv_eligibility():
+    d = lambda H, W, k=3, s=1, dil=1, pad=1: (H, W, H, W, k, s, dil, pad)
+    assert ops.win_eligible(d(336, 336), 384, 64)            # head conv at nuScenes resolution (3 x 128-pixel tiles)
+    assert ops.win_eligible(d(376, 376), 64, 64)             # Waymo-bench head
+    assert not ops.win_eligible(d(168, 168), 256, 256)       # 168 -> 2 tiles of 128 wastes 34 %: gather engine instead
+    assert not ops.win_eligible(d(336, 336, dil=6, pad=6), 256, 256)
+    assert not ops.win_eligible(d(336, 336, s=2), 64, 64)
+    assert not ops.win_eligible(None, 64, 64)
+    assert not ops.win_eligible(d(336, 336), 64, 64, out_fp32=True)
