@@ -119,7 +119,7 @@ int pnx_pfn_backward(const float* points, const int* bucket_off, const int* buck
                      const float* mean0, const float* invstd0, const float* gamma0, const float* scale1,
                      const float* shift1, const float* mean1, const float* invstd1, const float* gamma1,
                      int* argq1, float* d_x0, float* dxm_part, double* red, float* dW0, float* dW1,
-                     cudaStream_t stream);
+                     int phases, const int* bn_count, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- B1-B4 active sites / rulebook
  * Replaces spconv index-pair generation (sparse_conv.py:25-29,50-51; sparse_resnet.py:43-48,63-64).
@@ -157,7 +157,11 @@ int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void
               int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
               int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
               double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
-              long long ld_add, int sm_count, cudaStream_t stream);
+              long long ld_add, int nseg, long long a_lo_off, int addend_fp32, int sm_count, cudaStream_t stream);
+/* nseg > 1 selects the fp32-grade SPLIT mode (see "split rows" below): A rows hold bf16 pairs (hi at column c, lo at
+ * column a_lo_off + c), W is packed [taps, Cout, 2*Cin] = [w_hi | w_lo], and the K loop accumulates the segments
+ * hi*hi, lo*hi, hi*lo (nseg = 3) [+ lo*lo, nseg = 4] into the same fp32 TMEM accumulator.  addend_fp32 = 1: `addend`
+ * is fp32 [M, ld_add] (requires out_fp32).  nseg = 1, a_lo_off = 0, addend_fp32 = 0: the production bf16 path. */
 
 /* ---------------------------------------------------------------- dense 3x3 conv with TMA-folded im2col
  * out[(b,y,x), n] = sum_{r,s<3} sum_c A[(b, y+r-1, x+s-1), c] * W[r*3+s, n, c] (+bias)(relu), zero padding,
@@ -202,6 +206,37 @@ int pnx_add_relu(const void* a, long long lda, const void* b, long long ldb, lon
 int pnx_relu_bwd(const void* dy, long long lddy, const void* y, long long ldy, long long M, int C, void* g,
                  long long ldg, int accumulate, cudaStream_t stream);
 
+/* ---------------------------------------------------------------- fp32-grade "split rows" precision mode
+ * The reference is fp32 end to end (aspp.py:19-32, centerhead.py:128-136, sparse_conv.py:31-39; no autocast).  In
+ * this mode an activation row matrix stores every value as TWO bf16 numbers, hi = bf16(v) at column c and
+ * lo = bf16(v - hi) at column lo + c of the same row (~16 mantissa bits); the tensor-core kernels run over the hi/lo
+ * segments (pnx_igemm nseg = 3; three pnx_wgrad launches accumulate into the same dW) and raw convolution outputs,
+ * BatchNorm arithmetic and gradient sums stay fp32.  The kernels below are the row-wise glue of the mode
+ * (x = fp32 rows, everything named res / y / dy / dx / dres / a / b / g = split rows given as (pointer, ld, lo)).
+ * pnx_bn_bwd_reduce_split is two-stage with a fixed order (bit-reproducible): `part` = scratch of
+ * pnx_bn_bwd_reduce_split_scratch(C) doubles, `red` [2C] is fully written. */
+int pnx_rows_split(const float* x, long long ldx, long long M, int C, void* y, long long ldy, long long lo_y,
+                   cudaStream_t stream);
+int pnx_rows_merge(const void* x, long long ldx, long long lo_x, long long M, int C, float* y, long long ldy,
+                   int accumulate, cudaStream_t stream);
+int pnx_bn_apply_split(const float* x, long long ldx, long long M, int C, const float* scale, const float* shift,
+                       const void* res, long long ldr, long long lo_r, int relu, void* y, long long ldy, long long lo_y,
+                       cudaStream_t stream);
+long long pnx_bn_bwd_reduce_split_scratch(int C);
+int pnx_bn_bwd_reduce_split(const void* dy, long long lddy, long long lo_dy, const void* y, long long ldy,
+                            long long lo_y, const float* x, long long ldx, long long M, int C, const float* mean,
+                            const float* invstd, int relu, const float* fscale, const float* fshift, double* part,
+                            double* red, cudaStream_t stream);
+int pnx_bn_bwd_apply_split(const void* dy, long long lddy, long long lo_dy, const void* y, long long ldy,
+                           long long lo_y, const float* x, long long ldx, long long M, int C, const float* mean,
+                           const float* invstd, const float* gamma, const double* red, double count, int relu,
+                           const float* fscale, const float* fshift, void* dx, long long lddx, long long lo_dx,
+                           void* dres, long long lddres, long long lo_dres, cudaStream_t stream);
+int pnx_add_relu_split(const void* a, long long lda, long long lo_a, const void* b, long long ldb, long long lo_b,
+                       long long M, int C, void* y, long long ldy, long long lo_y, cudaStream_t stream);
+int pnx_relu_bwd_split(const float* dy, long long lddy, const void* y, long long ldy, long long lo_y, long long M,
+                       int C, void* g, long long ldg, long long lo_g, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- head final 3x3 convs as GEMM + stencil
  * out[m, j] = bias16[j] + sum_{t<9} Z[m + off_t, t*16 + j] on a B x H x W channels-last image (zero padding),
  * Z [M, ldz] fp32 = y . Wz^T from pnx_igemm (taps=1); pnx_tap_scatter is the mirrored backward gather
@@ -209,7 +244,8 @@ int pnx_relu_bwd(const void* dy, long long lddy, const void* y, long long ldy, l
  * of SepHead (centerhead.py:44-46) for all sibling heads at once. */
 int pnx_tap_gather_sum(const float* Z, long long ldz, const float* bias16, int B, int H, int W, float* out,
                        cudaStream_t stream);
-int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, cudaStream_t stream);
+int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, int nz, long long lo_off,
+                    cudaStream_t stream);   /* nz = GEMM columns (>= 144); lo_off > 0: also write the lo halves (split rows) */
 
 /* ---------------------------------------------------------------- L1 fused CenterPoint loss (forward + gradient)
  * One task: out/dout [B*H*W, npad] fp32 channels-last head output (columns reg2|height1|dim3|rot2|vel2|hm C|pad)
@@ -237,7 +273,7 @@ int pnx_center_loss_finalize(const double* acc, int n_tasks, const float* weight
  *   pnx_det_nms   : order = argsort(keys) (the caller sorts), seg_start = exclusive prefix of seg_count; for each
  *                   segment the first min(count, pre_max) candidates: suppression mask (scratch [B*C, pre_max,
  *                   ceil(pre_max/64)] u64) and greedy sweep on the device -> keep [B*C, post_max] (positions in the
- *                   segment's sorted run), keep_count [B*C].  pre_max <= 2048; mask row stride = ceil(pre_max/64).
+ *                   segment's sorted run), keep_count [B*C].  pre_max <= 8192 (reference Waymo configs: 4096); mask row stride = ceil(pre_max/64).
  *   pnx_det_gather: det_box [B*C, post_max, 9] (x,y,z,dx,dy,dz,vx,vy,yaw), det_score, det_label (+label_offset, i64).
  * The two *_host entry points evaluate the same inline decode / IoU code on HOST memory (CPU test hooks, no GPU). */
 int pnx_det_keys(const float* out, long long ld, int B, int H, int W, int C, const int* offs, float osf, float vs_x,

@@ -35,9 +35,9 @@ _SIGS = {
     "pnx_pfn_max0": [P, P, P, I, P, P, P, P],
     "pnx_pfn_lin1": [P, P, P, P, P, I, P, P, P, P, P, I, P],
     "pnx_pfn_max1": [P, P, P, I, P, P, P, P, P],
-    "pnx_pfn_backward": [P, P, P, P, P, P, I, I, F, F, F, F] + [P] * 23 + [P],
+    "pnx_pfn_backward": [P, P, P, P, P, P, I, I, F, F, F, F] + [P] * 23 + [I, P, P],
     "pnx_tap_gather_sum": [P, L, P, I, I, I, P, P],
-    "pnx_tap_scatter": [P, I, I, I, P, L, P],
+    "pnx_tap_scatter": [P, I, I, I, P, L, I, L, P],
     "pnx_center_loss_task": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, F, F, F, F, F, P, I, P, P],
     "pnx_center_loss_finalize": [P, I, P, P, P, P, P, P],
     "pnx_sites_out_dim": [I, I],
@@ -46,7 +46,7 @@ _SIGS = {
     "pnx_sites_coords": [P, P, P, I, I, I, P, I, P],
     "pnx_nbr_table": [P, P, I, P, P, P, I, I, I, I, I, P, P],
     "pnx_scatter_dense": [P, P, P, I, I, I, I, I, P, I, P],
-    "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, P, L, I, P],
+    "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, P, L, I, L, I, I, P],
     "pnx_conv3x3_win": [P, L, I, I, I, I, P, I, I, P, L, P, P, I, I, I, I, P],
     "pnx_wgrad": [P, L, I, P, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, P, I, P],
     "pnx_bn_apply": [P, L, L, I, P, P, P, L, I, P, L, P],
@@ -55,6 +55,15 @@ _SIGS = {
     "pnx_add_rows": [P, L, P, L, L, I, P],
     "pnx_add_relu": [P, L, P, L, L, I, P, L, P],
     "pnx_relu_bwd": [P, L, P, L, L, I, P, L, I, P],
+    # fp32-grade split-rows mode
+    "pnx_rows_split": [P, L, L, I, P, L, L, P],
+    "pnx_rows_merge": [P, L, L, L, I, P, L, I, P],
+    "pnx_bn_apply_split": [P, L, L, I, P, P, P, L, L, I, P, L, L, P],
+    "pnx_bn_bwd_reduce_split_scratch": [I],
+    "pnx_bn_bwd_reduce_split": [P, L, L, P, L, L, P, L, L, I, P, P, I, P, P, P, P, P],
+    "pnx_bn_bwd_apply_split": [P, L, L, P, L, L, P, L, L, I, P, P, P, P, ctypes.c_double, I, P, P, P, L, L, P, L, L, P],
+    "pnx_add_relu_split": [P, L, L, P, L, L, L, I, P, L, L, P],
+    "pnx_relu_bwd_split": [P, L, P, L, L, L, I, P, L, L, P],
     # F1: decode + rotated NMS.  common prefix = out, ld, B, H, W, C, offs, osf, vs_x, vs_y, pc_x, pc_y, score_thr, range6, rect
     "pnx_det_keys": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P],
     "pnx_det_nms": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P, P, I, I, P, P, P, P],
@@ -65,6 +74,7 @@ _SIGS = {
     "pnx_det_decode_host": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, L, P, P, P],
 }
 _RESTYPE = {"pnx_last_error": ctypes.c_char_p, "pnx_voxelize_bitmap_words": ctypes.c_size_t,
+            "pnx_bn_bwd_reduce_split_scratch": ctypes.c_longlong,
             "pnx_det_iou_bev_host": ctypes.c_float, "pnx_aligned_iou3d_host": ctypes.c_float}
 
 

@@ -35,6 +35,11 @@ struct IgemmParams {
   int shuffle, relu;
   const __nv_bfloat16* addend;  // optional [M, ld_add] bf16 added before the store (gradient accumulation)
   long long ld_add;
+  // fp32-grade "split" mode: A rows are bf16 pairs (hi at column c, lo at column a_lo_off + c), W rows are
+  // [w_hi(Cin) | w_lo(Cin)]; the K loop runs nseg segments (hi*hi, lo*hi, hi*lo[, lo*lo]) into the same fp32
+  // accumulator, so products carry ~16 mantissa bits.  nseg = 1: plain bf16.
+  int nseg, a_lo_off;
+  const float* addend_f32;      // fp32 addend (split mode: gradients are accumulated in fp32)
 };
 
 // threads = TMA warp + MMA warp + PW gather warps + 2 index warps + EW epilogue warps.
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
   const int num_pairs = (num_tiles + MT - 1) / MT;  // CTA iterations (groups of MT tiles)
   const int n0 = blockIdx.y * BN;
   const int kpt = p.Cin >> 6;
-  const int num_k = p.T * kpt;
+  const int num_k = p.T * kpt * p.nseg;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA weight producer
@@ -153,10 +158,11 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
       uint32_t phase = 0;
       for (int pt = blockIdx.x; pt < num_pairs; pt += gridDim.x) {
         for (int kc = 0; kc < num_k; ++kc) {
-          const int cc = kc / p.T, t = kc - cc * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
+          const int ccx = kc / p.T, t = kc - ccx * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
+          const int seg = ccx / kpt, cc = ccx - seg * kpt;
           pnx::mbar_wait(&empty[stage], phase ^ 1);
           pnx::mbar_arrive_expect_tx(&full[stage], kBBytes);
-          pnx::tma_load_2d(&wmap, &full[stage], sB + (size_t)stage * kBBytes, cc * 64, t * p.w_rows_per_tap + n0);
+          pnx::tma_load_2d(&wmap, &full[stage], sB + (size_t)stage * kBBytes, cc * 64 + (seg >= 2 ? p.Cin : 0), t * p.w_rows_per_tap + n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -218,7 +224,9 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
       for (int it = (int)((pw + kProducerWarps - i_base % kProducerWarps) % kProducerWarps); it < num_k * kParts; it += kProducerWarps) {
         const int kc = it / kParts, hs = it - kc * kParts;
         const int h = hs / SPLIT, part = hs - h * SPLIT;
-        const int cc = kc / p.T, t = kc - cc * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
+        const int ccx = kc / p.T, t = kc - ccx * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
+        const int seg = ccx / kpt, cc = ccx - seg * kpt;
+        const int acol = cc * 64 + ((seg & 1) ? p.a_lo_off : 0);
         const uint32_t g = g_base + (uint32_t)kc;
         const uint32_t stage = g % (uint32_t)kStages, phase = (g / (uint32_t)kStages) & 1u;
         const int* tbl = s_idx + ((tcount + h) % kTblSlots) * kTbl;
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
         if (lane == 0) pnx::mbar_arrive_expect_tx(&full[stage], kABytes / SPLIT);
         __syncwarp();
         if (lane < kLanes)
-          pnx::tma_gather4(&amap, &full[stage], pnx::smem_u32(sA + (size_t)stage * kAStage) + h * kABytes + l4 * 512, cc * 64,
+          pnx::tma_gather4(&amap, &full[stage], pnx::smem_u32(sA + (size_t)stage * kAStage) + h * kABytes + l4 * 512, acol,
                            rows.x, rows.y, rows.z, rows.w);
       }
       g_base += (uint32_t)num_k;
@@ -356,6 +364,14 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
             }
           }
         }
+        if (p.addend_f32 && active) {
+          const float4* ap = reinterpret_cast<const float4*>(p.addend_f32 + (long long)m * p.ld_add + ncol0);
+#pragma unroll
+          for (int k = 0; k < kColBlk / 4; ++k) {
+            const float4 u = __ldg(ap + k);
+            v[4 * k] += u.x; v[4 * k + 1] += u.y; v[4 * k + 2] += u.z; v[4 * k + 3] += u.w;
+          }
+        }
         if (p.relu) {
 #pragma unroll
           for (int k = 0; k < kColBlk; ++k) v[k] = fmaxf(v[k], 0.f);
@@ -376,6 +392,19 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
               const float4 val = *reinterpret_cast<const float4*>(slab + row * 128 + ((ch ^ (row & 7)) << 4));
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + mr * p.ldc + ncol0 + ch * 4) = val;
             }
+          }
+          if (p.stats) {
+            // lane = column of this 32-column block: sum the stored fp32 values over the tile's valid rows
+            const long long row0 = (long long)tile * 128 + quarter * 32;
+            const int nrows = (int)max((long long)0, min((long long)32, (long long)p.M - row0));
+            float s0 = 0.f, q0 = 0.f;
+            for (int row = 0; row < nrows; ++row) {
+              const float f = *reinterpret_cast<const float*>(slab + row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + (lane & 3) * 4);
+              s0 += f;
+              q0 = fmaf(f, f, q0);
+            }
+            atomicAdd(&st_sum[cb * 32 + lane], s0);
+            atomicAdd(&st_sq[cb * 32 + lane], q0);
           }
           __syncwarp();
         } else if (staged) {
@@ -520,7 +549,8 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
                          int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
                          int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
                          double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
-                         long long ld_add, int sm_count, cudaStream_t stream) {
+                         long long ld_add, int nseg, long long a_lo_off, int addend_fp32, int sm_count,
+                         cudaStream_t stream) {
   PNX_CHECK_ARG(M >= 0, "M");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(taps >= 1 && taps <= 9, "taps in [1,9]");
@@ -545,16 +575,23 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   p.out = out; p.ldc = ldc; p.out_fp32 = out_fp32; p.bias = bias;
   p.stats = stats; p.stats_C = stats_C; p.stats_mod = stats_mod > 0 ? stats_mod : 1 << 30;
   p.shuffle = shuffle; p.relu = relu;
-  p.addend = (const __nv_bfloat16*)addend; p.ld_add = ld_add;
+  p.addend = addend_fp32 ? nullptr : (const __nv_bfloat16*)addend;
+  p.addend_f32 = addend_fp32 ? (const float*)addend : nullptr;
+  p.ld_add = ld_add;
   PNX_CHECK_ARG(!(addend && shuffle), "addend is not supported with the pixel-shuffle store");
+  PNX_CHECK_ARG(nseg >= 1 && nseg <= 4, "nseg in [1,4]");
+  PNX_CHECK_ARG(nseg == 1 || (a_lo_off >= Cin && a_lo_off % 64 == 0 && a_lo_off + Cin <= lda), "split mode: a_lo_off");
+  PNX_CHECK_ARG(!addend_fp32 || out_fp32, "an fp32 addend needs an fp32 output");
+  p.nseg = nseg; p.a_lo_off = (int)a_lo_off;
+  const int wcols = nseg > 1 ? 2 * Cin : Cin;  // split mode: W rows are [w_hi | w_lo]
   CUtensorMap wmap;
-  int rc = pnx_encode_tmap_2d_bf16(&wmap, Wpacked, (uint64_t)taps * Cout, (uint64_t)Cin, (uint64_t)Cin * 2,
+  int rc = pnx_encode_tmap_2d_bf16(&wmap, Wpacked, (uint64_t)taps * Cout, (uint64_t)wcols, (uint64_t)wcols * 2,
                                    (uint32_t)block_n, 64);
   if (rc) return rc;
   // A as a 2-D tensor [rows, Cin] for tile::gather4 (box = one 64-channel row).  The row count only bounds the
   // out-of-range test of the gather (index -1 = absent neighbour = zero fill); valid indices come from the caller.
   CUtensorMap amap;
-  rc = pnx_encode_tmap_gather_bf16(&amap, A, (uint64_t)0x7fffffff, (uint64_t)Cin, (uint64_t)lda * 2);
+  rc = pnx_encode_tmap_gather_bf16(&amap, A, (uint64_t)0x7fffffff, (uint64_t)(nseg > 1 ? a_lo_off + Cin : Cin), (uint64_t)lda * 2);
   if (rc) return rc;
   const int n_blocks = Cout / block_n;
   switch (block_n) {
@@ -562,10 +599,10 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
     case 32: return launch_igemm<32, 8, 1, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     case 64: return launch_igemm<64, 8, 1, 1, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     case 128:
-      if (taps * (Cin / 64) <= 4) return launch_igemm<128, 4, 1, 2, 8>(wmap, amap, p, n_blocks, sm_count, stream);
+      if (taps * (Cin / 64) * nseg <= 4) return launch_igemm<128, 4, 1, 2, 8>(wmap, amap, p, n_blocks, sm_count, stream);
       return launch_igemm<128, 8, 1, 2, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     case 192:  // short K (1x1 convs of the head): the epilogue of 192 columns outlasts the MMA loop -> 8 epilogue warps
-      if (taps * (Cin / 64) <= 9) return launch_igemm<192, 4, 1, 2, 8>(wmap, amap, p, n_blocks, sm_count, stream);
+      if (taps * (Cin / 64) * nseg <= 9) return launch_igemm<192, 4, 1, 2, 8>(wmap, amap, p, n_blocks, sm_count, stream);
       return launch_igemm<192, 8, 1, 2, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     case 256:
       // (MT = 2, two tiles per weight stage, measured slower on every layer of the step: exposed epilogue of the single

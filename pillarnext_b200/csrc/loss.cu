@@ -115,7 +115,14 @@ __global__ void __launch_bounds__(128) loss_pos_kernel(LossTask t) {
   float pos = 0.f, el[10], iou_l = 0.f;
 #pragma unroll
   for (int c = 0; c < 10; ++c) el[c] = 0.f;
-  if (i < t.B * t.M && t.mask[i]) {
+  bool slot = i < t.B * t.M && t.mask[i];
+  if (slot && (t.ind[i] < 0 || t.ind[i] >= (long long)t.H * t.W || t.cat[i] < 0 || t.cat[i] >= t.C)) {
+    // a label built for another feature-map size / class list (the reference's gather raises an index error): skip the
+    // slot instead of writing outside the head matrix, and count it in acc[15] (res[15] = number of bad slots)
+    atomicAdd(&t.acc[15], 1.0);
+    slot = false;
+  }
+  if (slot) {
     const int b = i / t.M;
     const long long pix = (long long)b * t.H * t.W + t.ind[i];
     const float* o = t.out + pix * t.npad;
@@ -231,6 +238,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, int n_tasks
     res[t * 16 + 2] = loc;
     res[t * 16 + 3] = iou;
     res[t * 16 + 4] = npos;
+    res[t * 16 + 15] = (float)a[15];   // label slots skipped because ind / cat were out of range (0 for valid labels)
     tot += loss;
   }
   total[0] = tot;

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256)
                         const float* __restrict__ shift0, const float* __restrict__ mean1,
                         const float* __restrict__ invstd1, const float* __restrict__ gamma1,
                         const double* __restrict__ red1, const float* __restrict__ w1, float* __restrict__ d_x0,
-                        float* __restrict__ dxm_part, float* __restrict__ dW1) {
+                        float* __restrict__ dxm_part, float* __restrict__ dW1, const int* __restrict__ bn_count) {
   extern __shared__ float smem[];
   float* sdy = smem;                  // [64][kLd]
   float* sin_ = smem + 64 * kLd;      // [64][kLd]
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256)
   float* sc0 = sw + 4096;             // scale0[32], shift0[32]
   float* sbn = sc0 + 64;              // a[64] = gamma*invstd, b[64] = sum_g/n, c[64] = sum_gx/n, mean[64], invstd[64]
   const int nv = min(counts[1], cap_n);
-  const float inv_n = 1.f / (float)max(nv, 1);
+  const float inv_n = 1.f / (float)max(bn_count ? *bn_count : nv, 1);   // SyncBatchNorm: population of all ranks
   for (int k = threadIdx.x; k < 4096; k += 256) sw[k] = w1[k];
   if (threadIdx.x < 32) {
     sc0[threadIdx.x] = scale0[threadIdx.x];
@@ -185,12 +185,12 @@ __global__ void __launch_bounds__(320)
                         const float* __restrict__ pmean, const float* __restrict__ y0, const float* __restrict__ g0,
                         const int* __restrict__ counts, int cap_n, PfnGeom geo, const float* __restrict__ mean0,
                         const float* __restrict__ invstd0, const float* __restrict__ gamma0,
-                        const double* __restrict__ red0, float* __restrict__ dW0) {
+                        const double* __restrict__ red0, float* __restrict__ dW0, const int* __restrict__ bn_count) {
   __shared__ float sdy[32 * kLd];
   __shared__ float sf[10 * kLd];
   __shared__ float sbn[5 * 32];
   const int nv = min(counts[1], cap_n);
-  const float inv_n = 1.f / (float)max(nv, 1);
+  const float inv_n = 1.f / (float)max(bn_count ? *bn_count : nv, 1);
   if (threadIdx.x < 32) {
     const int c = threadIdx.x;
     sbn[c] = gamma0[c] * invstd0[c];
@@ -251,7 +251,7 @@ extern "C" int pnx_pfn_backward(const float* points, const int* bucket_off, cons
                                 const float* mean0, const float* invstd0, const float* gamma0, const float* scale1,
                                 const float* shift1, const float* mean1, const float* invstd1, const float* gamma1,
                                 int* argq1, float* d_x0, float* dxm_part, double* red, float* dW0, float* dW1,
-                                cudaStream_t stream) {
+                                int phases, const int* bn_count, cudaStream_t stream) {
   if (cap_points == 0 || cap_pillars == 0) return PNX_OK;
   static bool attr_set = false;
   const size_t smem_lin1 = (size_t)(2 * 64 * kLd + 4096 + 64 + 5 * 64) * sizeof(float);
@@ -263,19 +263,30 @@ extern "C" int pnx_pfn_backward(const float* points, const int* bucket_off, cons
   double* red1 = red + 64;   // [128]
   PfnGeom g{min_x, min_y, vs_x, vs_y};
   const int pblocks = min(pnx_cdiv((long long)cap_pillars * 32, 256), 148 * 8);
-  pfn_bwd_max1_kernel<<<pblocks, 256, 0, stream>>>(y1, feat, dfeat, bucket_off, counts, cap_pillars, scale1, shift1,
-                                                   mean1, invstd1, argq1, red1);
-  PNX_CHECK_LAUNCH();
-  pfn_bwd_lin1_kernel<<<pnx_cdiv(cap_points, 256), 256, smem_lin1, stream>>>(
-      y0, y1, x0max, dfeat, argq1, bucket_pts, pillar_of_point, counts, cap_points, scale0, shift0, mean1, invstd1,
-      gamma1, red1, w1, d_x0, dxm_part, dW1);
-  PNX_CHECK_LAUNCH();
-  pfn_bwd_max0_kernel<<<pblocks, 256, 0, stream>>>(y0, x0max, dxm_part, bucket_off, counts, cap_pillars, scale0,
-                                                   shift0, mean0, invstd0, d_x0, red0);
-  PNX_CHECK_LAUNCH();
-  pfn_bwd_lin0_kernel<<<pnx_cdiv(cap_points, 256), 320, 0, stream>>>(points, bucket_pts, pillar_of_point, coords,
-                                                                     pmean, y0, d_x0, counts, cap_points, g, mean0,
-                                                                     invstd0, gamma0, red0, dW0);
-  PNX_CHECK_LAUNCH();
+  // phases (bit mask; 0 = all four): 1 max1 | 2 lin1 | 4 max0 | 8 lin0.  SyncBatchNorm callers run {1}, all-reduce red1,
+  // {2,4}, all-reduce red0, {8}, and pass bn_count = device int holding the population of all ranks.
+  if (phases == 0) phases = 15;
+  if (phases & 1) {
+    pfn_bwd_max1_kernel<<<pblocks, 256, 0, stream>>>(y1, feat, dfeat, bucket_off, counts, cap_pillars, scale1, shift1,
+                                                     mean1, invstd1, argq1, red1);
+    PNX_CHECK_LAUNCH();
+  }
+  if (phases & 2) {
+    pfn_bwd_lin1_kernel<<<pnx_cdiv(cap_points, 256), 256, smem_lin1, stream>>>(
+        y0, y1, x0max, dfeat, argq1, bucket_pts, pillar_of_point, counts, cap_points, scale0, shift0, mean1, invstd1,
+        gamma1, red1, w1, d_x0, dxm_part, dW1, bn_count);
+    PNX_CHECK_LAUNCH();
+  }
+  if (phases & 4) {
+    pfn_bwd_max0_kernel<<<pblocks, 256, 0, stream>>>(y0, x0max, dxm_part, bucket_off, counts, cap_pillars, scale0,
+                                                     shift0, mean0, invstd0, d_x0, red0);
+    PNX_CHECK_LAUNCH();
+  }
+  if (phases & 8) {
+    pfn_bwd_lin0_kernel<<<pnx_cdiv(cap_points, 256), 320, 0, stream>>>(points, bucket_pts, pillar_of_point, coords,
+                                                                       pmean, y0, d_x0, counts, cap_points, g, mean0,
+                                                                       invstd0, gamma0, red0, dW0, bn_count);
+    PNX_CHECK_LAUNCH();
+  }
   return PNX_OK;
 }

@@ -241,20 +241,33 @@ __global__ void __launch_bounds__(64) det_mask_kernel(DetParams p, const long lo
   }
 }
 
-// greedy sweep of one segment by one warp: lane l owns word l of the removed-set (col_blocks <= 32)
+// greedy sweep of one segment by one warp: word w of the removed-set lives in lane w % 32, slot w / 32
+// (col_blocks <= 32 * kSweepSlots, i.e. pre_max <= 8192: the reference's Waymo configs use nms_pre_max_size 4096)
+constexpr int kSweepSlots = 4;
 __global__ void __launch_bounds__(32) det_sweep_kernel(const int* __restrict__ seg_count, int pre_max, int post_max,
                                                        int col_blocks, const unsigned long long* __restrict__ mask,
                                                        int* __restrict__ keep, int* __restrict__ keep_count) {
   const int s = blockIdx.x, lane = threadIdx.x;
   const int n = min(seg_count[s], pre_max);
-  unsigned long long remv = 0;
+  unsigned long long remv[kSweepSlots];
+#pragma unroll
+  for (int q = 0; q < kSweepSlots; ++q) remv[q] = 0;
   int kept = 0;
   for (int i = 0; i < n && kept < post_max; ++i) {
-    const unsigned long long w = __shfl_sync(0xffffffffu, remv, i >> 6);
+    const int wi = i >> 6, slot = wi >> 5;
+    unsigned long long mine = remv[0];
+#pragma unroll
+    for (int q = 1; q < kSweepSlots; ++q) mine = slot == q ? remv[q] : mine;
+    const unsigned long long w = __shfl_sync(0xffffffffu, mine, wi & 31);
     if (!((w >> (i & 63)) & 1ULL)) {
       if (lane == 0) keep[s * post_max + kept] = i;
       ++kept;
-      if (lane * 64 < n && lane >= (i >> 6)) remv |= mask[((size_t)s * pre_max + i) * col_blocks + lane];
+      const unsigned long long* row = mask + ((size_t)s * pre_max + i) * col_blocks;
+#pragma unroll
+      for (int q = 0; q < kSweepSlots; ++q) {
+        const int word = q * 32 + lane;
+        if (word < col_blocks && word * 64 < n && word >= wi) remv[q] |= row[word];
+      }
     }
   }
   if (lane == 0) keep_count[s] = kept;
@@ -334,7 +347,7 @@ extern "C" int pnx_det_nms(const float* out, long long ld, int B, int H, int W, 
   int rc = fill_params(&p, out, ld, B, H, W, C, offs, osf, vs_x, vs_y, pc_x, pc_y, score_thr, range6, rect, nms_thr);
   if (rc) return rc;
   PNX_CHECK_ARG(nms_thr, "nms thresholds");
-  PNX_CHECK_ARG(pre_max >= 1 && pre_max <= 2048, "pre_max in [1, 2048]");
+  PNX_CHECK_ARG(pre_max >= 1 && pre_max <= 64 * 32 * kSweepSlots, "pre_max in [1, 8192]");
   PNX_CHECK_ARG(post_max >= 1 && post_max <= pre_max, "post_max");
   const int col_blocks = (pre_max + 63) / 64;
   const int n_seg = B * C;

@@ -38,15 +38,16 @@ __global__ void tap_gather_sum_kernel(const float* __restrict__ Z, long long ldz
 }
 
 // dZ [M, ldz] bf16 (columns >= 144 zero) ; dout [M,16] fp32 ; one thread = one pixel x one 16-byte chunk of dZ
+// lo_off > 0 (fp32-grade split mode): dZ rows are [hi(nz) | lo(nz)] pairs, lo = bf16(v - hi) at column lo_off + c
 __global__ void tap_scatter_kernel(const float* __restrict__ dout, int B, int H, int W, __nv_bfloat16* __restrict__ dZ,
-                                   long long ldz) {
-  const int chunks = (int)(ldz >> 3);  // 8 bf16 per chunk
+                                   long long ldz, int nz, long long lo_off) {
+  const int chunks = nz >> 3;  // 8 bf16 per chunk
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long M = (long long)B * H * W;
   const long long m = t / chunks;
   const int c = (int)(t - m * chunks);
   if (m >= M) return;
-  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = make_uint4(0u, 0u, 0u, 0u);
   const int tap = c >> 1, half = c & 1;  // chunk c covers columns c*8 .. c*8+7 = tap (c/2), outputs half*8 ..
   if (tap < 9) {
     const int hw = H * W;
@@ -60,9 +61,18 @@ __global__ void tap_scatter_kernel(const float* __restrict__ dout, int B, int H,
       const float4 a = __ldg(reinterpret_cast<const float4*>(d)), bq = __ldg(reinterpret_cast<const float4*>(d + 4));
       o = make_uint4(pnx::pack_bf16x2(a.x, a.y), pnx::pack_bf16x2(a.z, a.w), pnx::pack_bf16x2(bq.x, bq.y),
                      pnx::pack_bf16x2(bq.z, bq.w));
+      if (lo_off > 0) {
+        const float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+        float l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) l[k] = v[k] - pnx::bf16_round(v[k]);
+        ol = make_uint4(pnx::pack_bf16x2(l[0], l[1]), pnx::pack_bf16x2(l[2], l[3]), pnx::pack_bf16x2(l[4], l[5]),
+                        pnx::pack_bf16x2(l[6], l[7]));
+      }
     }
   }
   *reinterpret_cast<uint4*>(dZ + m * ldz + c * 8) = o;
+  if (lo_off > 0) *reinterpret_cast<uint4*>(dZ + m * ldz + lo_off + c * 8) = ol;
 }
 
 }  // namespace
@@ -77,11 +87,13 @@ extern "C" int pnx_tap_gather_sum(const float* Z, long long ldz, const float* bi
   return PNX_OK;
 }
 
-extern "C" int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, cudaStream_t stream) {
-  PNX_CHECK_ARG(ldz >= 144 && ldz % 8 == 0, "ldz");
-  const long long threads = (long long)B * H * W * (ldz / 8);
+extern "C" int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, int nz, long long lo_off,
+                               cudaStream_t stream) {
+  PNX_CHECK_ARG(nz >= 144 && nz % 8 == 0 && ldz >= nz && ldz % 8 == 0, "nz/ldz");
+  PNX_CHECK_ARG(lo_off == 0 || (lo_off >= nz && lo_off + nz <= ldz && lo_off % 8 == 0), "lo_off");
+  const long long threads = (long long)B * H * W * (nz / 8);
   if (threads == 0) return PNX_OK;
-  tap_scatter_kernel<<<pnx_cdiv(threads, 256), 256, 0, stream>>>(dout, B, H, W, (__nv_bfloat16*)dZ, ldz);
+  tap_scatter_kernel<<<pnx_cdiv(threads, 256), 256, 0, stream>>>(dout, B, H, W, (__nv_bfloat16*)dZ, ldz, nz, lo_off);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }

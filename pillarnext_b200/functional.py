@@ -11,6 +11,50 @@ import torch.distributed as dist
 from . import ops
 
 
+# ------------------------------------------------------------------------------------------- precision mode
+# "bf16"  : production path -- bf16 tensor-core operands and stored activations, fp32 accumulation.
+# "split" : fp32-grade parity mode -- every activation is a (hi, lo) bf16 pair ([M, 2C] rows, include/pnx.h "split
+#           rows"), the same tcgen05 kernels run over the hi/lo segments, raw conv outputs / BatchNorm / gradient sums
+#           are fp32.  ~3x the tensor work and ~3x the bytes: used to demonstrate the north-star tolerance (1e-3 abs
+#           vs the fp32 reference), not for throughput.
+_PRECISION = "bf16"
+
+
+def set_precision(mode):
+    global _PRECISION
+    assert mode in ("bf16", "split")
+    prev, _PRECISION = _PRECISION, mode
+    return prev
+
+
+def get_precision():
+    return _PRECISION
+
+
+class precision:
+    """with precision("split"): ...   (the mode is read at forward time and remembered for the backward)"""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = set_precision(self.mode)
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
+def _split():
+    return _PRECISION == "split"
+
+
+def _to_hilo(p):
+    """fp32 packed weights [..., K] -> bf16 [..., 2K] = [hi | lo]."""
+    hi = p.to(torch.bfloat16)
+    lo = (p - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], -1).contiguous()
+
+
 # ------------------------------------------------------------------------------------------- weights
 class WLayout:
     """Packing between a parameter's native layout and the kernels' [taps, Cout, Cin] layout.
@@ -20,7 +64,7 @@ class WLayout:
     def __init__(self, kind):
         self.kind = kind
 
-    def pack_fwd(self, w):
+    def pack_fwd(self, w, split=False):
         if self.kind == "dense":
             co, ci, kh, kw = w.shape
             p = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
@@ -30,17 +74,24 @@ class WLayout:
         else:
             ci, co, kh, kw = w.shape
             p = w.permute(2, 3, 1, 0).reshape(1, kh * kw * co, ci)
-        return p.to(torch.bfloat16).contiguous()
+        return _to_hilo(p.float()) if split else p.to(torch.bfloat16).contiguous()
 
-    def pack_dgrad(self, w, flip):
-        """[taps_d, Cin, Cout] bf16 for the data-gradient GEMM."""
+    def pack_dgrad(self, w, flip, split=False):
+        """[taps_d, Cin, Cout] bf16 for the data-gradient GEMM (split: [taps_d, Cin, 2*Cout] = hi | lo)."""
         if self.kind == "convT":
             ci, co, kh, kw = w.shape
-            return w.permute(2, 3, 0, 1).reshape(kh * kw, ci, co).to(torch.bfloat16).contiguous()
-        p = self.pack_fwd(w)
-        if flip:
-            p = p.flip(0)
-        return p.transpose(1, 2).contiguous()
+            p = w.permute(2, 3, 0, 1).reshape(kh * kw, ci, co)
+        else:
+            if self.kind == "dense":
+                co, ci, kh, kw = w.shape
+                p = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+            else:
+                co, kh, kw, ci = w.shape
+                p = w.permute(2, 1, 0, 3).reshape(kh * kw, co, ci)
+            if flip:
+                p = p.flip(0)
+            p = p.transpose(1, 2)
+        return _to_hilo(p.float()) if split else p.to(torch.bfloat16).contiguous()
 
     def unpack_grad(self, g, shape):
         """g fp32 [taps, Cout, Cin] (convT: [4, Cin, Cout]) -> gradient in the parameter's layout."""
@@ -57,18 +108,20 @@ class WLayout:
 _pack_cache = {}
 
 
-def packed(w, layout, which, flip=False):
-    """Cache of bf16 packed weights keyed by parameter identity + version (repacked after optimizer steps)."""
-    if not w.is_leaf:  # e.g. per-step torch.cat of sibling-head weights: nothing stable to key on
+def packed(w, layout, which, flip=False, split=False):
+    """Cache of bf16 packed weights keyed by parameter identity + version (repacked after optimizer steps).
+    Only real parameters are cached: transient tensors (e.g. a torch.cat of sibling-head weights, a leaf under
+    no_grad) have no stable identity and would only grow the cache."""
+    if not isinstance(w, torch.nn.Parameter):
         with torch.no_grad():
-            return layout.pack_fwd(w) if which == "fwd" else layout.pack_dgrad(w, flip)
-    key = (id(w), which, flip, layout.kind)
+            return layout.pack_fwd(w, split) if which == "fwd" else layout.pack_dgrad(w, flip, split)
+    key = (id(w), which, flip, layout.kind, split)
     ent = _pack_cache.get(key)
     ver = w._version
     if ent is not None and ent[0] == ver and ent[1]() is w and ent[3] == w.data_ptr():
         return ent[2]
     with torch.no_grad():
-        p = layout.pack_fwd(w) if which == "fwd" else layout.pack_dgrad(w, flip)
+        p = layout.pack_fwd(w, split) if which == "fwd" else layout.pack_dgrad(w, flip, split)
     if len(_pack_cache) > 4096:      # ids of dead tensors: drop everything rather than grow without bound
         _pack_cache.clear()
     _pack_cache[key] = (ver, weakref.ref(w), p, w.data_ptr())
@@ -117,13 +170,21 @@ class ConvFn(torch.autograd.Function):
             cout, cin = shape[0], shape[3]
         else:
             cin, cout = shape[0], shape[1]
-        wp = packed(w, layout, "fwd")
+        split = _split()
+        wp = packed(w, layout, "fwd", split=split)
         n_cols = wp.shape[1]
         rows = spec.M_out * (4 if spec.shuffle else 1)
         out_c = cout
+        if split:
+            out_fp32 = True      # raw convolution outputs stay fp32 in the fp32-grade mode
+            assert not relu and x.shape[1] % 2 == 0 and x.shape[1] // 2 >= cin
         out = torch.empty(rows, out_c, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
         stats = torch.zeros(2 * cout if want_stats else 0, dtype=torch.float64, device=x.device)
-        if layout.kind == "dense" and spec.nbr is None and ops.win_eligible(spec.dense, n_cols, cin, out_fp32, spec.shuffle):
+        if split:
+            ops.igemm(x, spec.M_out, wp, wp.shape[0], cin, n_cols, out, lda=x.stride(0), ldc=out_c, nbr=spec.nbr,
+                      dense=spec.dense, bias=bias, stats=stats if want_stats else None,
+                      stats_mod=cout if want_stats else None, shuffle=spec.shuffle, nseg=3, a_lo_off=x.shape[1] // 2)
+        elif layout.kind == "dense" and spec.nbr is None and ops.win_eligible(spec.dense, n_cols, cin, out_fp32, spec.shuffle):
             H_, W_ = spec.dense[0], spec.dense[1]
             ops.conv3x3_win(x, spec.M_out // (H_ * W_), H_, W_, wp, cin, n_cols, out, bias=bias,
                             stats=stats if want_stats else None, relu=relu)          # im2col folded into TMA
@@ -135,11 +196,48 @@ class ConvFn(torch.autograd.Function):
         ctx.spec, ctx.layout, ctx.dims = spec, layout, (cin, cout, shape)
         ctx.has_bias, ctx.relu, ctx.out_fp32 = bias is not None, relu, out_fp32
         ctx.bias_feeds_bn = bool(bias_feeds_bn)
+        ctx.split = split
         ctx.mark_non_differentiable(stats)
         return out, stats
 
     @staticmethod
+    def _backward_split(ctx, dout):
+        """fp32-grade mode: dout = split rows [rows, 2*cout]; data gradient = hi/lo-segment GEMM -> fp32 -> split rows,
+        weight gradient = three launches (hi*hi, lo*hi, hi*lo) into the same fp32 accumulator."""
+        x, w, _ = ctx.saved_tensors
+        spec, layout = ctx.spec, ctx.layout
+        cin, cout, shape = ctx.dims
+        rows = dout.shape[0]
+        assert dout.dtype == torch.bfloat16 and dout.shape[1] == 2 * cout and cout % 64 == 0, "split mode: gradient rows [M, 2*Cout]"
+        dy = dout.contiguous()
+        xlo = x.shape[1] // 2
+        dbias = None
+        if ctx.has_bias:
+            dbias = torch.zeros(cout, dtype=torch.float32, device=dy.device) if ctx.bias_feeds_bn else \
+                ops.rows_merge(dy, cout, cout).sum(0)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wd = packed(w, layout, "dgrad", spec.d_flip, split=True)        # [taps_d, Cin, 2*Cout]
+            d32 = torch.empty(spec.M_in, cin, dtype=torch.float32, device=dy.device)
+            ops.igemm(dy, spec.M_in, wd, wd.shape[0], cout, cin, d32, nbr=spec.d_nbr, dense=spec.d_dense, nseg=3, a_lo_off=cout)
+            dx = torch.zeros(x.shape[0], x.shape[1], dtype=torch.bfloat16, device=dy.device) if xlo != cin else \
+                torch.empty(x.shape[0], x.shape[1], dtype=torch.bfloat16, device=dy.device)
+            ops.rows_split(d32, cin, out=dx, lo=xlo)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if layout.kind == "convT":
+                g = torch.zeros(4, cin, cout, dtype=torch.float32, device=dy.device)
+                ops.wgrad_split(x, xlo, cin, dy, cout, cout, spec.M_out, 4, g, dense=spec.d_dense, shuffle=True)
+            else:
+                g = torch.zeros(spec.taps, cout, cin, dtype=torch.float32, device=dy.device)
+                ops.wgrad_split(dy, cout, cout, x, xlo, cin, spec.M_out, spec.taps, g, nbr=spec.nbr, dense=spec.dense)
+            dw = layout.unpack_grad(g, shape)
+        return dx, dw, dbias, None, None, None, None, None, None
+
+    @staticmethod
     def backward(ctx, dout, _dstats):
+        if ctx.split:
+            return ConvFn._backward_split(ctx, dout)
         x, w, out = ctx.saved_tensors
         spec, layout = ctx.spec, ctx.layout
         cin, cout, shape = ctx.dims
@@ -231,14 +329,42 @@ class BNActFn(torch.autograd.Function):
         else:
             scale, shift = ops.bn_eval_affine(gamma, beta, bn.running_mean, bn.running_var, bn.eps)
             mean = invstd = None
-        y = torch.empty(M, C, dtype=torch.bfloat16, device=x_raw.device)
-        ops.bn_apply(x_raw, M, C, scale, shift, y, res=residual, relu=relu)
+        ctx.split = x_raw.dtype == torch.float32
+        if ctx.split:            # fp32-grade mode: fp32 raw conv output -> split rows
+            y = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=x_raw.device)
+            ops.bn_apply_split(x_raw, M, C, scale, shift, y, C, res=residual, res_lo=C, relu=relu)
+        else:
+            y = torch.empty(M, C, dtype=torch.bfloat16, device=x_raw.device)
+            ops.bn_apply(x_raw, M, C, scale, shift, y, res=residual, relu=relu)
         ctx.save_for_backward(x_raw, y, gamma, mean, invstd, scale, shift)
         ctx.relu, ctx.count, ctx.has_res, ctx.sync, ctx.training = relu, count, residual is not None, _sync_enabled(bn), bn.training
         return y
 
     @staticmethod
+    def _backward_split(ctx, dy):
+        x_raw, y, gamma, mean, invstd, scale, shift = ctx.saved_tensors
+        M, C = x_raw.shape
+        dy = dy.contiguous()
+        assert dy.shape[1] == 2 * C
+        ysrc = y if ctx.has_res else None
+        red = ops.bn_bwd_reduce_split(dy, C, ysrc, C, x_raw, M, C, mean, invstd, ctx.relu, (scale, shift))
+        local = red
+        if ctx.sync:
+            red = red.clone()
+            dist.all_reduce(red)
+        dx = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=dy.device)
+        dres = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=dy.device) if ctx.has_res else None
+        ops.bn_bwd_apply_split(dy, C, ysrc, C, x_raw, M, C, mean, invstd, gamma, red, ctx.count, ctx.relu, (scale, shift),
+                               dx, C, dres=dres, dres_lo=C)
+        r = local.float()
+        return dx, None, r[C:], r[:C], dres, None, None, None
+
+    @staticmethod
     def backward(ctx, dy):
+        if not ctx.training:
+            raise RuntimeError("pillarnext_b200: backward through eval-mode BatchNorm is not supported")
+        if ctx.split:
+            return BNActFn._backward_split(ctx, dy)
         x_raw, y, gamma, mean, invstd, scale, shift = ctx.saved_tensors
         M, C = x_raw.shape
         dy = dy.contiguous()
@@ -268,6 +394,33 @@ class BNActFn(torch.autograd.Function):
 
 def bn_act(x_raw, stats, bn, relu=True, residual=None, count=None):
     return BNActFn.apply(x_raw, stats, bn.weight, bn.bias, residual, bn, relu, x_raw.shape[0] if count is None else count)
+
+
+# ------------------------------------------------------------------------------------------- fp32 <-> split rows
+class SplitFn(torch.autograd.Function):
+    """fp32 rows [M, C] -> split rows [M, 2C] (fp32-grade mode); backward merges the gradient halves."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.C = x.shape[1]
+        return ops.rows_split(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, d):
+        return ops.rows_merge(d.contiguous(), ctx.C, ctx.C)
+
+
+class MergeFn(torch.autograd.Function):
+    """split rows [M, 2C] -> fp32 rows [M, C]; backward splits the fp32 gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        C = x.shape[1] // 2
+        return ops.rows_merge(x.contiguous(), C, C)
+
+    @staticmethod
+    def backward(ctx, d):
+        return ops.rows_split(d.contiguous())
 
 
 # ------------------------------------------------------------------------------------------- dense()
@@ -300,7 +453,55 @@ class ASPPBranchesFn(torch.autograd.Function):
     DILS = (1, 6, 12, 18)
 
     @staticmethod
+    def _forward_split(ctx, o, idt, w1x1, wshared, B, H, W):
+        """fp32-grade mode: cat buffer [M, 12C] = six hi slots then six lo slots (a split matrix with lo = 6C)."""
+        M, C = o.shape[0], o.shape[1] // 2
+        C6, ld = 6 * C, 12 * C
+        cat_buf = torch.empty(M, ld, dtype=torch.bfloat16, device=o.device)
+        l = WLayout("dense")
+        ops.add_relu_split(o, C, idt, C, M, C, cat_buf, C6)
+        tmp = torch.empty(M, C, dtype=torch.float32, device=o.device)
+        ops.igemm(cat_buf, M, packed(w1x1, l, "fwd", split=True), 1, C, C, tmp, lda=ld, nseg=3, a_lo_off=C6)
+        ops.rows_split(tmp, C, out=cat_buf[:, C:], lo=C6)
+        wp = packed(wshared, l, "fwd", split=True)
+        for j, d in enumerate(ASPPBranchesFn.DILS):
+            ops.igemm(cat_buf, M, wp, 9, C, C, tmp, lda=ld, dense=(H, W, H, W, 3, 1, d, d), nseg=3, a_lo_off=C6)
+            ops.rows_split(tmp, C, out=cat_buf[:, (2 + j) * C:], lo=C6)
+        ctx.save_for_backward(cat_buf, w1x1, wshared)
+        ctx.geo = (B, H, W, C)
+        ctx.split = True
+        return cat_buf
+
+    @staticmethod
+    def _backward_split(ctx, dcat):
+        cat_buf, w1x1, wshared = ctx.saved_tensors
+        B, H, W, C = ctx.geo
+        M = cat_buf.shape[0]
+        C6, ld = 6 * C, 12 * C
+        l = WLayout("dense")
+        dcat = dcat.contiguous()
+        dx = ops.rows_merge(dcat, C, C6)                                   # fp32 accumulator of the five branches
+        nxt = torch.empty_like(dx)
+        ops.igemm(dcat[:, C:], M, packed(w1x1, l, "dgrad", True, split=True), 1, C, C, nxt, lda=ld, addend=dx, nseg=3, a_lo_off=C6)
+        dx, nxt = nxt, dx
+        wd = packed(wshared, l, "dgrad", True, split=True)
+        for j, d in enumerate(ASPPBranchesFn.DILS):
+            ops.igemm(dcat[:, (2 + j) * C:], M, wd, 9, C, C, nxt, lda=ld, dense=(H, W, H, W, 3, 1, d, d), addend=dx, nseg=3, a_lo_off=C6)
+            dx, nxt = nxt, dx
+        g1 = torch.zeros(1, C, C, dtype=torch.float32, device=dcat.device)
+        ops.wgrad_split(dcat[:, C:], C6, C, cat_buf, C6, C, M, 1, g1)
+        gs = torch.zeros(9, C, C, dtype=torch.float32, device=dcat.device)
+        for j, d in enumerate(ASPPBranchesFn.DILS):
+            ops.wgrad_split(dcat[:, (2 + j) * C:], C6, C, cat_buf, C6, C, M, 9, gs, dense=(H, W, H, W, 3, 1, d, d))
+        g = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=dcat.device)
+        ops.relu_bwd_split(dx, cat_buf, C6, M, C, g, C)
+        return g, g, l.unpack_grad(g1, tuple(w1x1.shape)), l.unpack_grad(gs, tuple(wshared.shape)), None, None, None
+
+    @staticmethod
     def forward(ctx, o, idt, w1x1, wshared, B, H, W):
+        if _split():
+            return ASPPBranchesFn._forward_split(ctx, o, idt, w1x1, wshared, B, H, W)
+        ctx.split = False
         M, C = o.shape
         C6 = 6 * C
         cat_buf = torch.empty(M, C6, dtype=torch.bfloat16, device=o.device)
@@ -317,6 +518,8 @@ class ASPPBranchesFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dcat):
+        if ctx.split:
+            return ASPPBranchesFn._backward_split(ctx, dcat)
         cat_buf, w1x1, wshared = ctx.saved_tensors
         B, H, W, C = ctx.geo
         M, C6 = cat_buf.shape
@@ -349,7 +552,8 @@ class PFNFn(torch.autograd.Function):
     def forward(ctx, w0, g0, b0, w1, g1, b1, voxels, bn0, bn1, training):
         P, _ = voxels.sync_counts()
         fwd = ops.pfn_forward(voxels, w0, (g0, b0, bn0.running_mean, bn0.running_var), w1,
-                              (g1, b1, bn1.running_mean, bn1.running_var), training, eps=bn0.eps, momentum=bn0.momentum)
+                              (g1, b1, bn1.running_mean, bn1.running_var), training, eps=bn0.eps, momentum=bn0.momentum,
+                              sync=_sync_enabled(bn0) or _sync_enabled(bn1))
         if training:
             for bn in (bn0, bn1):
                 if bn.num_batches_tracked is not None:
@@ -417,7 +621,8 @@ class CenterLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, _g_res):
-        return (None,) + tuple(d.mul_(g_total) for d in ctx.douts)
+        # out of place: the cached gradients stay valid for a second backward (retain_graph) and are never aliased
+        return (None,) + tuple(d * g_total for d in ctx.douts)
 
 
 # ------------------------------------------------------------------------------------------- head final convs
@@ -431,13 +636,16 @@ class HeadFinalConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, wb, bias, B, H, W):
         from ._lib import check, lib, ptr, stream
-        M, cin = y.shape
+        split = _split()
+        M, cin = y.shape[0], y.shape[1] // (2 if split else 1)
         assert wb.shape[0] == 16 and wb.shape[2] == 3
         with torch.no_grad():
-            wz = torch.zeros(1, HeadFinalConvFn.NZ, cin, dtype=torch.bfloat16, device=y.device)
-            wz[0, :144] = wb.permute(2, 3, 0, 1).reshape(144, cin).to(torch.bfloat16)       # row = tap*16 + j
+            wz = torch.zeros(1, HeadFinalConvFn.NZ, cin, dtype=torch.float32, device=y.device)
+            wz[0, :144] = wb.permute(2, 3, 0, 1).reshape(144, cin)                          # row = tap*16 + j
+            wz = _to_hilo(wz) if split else wz.to(torch.bfloat16)
         Z = torch.empty(M, HeadFinalConvFn.NZ, dtype=torch.float32, device=y.device)
-        ops.igemm(y, M, wz, 1, cin, HeadFinalConvFn.NZ, Z, block_n=192)
+        ops.igemm(y, M, wz, 1, cin, HeadFinalConvFn.NZ, Z, block_n=192, nseg=3 if split else 1, a_lo_off=cin if split else 0)
+        ctx.split = split
         out = torch.empty(M, 16, dtype=torch.float32, device=y.device)
         ops._count(1)
         check(lib().pnx_tap_gather_sum(ptr(Z), HeadFinalConvFn.NZ, ptr(bias.detach().float().contiguous()), B, H, W, ptr(out), stream()))
@@ -452,9 +660,22 @@ class HeadFinalConvFn(torch.autograd.Function):
         B, H, W, cin, wshape = ctx.geo
         M, NZ = y.shape[0], HeadFinalConvFn.NZ
         dout = dout.contiguous().float()
+        if ctx.split:
+            dZ = torch.empty(M, 2 * NZ, dtype=torch.bfloat16, device=dout.device)
+            ops._count(1)
+            check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), 2 * NZ, NZ, NZ, stream()))
+            dbias = dout.sum(0)
+            wzf = wz[0, :, :cin].float() + wz[0, :, cin:].float()                           # [NZ, cin] (hi + lo)
+            d32 = torch.empty(M, cin, dtype=torch.float32, device=dout.device)
+            ops.igemm(dZ, M, _to_hilo(wzf.t().contiguous().unsqueeze(0)), 1, NZ, cin, d32, nseg=3, a_lo_off=NZ)
+            dy = ops.rows_split(d32)
+            g = torch.zeros(1, cin, NZ, dtype=torch.float32, device=dout.device)
+            ops.wgrad_split(y, cin, cin, dZ, NZ, NZ, M, 1, g)
+            dwb = g[0, :, :144].reshape(cin, 3, 3, 16).permute(3, 0, 1, 2).contiguous()
+            return dy, dwb, dbias, None, None, None
         dZ = torch.empty(M, NZ, dtype=torch.bfloat16, device=dout.device)
         ops._count(1)
-        check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), NZ, stream()))
+        check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), NZ, NZ, 0, stream()))
         dbias = dout.sum(0)
         dy = torch.empty(M, cin, dtype=torch.bfloat16, device=dout.device)
         ops.igemm(dZ, M, wz.transpose(1, 2).contiguous(), 1, NZ, cin, dy)          # dy = dZ . Wz

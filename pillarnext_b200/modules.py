@@ -211,7 +211,8 @@ class SparseResNet(nn.Module):
         pyr = getattr(vox, "pyramid", None)
         if pyr is None:
             pyr = vox.pyramid = build_pyramid(vox, self._layer_strides)
-        x = Fn.ToBF16RowsFn.apply(pillar_features, vox.feat_bf16)
+        split = Fn.get_precision() == "split"
+        x = Fn.SplitFn.apply(pillar_features) if split else Fn.ToBF16RowsFn.apply(pillar_features, vox.feat_bf16)
         for s, stage in enumerate(self.blocks):
             x = stage[0].run(x, pyr.entry[s])
             for blk in list(stage)[1:]:
@@ -220,6 +221,8 @@ class SparseResNet(nn.Module):
         x = Fn.bn_act(raw, stats, self.mapping[1], relu=True)
         last = pyr.levels[-1]
         rows = Fn.DensifyFn.apply(x, last)
+        if split:
+            rows = Fn.MergeFn.apply(rows)         # fp32-grade mode: modules exchange fp32 NCHW tensors like the reference
         return rows.view(last.batch, last.V, last.U, self.out_channels).permute(0, 3, 1, 2)
 
 
@@ -267,9 +270,12 @@ class BasicBlock(nn.Module):
 
 
 def _to_rows(x):
-    """NCHW tensor (any dtype/strides) -> (rows bf16 [B*H*W, C], B, H, W); free if already channels-last bf16."""
+    """NCHW tensor (any dtype/strides) -> (rows bf16 [B*H*W, C], B, H, W); free if already channels-last bf16.
+    fp32-grade mode: split rows [B*H*W, 2C] (hi | lo)."""
     B, C, H, W = x.shape
     r = x.permute(0, 2, 3, 1)
+    if Fn.get_precision() == "split":
+        return Fn.SplitFn.apply(r.float().contiguous().view(B * H * W, C)), B, H, W
     if r.dtype != torch.bfloat16:
         r = r.to(torch.bfloat16)
     return r.contiguous().view(B * H * W, C), B, H, W
@@ -293,6 +299,8 @@ class ASPPNeck(nn.Module):
         o = self.pre_conv.block2.run(o, B, H, W)
         cat = Fn.ASPPBranchesFn.apply(o, rows, self.conv1x1.weight, self.weight, B, H, W)
         y = self.post_conv.run(cat, B, H, W)
+        if Fn.get_precision() == "split":
+            y = Fn.MergeFn.apply(y)
         return y.view(B, H, W, C).permute(0, 3, 1, 2)
 
 
@@ -467,6 +475,11 @@ class CenterHead(nn.Module):
         for t, r in enumerate(raws):
             labels = {k: example[k][t].contiguous() for k in ("hm", "anno_box", "ind", "mask", "cat", "gt_boxes")}
             assert labels["hm"].dtype == torch.float32 and labels["ind"].dtype == torch.int64 and labels["mask"].dtype == torch.uint8
+            assert labels["cat"].dtype == torch.int64 and labels["anno_box"].dtype == torch.float32 and labels["gt_boxes"].dtype == torch.float32
+            Mobj = labels["ind"].shape[1]
+            assert tuple(labels["anno_box"].shape) == (r["B"], Mobj, 10) and tuple(labels["gt_boxes"].shape) == (r["B"], Mobj, 7), \
+                "label tensors must be anno_box [B, M, 10] / gt_boxes [B, M, 7] (det3d/datasets/pipelines/assign.py:42-48)"
+            assert tuple(labels["hm"].shape) == (r["B"], r["C"], r["H"], r["W"]), "heat-map label shape does not match the head output"
             osf = self.out_size_factor[t] if self.with_reg_iou else 1
             vs = self.voxel_size if self.with_reg_iou else [1.0, 1.0]
             pr = self.pc_range if self.with_reg_iou else [0.0, 0.0]

@@ -133,9 +133,18 @@ def bn_eval_affine(gamma, beta, rm, rv, eps):
 
 
 # --------------------------------------------------------------------------------- PFN forward
-def pfn_forward(v, w0, bn0, w1, bn1, training, eps=1e-3, momentum=0.01, want_f32=True):
+def _sync_stats(stats, count):
+    """SyncBatchNorm (reference tools/train.py:55-56): batch statistics over the points of ALL ranks.
+    stats fp64 [2C] local sums, count = device int tensor [1] -> (global stats, global count as device int32 [1])."""
+    import torch.distributed as dist
+    pack = torch.cat([stats, count.to(torch.float64)])
+    dist.all_reduce(pack)
+    return pack[:-1], pack[-1:].round().to(torch.int32)
+
+
+def pfn_forward(v, w0, bn0, w1, bn1, training, eps=1e-3, momentum=0.01, want_f32=True, sync=False):
     """P1-P3. bn0/bn1 = (gamma, beta, running_mean, running_var). Returns dict with feat (fp32 [capP,64]),
-    feat_bf16, and everything the backward needs."""
+    feat_bf16, and everything the backward needs.  sync: SyncBatchNorm statistics (all-reduced over the ranks)."""
     L = lib()
     dev = v.points.device
     f32 = dict(dtype=torch.float32, device=dev)
@@ -155,8 +164,12 @@ def pfn_forward(v, w0, bn0, w1, bn1, training, eps=1e-3, momentum=0.01, want_f32
     check(L.pnx_pfn_lin0(ptr(v.points), ptr(v.bucket_pts), ptr(v.pillar_of_point), ptr(v.coords), ptr(mean),
                          ptr(v.counts), v.n, v.min_x, v.min_y, v.vs_x, v.vs_y, ptr(w0), ptr(y0), ptr(s0), tr,
                          stream()))
+    sync = bool(sync and training)
+    s0f, s1f, nv_bn = s0, s1, nv_ptr
+    if sync:
+        s0f, nv_bn = _sync_stats(s0, nv_ptr)
     if training:
-        sc0, sh0, m0, i0 = bn_finalize(s0, 32, nv_ptr, 1, bn0[0], bn0[1], eps, momentum, bn0[2], bn0[3])
+        sc0, sh0, m0, i0 = bn_finalize(s0f, 32, nv_bn, 1, bn0[0], bn0[1], eps, momentum, bn0[2], bn0[3])
     else:
         sc0, sh0 = bn_eval_affine(bn0[0], bn0[1], bn0[2], bn0[3], eps)
         m0 = i0 = None
@@ -164,8 +177,10 @@ def pfn_forward(v, w0, bn0, w1, bn1, training, eps=1e-3, momentum=0.01, want_f32
                          stream()))
     check(L.pnx_pfn_lin1(ptr(y0), ptr(x0max), ptr(v.bucket_pts), ptr(v.pillar_of_point), ptr(v.counts), v.n,
                          ptr(sc0), ptr(sh0), ptr(w1), ptr(y1), ptr(s1), tr, stream()))
+    if sync:
+        s1f, _ = _sync_stats(s1, nv_ptr)
     if training:
-        sc1, sh1, m1, i1 = bn_finalize(s1, 64, nv_ptr, 1, bn1[0], bn1[1], eps, momentum, bn1[2], bn1[3])
+        sc1, sh1, m1, i1 = bn_finalize(s1f, 64, nv_bn, 1, bn1[0], bn1[1], eps, momentum, bn1[2], bn1[3])
     else:
         sc1, sh1 = bn_eval_affine(bn1[0], bn1[1], bn1[2], bn1[3], eps)
         m1 = i1 = None
@@ -174,7 +189,7 @@ def pfn_forward(v, w0, bn0, w1, bn1, training, eps=1e-3, momentum=0.01, want_f32
     check(L.pnx_pfn_max1(ptr(y1), ptr(v.bucket_off), ptr(v.counts), v.cap_p, ptr(sc1), ptr(sh1),
                          ptr(feat) if want_f32 else None, ptr(feat_bf16), stream()))
     out.update(feat=feat, feat_bf16=feat_bf16, mean=mean, y0=y0, y1=y1, x0max=x0max, sc0=sc0, sh0=sh0, sc1=sc1,
-               sh1=sh1, mean0=m0, invstd0=i0, mean1=m1, invstd1=i1)
+               sh1=sh1, mean0=m0, invstd0=i0, mean1=m1, invstd1=i1, bn_count=nv_bn if sync else None)
     return out
 
 
@@ -195,13 +210,32 @@ def pfn_backward(v, fwd, dfeat, w1, gamma0, gamma1):
     dW0 = torch.zeros(32, 10, dtype=torch.float32, device=dev)
     dW1 = torch.zeros(64, 64, dtype=torch.float32, device=dev)
     _count(4)
-    check(lib().pnx_pfn_backward(ptr(v.points), ptr(v.bucket_off), ptr(v.bucket_pts), ptr(v.pillar_of_point),
-                                 ptr(v.coords), ptr(v.counts), v.n, v.cap_p, v.min_x, v.min_y, v.vs_x, v.vs_y,
-                                 ptr(fwd["mean"]), ptr(fwd["y0"]), ptr(fwd["y1"]), ptr(fwd["x0max"]), ptr(fwd["feat"]),
-                                 ptr(dfeat), ptr(w1), ptr(fwd["sc0"]), ptr(fwd["sh0"]), ptr(fwd["mean0"]),
-                                 ptr(fwd["invstd0"]), ptr(gamma0), ptr(fwd["sc1"]), ptr(fwd["sh1"]), ptr(fwd["mean1"]),
-                                 ptr(fwd["invstd1"]), ptr(gamma1), ptr(argq1), ptr(d_x0), ptr(dxm), ptr(red), ptr(dW0),
-                                 ptr(dW1), stream()))
+    bn_count = fwd.get("bn_count")
+
+    def run(phases, red_buf):
+        check(lib().pnx_pfn_backward(ptr(v.points), ptr(v.bucket_off), ptr(v.bucket_pts), ptr(v.pillar_of_point),
+                                     ptr(v.coords), ptr(v.counts), v.n, v.cap_p, v.min_x, v.min_y, v.vs_x, v.vs_y,
+                                     ptr(fwd["mean"]), ptr(fwd["y0"]), ptr(fwd["y1"]), ptr(fwd["x0max"]), ptr(fwd["feat"]),
+                                     ptr(dfeat), ptr(w1), ptr(fwd["sc0"]), ptr(fwd["sh0"]), ptr(fwd["mean0"]),
+                                     ptr(fwd["invstd0"]), ptr(gamma0), ptr(fwd["sc1"]), ptr(fwd["sh1"]), ptr(fwd["mean1"]),
+                                     ptr(fwd["invstd1"]), ptr(gamma1), ptr(argq1), ptr(d_x0), ptr(dxm), ptr(red_buf), ptr(dW0),
+                                     ptr(dW1), phases, ptr(bn_count) if bn_count is not None else None, stream()))
+
+    if bn_count is None:
+        run(0, red)
+    else:
+        # SyncBatchNorm backward: the two per-channel sums of each BN are all-reduced between the phase that produces
+        # them and the phase that applies them; dgamma / dbeta stay local (DDP averages parameter gradients)
+        import torch.distributed as dist
+        glob = torch.zeros_like(red)
+        run(1, red)
+        glob[64:] = red[64:]
+        dist.all_reduce(glob[64:])
+        run(2, glob)
+        run(4, red)
+        glob[:64] = red[:64]
+        dist.all_reduce(glob[:64])
+        run(8, glob)
     r = red.float()
     return dW0, dW1, r[32:64], r[0:32], r[128:192], r[64:128]
 
@@ -306,11 +340,12 @@ def pick_block_n(cout):
 
 
 def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None, dense=None, bias=None, stats=None,
-          stats_mod=None, shuffle=False, relu=False, block_n=None, addend=None):
+          stats_mod=None, shuffle=False, relu=False, block_n=None, addend=None, nseg=1, a_lo_off=0):
     """out[m, :cout] = sum_t A[nbr(m,t)] @ W[t]^T.  w_packed [taps, cout, cin] bf16.
-    dense = (Hout, Wout, Hin, Win, kw, mul, dil, pad) or None."""
+    dense = (Hout, Wout, Hin, Win, kw, mul, dil, pad) or None.
+    nseg > 1: fp32-grade split mode -- A rows are (hi | lo at +a_lo_off) bf16 pairs, w_packed [taps, cout, 2*cin]."""
     assert A.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous()
-    assert tuple(w_packed.shape) == (taps, cout, cin), (tuple(w_packed.shape), (taps, cout, cin))
+    assert tuple(w_packed.shape) == (taps, cout, cin * (2 if nseg > 1 else 1)), (tuple(w_packed.shape), (taps, cout, cin), nseg)
     lda = A.stride(0) if lda is None else lda
     ldc = out.stride(-2) if ldc is None else ldc
     bn = block_n or pick_block_n(cout)
@@ -319,14 +354,15 @@ def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None,
     assert out.dtype in (torch.float32, torch.bfloat16)
     sC = stats.numel() // 2 if stats is not None else 0
     _count(1)
-    with _Timed("igemm", 2.0 * M * taps * cin * cout, 2.0 * M * (cin * min(taps, 2) + cout) + 2.0 * taps * cin * cout,
+    add_f32 = 1 if (addend is not None and addend.dtype == torch.float32) else 0
+    with _Timed("igemm", 2.0 * M * taps * cin * cout * nseg, 2.0 * M * (cin * min(taps, 2) + cout) + 2.0 * taps * cin * cout,
                 "M%d_T%d_K%d_N%d_bn%d%s" % (M, taps, cin, cout, bn, "_tbl" if nbr is not None else ("_dense" if dense else ""))):
       check(lib().pnx_igemm(ptr(A), lda, M, taps, cin, ptr(w_packed), cout, bn, ptr(nbr) if nbr is not None else None,
                           1 if dense else 0, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], ptr(out), ldc, out_fp32,
                           ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None, sC,
                           stats_mod or (sC if sC else 1), 1 if shuffle else 0, 1 if relu else 0,
                           ptr(addend) if addend is not None else None, addend.stride(0) if addend is not None else 0,
-                          sm_count(), stream()))
+                          int(nseg), int(a_lo_off), add_f32, sm_count(), stream()))
     return out
 
 
@@ -436,6 +472,89 @@ def relu_bwd(dy, y, M, C, g, accumulate=False):
     check(lib().pnx_relu_bwd(ptr(dy), dy.stride(0), ptr(y), y.stride(0), M, C, ptr(g), g.stride(0),
                              1 if accumulate else 0, stream()))
     return g
+
+
+# --------------------------------------------------------------------------------- fp32-grade split rows
+# A "split" activation is a bf16 tensor [M, 2C]: hi = bf16(v) in columns [0, C), lo = bf16(v - hi) in [C, 2C)
+# (include/pnx.h, "split rows").  The wrappers take (tensor-or-view, lo offset in elements) per operand.
+def rows_split(x, C=None, out=None, lo=None):
+    """fp32 rows [M, >=C] -> split rows.  out/lo: write into an existing buffer (view) with the lo half at +lo."""
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    M = x.shape[0]
+    C = x.shape[1] if C is None else C
+    if out is None:
+        out = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=x.device)
+        lo = C
+    _count(1)
+    check(lib().pnx_rows_split(ptr(x), x.stride(0), M, C, ptr(out), out.stride(0), int(lo), stream()))
+    return out
+
+
+def rows_merge(x, C, lo, out=None, accumulate=False):
+    """split rows -> fp32 [M, C] (hi + lo)."""
+    M = x.shape[0]
+    if out is None:
+        out = torch.empty(M, C, dtype=torch.float32, device=x.device)
+    _count(1)
+    check(lib().pnx_rows_merge(ptr(x), x.stride(0), int(lo), M, C, ptr(out), out.stride(0), 1 if accumulate else 0, stream()))
+    return out
+
+
+def bn_apply_split(x, M, C, scale, shift, y, y_lo, res=None, res_lo=0, relu=True):
+    _count(1)
+    check(lib().pnx_bn_apply_split(ptr(x), x.stride(0), M, C, ptr(scale), ptr(shift), ptr(res) if res is not None else None,
+                                   res.stride(0) if res is not None else 16, int(res_lo) if res is not None else 16, 1 if relu else 0,
+                                   ptr(y), y.stride(0), int(y_lo), stream()))
+    return y
+
+
+def bn_bwd_reduce_split(dy, dy_lo, y, y_lo, x, M, C, mean, invstd, relu, affine):
+    L = lib()
+    part = torch.empty(L.pnx_bn_bwd_reduce_split_scratch(C), dtype=torch.float64, device=dy.device)
+    red = torch.empty(2 * C, dtype=torch.float64, device=dy.device)
+    fs, fh = affine if affine is not None else (None, None)
+    _count(2)
+    check(L.pnx_bn_bwd_reduce_split(ptr(dy), dy.stride(0), int(dy_lo), ptr(y) if y is not None else None,
+                                    y.stride(0) if y is not None else 16, int(y_lo) if y is not None else 16, ptr(x), x.stride(0), M, C,
+                                    ptr(mean), ptr(invstd), 1 if relu else 0, ptr(fs) if fs is not None else None,
+                                    ptr(fh) if fh is not None else None, ptr(part), ptr(red), stream()))
+    return red
+
+
+def bn_bwd_apply_split(dy, dy_lo, y, y_lo, x, M, C, mean, invstd, gamma, red, count, relu, affine, dx, dx_lo, dres=None, dres_lo=0):
+    fs, fh = affine if affine is not None else (None, None)
+    _count(1)
+    check(lib().pnx_bn_bwd_apply_split(ptr(dy), dy.stride(0), int(dy_lo), ptr(y) if y is not None else None,
+                                       y.stride(0) if y is not None else 16, int(y_lo) if y is not None else 16, ptr(x), x.stride(0), M, C,
+                                       ptr(mean), ptr(invstd), ptr(gamma), ptr(red), float(max(count, 1)), 1 if relu else 0,
+                                       ptr(fs) if fs is not None else None, ptr(fh) if fh is not None else None, ptr(dx), dx.stride(0),
+                                       int(dx_lo), ptr(dres) if dres is not None else None,
+                                       dres.stride(0) if dres is not None else 16, int(dres_lo) if dres is not None else 16, stream()))
+    return dx
+
+
+def add_relu_split(a, a_lo, b, b_lo, M, C, y, y_lo):
+    _count(1)
+    check(lib().pnx_add_relu_split(ptr(a), a.stride(0), int(a_lo), ptr(b), b.stride(0), int(b_lo), M, C, ptr(y), y.stride(0),
+                                   int(y_lo), stream()))
+    return y
+
+
+def relu_bwd_split(dy_f32, y, y_lo, M, C, g, g_lo):
+    _count(1)
+    check(lib().pnx_relu_bwd_split(ptr(dy_f32), dy_f32.stride(0), ptr(y), y.stride(0), int(y_lo), M, C, ptr(g), g.stride(0),
+                                   int(g_lo), stream()))
+    return g
+
+
+def wgrad_split(X, x_lo, x_channels, Y, y_lo, y_channels, M, taps, dW, **kw):
+    """Weight gradient of split operands: hi*hi + lo*hi + hi*lo, three launches accumulating into the same fp32 dW."""
+    Xh, Xl = X[:, :x_channels], X[:, x_lo:x_lo + x_channels]
+    Yh, Yl = Y[:, :y_channels], Y[:, y_lo:y_lo + y_channels]
+    wgrad(Xh, x_channels, Yh, y_channels, M, taps, dW, **kw)
+    wgrad(Xl, x_channels, Yh, y_channels, M, taps, dW, **kw)
+    wgrad(Xh, x_channels, Yl, y_channels, M, taps, dW, **kw)
+    return dW
 
 
 # --------------------------------------------------------------------------------- F1: decode + rotated NMS

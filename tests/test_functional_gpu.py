@@ -248,3 +248,43 @@ def test_fused_center_loss_matches_torch_loss():
         assert torch.allclose(rets[t]["loc_loss_elem"], rets2[t]["loc_loss_elem"], rtol=1e-4, atol=1e-6)
         e = (gf[t] - gt[t]).abs().max().item()
         assert e < 1e-3 * gt[t].abs().max().item(), (t, e, gt[t].abs().max().item())
+
+
+def test_fused_center_loss_matches_oracle_directly():
+    """pnx_center_loss_task/_finalize (the fused CUDA loss + gradient) against oracle.center_loss -- the restatement that
+    is pinned to the reference's own centerhead.py:142-229 / centerloss.py by tests/golden/ref_tiny.npz -- on the same
+    head outputs and labels (NaN velocities, empty tasks included): values 1e-5 relative, d(loss)/d(head output) 1e-4."""
+    from oracle import pillarnext_oracle as O
+    cfg = synth.tiny_config(128, [["car"], ["truck", "construction_vehicle"], ["bus", "trailer"]])
+    torch.manual_seed(1)
+    head = modules.CenterHead(256, cfg["tasks"], cfg["weight"], cfg["code_weights"], cfg["common_heads"], cfg["head_strides"],
+                              with_reg_iou=True, voxel_size=cfg["voxel_size"], pc_range=cfg["pc_range"],
+                              out_size_factor=cfg["out_size_factor"]).cuda().train()
+    ex = synth.make_batch([3, 4], 1000, cfg, n_boxes=30)
+    for key in ("mask",):
+        ex[key][2].zero_()                                     # a task without any object: the "no positives" branch
+    exg = {k: [e.cuda() for e in v] for k, v in ex.items() if isinstance(v, list) and torch.is_tensor(v[0])}
+    preds = head(torch.randn(2, 256, 16, 16, device="cuda"))
+    raws = [p["hm"]._pnx_raw for p in preds]
+    total, rets = head.loss(exg, preds)
+    gf = torch.autograd.grad(total, [r["out"] for r in raws])
+    # the same numbers through the oracle: NCHW fp32 leaves built from the channels-last matrices
+    leaves, preds_o = [], []
+    for r in raws:
+        out4 = r["out"].detach().cpu().view(r["B"], r["H"], r["W"], r["npad"]).clone().requires_grad_()
+        leaves.append(out4)
+        pd, names = {}, [n for n in cfg["common_heads"]] + ["hm"]
+        for n in names:
+            c = r["C"] if n == "hm" else cfg["common_heads"][n][0]
+            pd[n] = out4[..., r["off"][n]:r["off"][n] + c].permute(0, 3, 1, 2)
+        preds_o.append(pd)
+    total_o, rets_o = O.center_loss(ex, preds_o, cfg["weight"], cfg["code_weights"], True, cfg["voxel_size"], cfg["pc_range"],
+                                    cfg["out_size_factor"])
+    go = torch.autograd.grad(total_o, leaves)
+    assert abs(total.item() - total_o.item()) < 1e-5 * abs(total_o.item()), (total.item(), total_o.item())
+    for t in range(len(rets)):
+        for k in ("hm_loss", "loc_loss", "iou_reg_loss", "num_positive"):
+            assert abs(float(rets[t][k]) - float(rets_o[t][k])) < 1e-5 * max(1.0, abs(float(rets_o[t][k]))), (t, k)
+        assert torch.allclose(rets[t]["loc_loss_elem"].cpu(), rets_o[t]["loc_loss_elem"], rtol=1e-4, atol=1e-6)
+        g, o = gf[t].cpu().view_as(go[t]), go[t]
+        assert (g - o).abs().max().item() < 1e-4 * o.abs().max().item(), (t, (g - o).abs().max().item(), o.abs().max().item())

@@ -129,3 +129,52 @@ def test_detector_eval_forward_matches_oracle_predict():
         assert torch.equal(g["label_preds"], w["label_preds"])
         assert torch.allclose(g["scores"], w["scores"], atol=1e-6)
         assert torch.allclose(g["box3d_lidar"], w["box3d_lidar"], atol=1e-5, rtol=1e-6)
+
+
+def test_postprocess_waymo_pre_max_4096():
+    """The reference's Waymo configs use nms_pre_max_size 4096 (configs/experiments/waymo_det_pp18_aspp_iou_car_sp.yaml
+    post_processing): 4096 candidates of one class in one frame go through the mask + on-GPU sweep (removed-set words
+    spread over lanes x 4 slots) and must match the oracle's greedy NMS.  post_max = 4096 so the sweep walks the whole
+    candidate list (about 200 suppressions happen past candidate 2048).  The CPU side prefilters pairs by centre distance
+    (disjoint boxes have IoU exactly 0) before the exact oracle IoU; the seed keeps every evaluated pair 1e-4 away from
+    the threshold."""
+    import numpy as np
+    cfg = _test_cfg()
+    B, H, W, C = 1, 96, 96, 1
+    g = torch.Generator().manual_seed(77)
+    pd = _fake_preds(B, H, W, C, 31)
+    n = H * W
+    pd["hm"] = torch.linspace(-2.0, 3.0, n)[torch.randperm(n, generator=g)].view(B, C, H, W)      # distinct scores
+    pd["dim"] = torch.randn(B, 3, H, W, generator=g) * 0.3 - 1.3                                    # ~0.3 m boxes on 0.3 m cells
+    boxes, hm, iou = P.decode(pd, cfg["out_size_factor"][0], cfg["voxel_size"], cfg["pc_range"])
+    thr = 0.25
+    sc = hm[0, :, 0]
+    pcr = torch.tensor(cfg["post_center_limit_range"])
+    m = (sc > cfg["score_threshold"]) & (boxes[0][:, :3] >= pcr[:3]).all(1) & (boxes[0][:, :3] <= pcr[3:]).all(1)
+    assert int(m.sum()) > 4096, int(m.sum())
+    order = sc[m].sort(descending=True)[1][:4096]
+    assert sc[m][order].unique().numel() == 4096, "tied scores: change the seed"
+    b7 = boxes[0][m][order][:, [0, 1, 2, 3, 4, 5, 8]].contiguous().numpy().astype(np.float32)
+    rad = 0.5 * np.sqrt(b7[:, 3] ** 2 + b7[:, 4] ** 2)
+    removed = np.zeros(len(b7), dtype=bool)
+    keep, late = [], 0
+    for i in range(len(b7)):
+        if removed[i]:
+            continue
+        keep.append(i)
+        d = np.hypot(b7[i + 1:, 0] - b7[i, 0], b7[i + 1:, 1] - b7[i, 1])
+        for j in np.nonzero((d < rad[i + 1:] + rad[i]) & ~removed[i + 1:])[0] + i + 1:
+            v = float(P.iou_bev(b7[i], b7[j]))
+            assert abs(v - thr) > 1e-4, "test input sits on the NMS threshold: change the seed"
+            if v > thr:
+                removed[j] = True
+                late += int(j > 2048)
+    assert late > 50 and 3000 < len(keep) < 4096          # suppressions past word 32 of the removed-set
+    out = to_rows(pd).cuda()
+    det_box, det_score, det_label, cnt = ops.det_postprocess(
+        out, B, H, W, C, OFFS7, cfg["out_size_factor"][0], cfg["voxel_size"], cfg["pc_range"], cfg["score_threshold"],
+        cfg["post_center_limit_range"], [0.0], [thr], 4096, 4096)
+    assert int(cnt[0]) == len(keep), (int(cnt[0]), len(keep))
+    sel = torch.tensor(keep)
+    assert torch.allclose(det_box[0, :len(keep)].cpu(), boxes[0][m][order][sel], atol=1e-5, rtol=1e-6)
+    assert torch.allclose(det_score[0, :len(keep)].cpu(), sc[m][order][sel], atol=1e-6)
