@@ -157,11 +157,14 @@ int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void
               int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
               int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
               double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
-              long long ld_add, int nseg, long long a_lo_off, int addend_fp32, int sm_count, cudaStream_t stream);
-/* nseg > 1 selects the fp32-grade SPLIT mode (see "split rows" below): A rows hold bf16 pairs (hi at column c, lo at
- * column a_lo_off + c), W is packed [taps, Cout, 2*Cin] = [w_hi | w_lo], and the K loop accumulates the segments
- * hi*hi, lo*hi, hi*lo (nseg = 3) [+ lo*lo, nseg = 4] into the same fp32 TMEM accumulator.  addend_fp32 = 1: `addend`
- * is fp32 [M, ld_add] (requires out_fp32).  nseg = 1, a_lo_off = 0, addend_fp32 = 0: the production bf16 path. */
+              long long ld_add, int nseg, long long a_lo_off, long long seg_code, int addend_fp32, int sm_count,
+              cudaStream_t stream);
+/* nseg > 1 selects the fp32-grade SPLIT mode (see "split rows" below): every value is a sum of bf16 PIECES, A rows
+ * hold piece p of channel c at column p*a_lo_off + c, W is packed [taps, Cout, pieces*Cin] = [piece 0 | piece 1 | ..],
+ * and the K loop accumulates nseg (A piece, W piece) segments into the same fp32 TMEM accumulator in the order given
+ * by seg_code (4 bits per segment: (A piece << 2) | W piece; callers put the smallest products first).
+ * addend_fp32 = 1: `addend` is fp32 [M, ld_add] (requires out_fp32).  nseg = 1, seg_code = 0, a_lo_off = 0,
+ * addend_fp32 = 0: the production bf16 path. */
 
 /* ---------------------------------------------------------------- dense 3x3 conv with TMA-folded im2col
  * out[(b,y,x), n] = sum_{r,s<3} sum_c A[(b, y+r-1, x+s-1), c] * W[r*3+s, n, c] (+bias)(relu), zero padding,
@@ -208,13 +211,16 @@ int pnx_relu_bwd(const void* dy, long long lddy, const void* y, long long ldy, l
 
 /* ---------------------------------------------------------------- fp32-grade "split rows" precision mode
  * The reference is fp32 end to end (aspp.py:19-32, centerhead.py:128-136, sparse_conv.py:31-39; no autocast).  In
- * this mode an activation row matrix stores every value as TWO bf16 numbers, hi = bf16(v) at column c and
- * lo = bf16(v - hi) at column lo + c of the same row (~16 mantissa bits); the tensor-core kernels run over the hi/lo
- * segments (pnx_igemm nseg = 3; three pnx_wgrad launches accumulate into the same dW) and raw convolution outputs,
- * BatchNorm arithmetic and gradient sums stay fp32.  The kernels below are the row-wise glue of the mode
+ * this mode an activation row matrix stores every value as P bf16 PIECES (pnx_split_set_pieces: 2 = 16 mantissa
+ * bits, 3 = 24 bits = an exact fp32): piece 0 = bf16(v) at column c, piece q = bf16(v - pieces before) at column
+ * q*lo + c of the same row; the tensor-core kernels run over (piece, piece) segments (pnx_igemm nseg/seg_code; one
+ * pnx_wgrad launch per segment, all accumulating into the same dW) and raw convolution outputs, BatchNorm arithmetic
+ * and gradient sums stay fp32.  The kernels below are the row-wise glue of the mode
  * (x = fp32 rows, everything named res / y / dy / dx / dres / a / b / g = split rows given as (pointer, ld, lo)).
  * pnx_bn_bwd_reduce_split is two-stage with a fixed order (bit-reproducible): `part` = scratch of
  * pnx_bn_bwd_reduce_split_scratch(C) doubles, `red` [2C] is fully written. */
+int pnx_split_set_pieces(int pieces);   /* 2 or 3; process-wide; returns the previous value */
+int pnx_split_get_pieces(void);
 int pnx_rows_split(const float* x, long long ldx, long long M, int C, void* y, long long ldy, long long lo_y,
                    cudaStream_t stream);
 int pnx_rows_merge(const void* x, long long ldx, long long lo_x, long long M, int C, float* y, long long ldy,

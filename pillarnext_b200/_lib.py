@@ -46,7 +46,7 @@ _SIGS = {
     "pnx_sites_coords": [P, P, P, I, I, I, P, I, P],
     "pnx_nbr_table": [P, P, I, P, P, P, I, I, I, I, I, P, P],
     "pnx_scatter_dense": [P, P, P, I, I, I, I, I, P, I, P],
-    "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, P, L, I, L, I, I, P],
+    "pnx_igemm": [P, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, P, L, I, L, L, I, I, P],
     "pnx_conv3x3_win": [P, L, I, I, I, I, P, I, I, P, L, P, P, I, I, I, I, P],
     "pnx_wgrad": [P, L, I, P, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, P, I, P],
     "pnx_bn_apply": [P, L, L, I, P, P, P, L, I, P, L, P],
@@ -56,6 +56,8 @@ _SIGS = {
     "pnx_add_relu": [P, L, P, L, L, I, P, L, P],
     "pnx_relu_bwd": [P, L, P, L, L, I, P, L, I, P],
     # fp32-grade split-rows mode
+    "pnx_split_set_pieces": [I],
+    "pnx_split_get_pieces": [],
     "pnx_rows_split": [P, L, L, I, P, L, L, P],
     "pnx_rows_merge": [P, L, L, L, I, P, L, I, P],
     "pnx_bn_apply_split": [P, L, L, I, P, P, P, L, L, I, P, L, L, P],

@@ -35,10 +35,14 @@ struct IgemmParams {
   int shuffle, relu;
   const __nv_bfloat16* addend;  // optional [M, ld_add] bf16 added before the store (gradient accumulation)
   long long ld_add;
-  // fp32-grade "split" mode: A rows are bf16 pairs (hi at column c, lo at column a_lo_off + c), W rows are
-  // [w_hi(Cin) | w_lo(Cin)]; the K loop runs nseg segments (hi*hi, lo*hi, hi*lo[, lo*lo]) into the same fp32
-  // accumulator, so products carry ~16 mantissa bits.  nseg = 1: plain bf16.
+  // fp32-grade "split" mode: every value is the sum of P bf16 PIECES (P = 2: hi + lo, 16 mantissa bits; P = 3:
+  // hi + mid + lo, 24 bits).  A rows hold piece p of channel c at column p * a_lo_off + c, W rows are
+  // [piece 0 (Cin) | piece 1 (Cin) | ...]; the K loop runs nseg (A piece, W piece) segments into the same fp32
+  // accumulator, the small correction terms FIRST, while the accumulator is small: the tensor core's fp32
+  // accumulation truncates (measured: tools/split_error_probe.py), and adding 2^-9-sized terms to a full-sized
+  // accumulator would lose most of their low bits.  nseg = 1 (piece 0 x piece 0): plain bf16.
   int nseg, a_lo_off;
+  unsigned long long seg_code;  // 4 bits per segment, in execution order: (A piece << 2) | W piece
   const float* addend_f32;      // fp32 addend (split mode: gradients are accumulated in fp32)
 };
 
@@ -160,9 +164,10 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
         for (int kc = 0; kc < num_k; ++kc) {
           const int ccx = kc / p.T, t = kc - ccx * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
           const int seg = ccx / kpt, cc = ccx - seg * kpt;
+          const int wpiece = (int)((p.seg_code >> (4 * seg)) & 3ull);
           pnx::mbar_wait(&empty[stage], phase ^ 1);
           pnx::mbar_arrive_expect_tx(&full[stage], kBBytes);
-          pnx::tma_load_2d(&wmap, &full[stage], sB + (size_t)stage * kBBytes, cc * 64 + (seg >= 2 ? p.Cin : 0), t * p.w_rows_per_tap + n0);
+          pnx::tma_load_2d(&wmap, &full[stage], sB + (size_t)stage * kBBytes, cc * 64 + wpiece * p.Cin, t * p.w_rows_per_tap + n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
         const int h = hs / SPLIT, part = hs - h * SPLIT;
         const int ccx = kc / p.T, t = kc - ccx * p.T;  // chunk outer, tap inner: consecutive stages re-read overlapping rows
         const int seg = ccx / kpt, cc = ccx - seg * kpt;
-        const int acol = cc * 64 + ((seg & 1) ? p.a_lo_off : 0);
+        const int acol = cc * 64 + (int)((p.seg_code >> (4 * seg + 2)) & 3ull) * p.a_lo_off;
         const uint32_t g = g_base + (uint32_t)kc;
         const uint32_t stage = g % (uint32_t)kStages, phase = (g / (uint32_t)kStages) & 1u;
         const int* tbl = s_idx + ((tcount + h) % kTblSlots) * kTbl;
@@ -549,8 +554,8 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
                          int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
                          int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
                          double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
-                         long long ld_add, int nseg, long long a_lo_off, int addend_fp32, int sm_count,
-                         cudaStream_t stream) {
+                         long long ld_add, int nseg, long long a_lo_off, long long seg_code, int addend_fp32,
+                         int sm_count, cudaStream_t stream) {
   PNX_CHECK_ARG(M >= 0, "M");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(taps >= 1 && taps <= 9, "taps in [1,9]");
@@ -579,11 +584,19 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   p.addend_f32 = addend_fp32 ? (const float*)addend : nullptr;
   p.ld_add = ld_add;
   PNX_CHECK_ARG(!(addend && shuffle), "addend is not supported with the pixel-shuffle store");
-  PNX_CHECK_ARG(nseg >= 1 && nseg <= 4, "nseg in [1,4]");
-  PNX_CHECK_ARG(nseg == 1 || (a_lo_off >= Cin && a_lo_off % 64 == 0 && a_lo_off + Cin <= lda), "split mode: a_lo_off");
+  PNX_CHECK_ARG(nseg >= 1 && nseg <= 9, "nseg in [1,9]");
+  int a_pieces = 1, w_pieces = 1;
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    const int ap = (int)((seg_code >> (4 * sgi + 2)) & 3), wp = (int)((seg_code >> (4 * sgi)) & 3);
+    PNX_CHECK_ARG(ap <= 2 && wp <= 2, "segment code: piece index <= 2");
+    if (ap + 1 > a_pieces) a_pieces = ap + 1;
+    if (wp + 1 > w_pieces) w_pieces = wp + 1;
+  }
+  PNX_CHECK_ARG(nseg > 1 || seg_code == 0, "nseg = 1 is the plain bf16 path (segment code 0)");
+  PNX_CHECK_ARG(a_pieces == 1 || (a_lo_off >= Cin && a_lo_off % 64 == 0 && (a_pieces - 1) * a_lo_off + Cin <= lda), "split mode: a_lo_off");
   PNX_CHECK_ARG(!addend_fp32 || out_fp32, "an fp32 addend needs an fp32 output");
-  p.nseg = nseg; p.a_lo_off = (int)a_lo_off;
-  const int wcols = nseg > 1 ? 2 * Cin : Cin;  // split mode: W rows are [w_hi | w_lo]
+  p.nseg = nseg; p.a_lo_off = (int)a_lo_off; p.seg_code = (unsigned long long)seg_code;
+  const int wcols = w_pieces * Cin;  // split mode: W rows are [piece 0 | piece 1 | ...]
   CUtensorMap wmap;
   int rc = pnx_encode_tmap_2d_bf16(&wmap, Wpacked, (uint64_t)taps * Cout, (uint64_t)wcols, (uint64_t)wcols * 2,
                                    (uint32_t)block_n, 64);
@@ -591,7 +604,7 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   // A as a 2-D tensor [rows, Cin] for tile::gather4 (box = one 64-channel row).  The row count only bounds the
   // out-of-range test of the gather (index -1 = absent neighbour = zero fill); valid indices come from the caller.
   CUtensorMap amap;
-  rc = pnx_encode_tmap_gather_bf16(&amap, A, (uint64_t)0x7fffffff, (uint64_t)(nseg > 1 ? a_lo_off + Cin : Cin), (uint64_t)lda * 2);
+  rc = pnx_encode_tmap_gather_bf16(&amap, A, (uint64_t)0x7fffffff, (uint64_t)((a_pieces - 1) * a_lo_off + Cin), (uint64_t)lda * 2);
   if (rc) return rc;
   const int n_blocks = Cout / block_n;
   switch (block_n) {

@@ -28,27 +28,34 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
                     pnx::pack_bf16x2(f[6], f[7]));
 }
 
-struct Rows {  // a split row matrix: hi at p[m*ld + c], lo at p[m*ld + lo + c]
+struct Rows {  // a split row matrix: piece q of channel c at p[m*ld + q*lo + c], value = sum of the pieces
   __nv_bfloat16* p;
   long long ld, lo;
+  int pieces;
 };
 
 __device__ __forceinline__ void load_split8(const Rows& r, long long m, int c0, float (&f)[8]) {
-  float g[8];
-  unpack8(*reinterpret_cast<const uint4*>(r.p + m * r.ld + c0), f);
-  unpack8(*reinterpret_cast<const uint4*>(r.p + m * r.ld + r.lo + c0), g);
+  // smallest piece first: the partial sums are exact in fp32 (pieces are non-overlapping 8-bit windows of one fp32)
+  unpack8(*reinterpret_cast<const uint4*>(r.p + m * r.ld + (r.pieces - 1) * r.lo + c0), f);
+  for (int q = r.pieces - 2; q >= 0; --q) {
+    float g[8];
+    unpack8(*reinterpret_cast<const uint4*>(r.p + m * r.ld + q * r.lo + c0), g);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) f[k] += g[k];
+    for (int k = 0; k < 8; ++k) f[k] += g[k];
+  }
 }
 __device__ __forceinline__ void store_split8(const Rows& r, long long m, int c0, const float (&f)[8]) {
-  float hi[8], lo[8];
+  float rem[8], pc[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    hi[k] = pnx::bf16_round(f[k]);
-    lo[k] = f[k] - hi[k];
+  for (int k = 0; k < 8; ++k) rem[k] = f[k];
+  for (int q = 0; q < r.pieces; ++q) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      pc[k] = pnx::bf16_round(rem[k]);
+      rem[k] -= pc[k];            // exact: the residual of a bf16 rounding is representable in fp32
+    }
+    *reinterpret_cast<uint4*>(r.p + m * r.ld + q * r.lo + c0) = pack8(pc);
   }
-  *reinterpret_cast<uint4*>(r.p + m * r.ld + c0) = pack8(hi);
-  *reinterpret_cast<uint4*>(r.p + m * r.ld + r.lo + c0) = pack8(lo);
 }
 __device__ __forceinline__ void load_f32x8(const float* p, float (&f)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -236,13 +243,23 @@ inline int ew_blocks(long long total) {
   const long long cap = 148LL * 16;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
-inline Rows rows(const void* p, long long ld, long long lo) { return Rows{(__nv_bfloat16*)p, ld, lo}; }
+int g_pieces = 2;  // pieces per value of every split row matrix handled by this library instance (pnx_split_set_pieces)
+inline Rows rows(const void* p, long long ld, long long lo) { return Rows{(__nv_bfloat16*)p, ld, lo, g_pieces}; }
 inline bool rows_ok(const void* p, long long ld, long long lo, int C) {
-  return !p || (ld % 8 == 0 && lo % 8 == 0 && lo >= C && (reinterpret_cast<uintptr_t>(p) & 15) == 0);
+  return !p || (ld % 8 == 0 && lo % 8 == 0 && lo >= C && (g_pieces - 1) * lo + C <= ld && (reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
 constexpr int kRedBlocks = 296;
 
 }  // namespace
+
+// Pieces per value (2 = hi+lo, 16 mantissa bits; 3 = hi+mid+lo, 24 bits) of the split row matrices handled by the
+// pnx_*_split entry points and pnx_tap_scatter.  Process-wide setting of the parity mode; returns the previous value.
+extern "C" int pnx_split_set_pieces(int pieces) {
+  const int prev = g_pieces;
+  if (pieces == 2 || pieces == 3) g_pieces = pieces;
+  return prev;
+}
+extern "C" int pnx_split_get_pieces(void) { return g_pieces; }
 
 extern "C" int pnx_rows_split(const float* x, long long ldx, long long M, int C, void* y, long long ldy, long long lo_y,
                               cudaStream_t stream) {

@@ -40,14 +40,14 @@ __global__ void tap_gather_sum_kernel(const float* __restrict__ Z, long long ldz
 // dZ [M, ldz] bf16 (columns >= 144 zero) ; dout [M,16] fp32 ; one thread = one pixel x one 16-byte chunk of dZ
 // lo_off > 0 (fp32-grade split mode): dZ rows are [hi(nz) | lo(nz)] pairs, lo = bf16(v - hi) at column lo_off + c
 __global__ void tap_scatter_kernel(const float* __restrict__ dout, int B, int H, int W, __nv_bfloat16* __restrict__ dZ,
-                                   long long ldz, int nz, long long lo_off) {
+                                   long long ldz, int nz, long long lo_off, int pieces) {
   const int chunks = nz >> 3;  // 8 bf16 per chunk
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long M = (long long)B * H * W;
   const long long m = t / chunks;
   const int c = (int)(t - m * chunks);
   if (m >= M) return;
-  uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = make_uint4(0u, 0u, 0u, 0u);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = make_uint4(0u, 0u, 0u, 0u), ol2 = make_uint4(0u, 0u, 0u, 0u);
   const int tap = c >> 1, half = c & 1;  // chunk c covers columns c*8 .. c*8+7 = tap (c/2), outputs half*8 ..
   if (tap < 9) {
     const int hw = H * W;
@@ -63,16 +63,22 @@ __global__ void tap_scatter_kernel(const float* __restrict__ dout, int B, int H,
                      pnx::pack_bf16x2(bq.z, bq.w));
       if (lo_off > 0) {
         const float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
-        float l[8];
+        float l[8], l2[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) l[k] = v[k] - pnx::bf16_round(v[k]);
+        for (int k = 0; k < 8; ++k) {
+          l[k] = v[k] - pnx::bf16_round(v[k]);
+          l2[k] = l[k] - pnx::bf16_round(l[k]);
+        }
         ol = make_uint4(pnx::pack_bf16x2(l[0], l[1]), pnx::pack_bf16x2(l[2], l[3]), pnx::pack_bf16x2(l[4], l[5]),
                         pnx::pack_bf16x2(l[6], l[7]));
+        ol2 = make_uint4(pnx::pack_bf16x2(l2[0], l2[1]), pnx::pack_bf16x2(l2[2], l2[3]), pnx::pack_bf16x2(l2[4], l2[5]),
+                         pnx::pack_bf16x2(l2[6], l2[7]));
       }
     }
   }
   *reinterpret_cast<uint4*>(dZ + m * ldz + c * 8) = o;
   if (lo_off > 0) *reinterpret_cast<uint4*>(dZ + m * ldz + lo_off + c * 8) = ol;
+  if (lo_off > 0 && pieces > 2) *reinterpret_cast<uint4*>(dZ + m * ldz + 2 * lo_off + c * 8) = ol2;
 }
 
 }  // namespace
@@ -87,13 +93,16 @@ extern "C" int pnx_tap_gather_sum(const float* Z, long long ldz, const float* bi
   return PNX_OK;
 }
 
+extern "C" int pnx_split_get_pieces(void);
+
 extern "C" int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, int nz, long long lo_off,
                                cudaStream_t stream) {
   PNX_CHECK_ARG(nz >= 144 && nz % 8 == 0 && ldz >= nz && ldz % 8 == 0, "nz/ldz");
-  PNX_CHECK_ARG(lo_off == 0 || (lo_off >= nz && lo_off + nz <= ldz && lo_off % 8 == 0), "lo_off");
+  const int pieces = lo_off > 0 ? pnx_split_get_pieces() : 1;
+  PNX_CHECK_ARG(lo_off == 0 || (lo_off >= nz && (pieces - 1) * lo_off + nz <= ldz && lo_off % 8 == 0), "lo_off");
   const long long threads = (long long)B * H * W * (nz / 8);
   if (threads == 0) return PNX_OK;
-  tap_scatter_kernel<<<pnx_cdiv(threads, 256), 256, 0, stream>>>(dout, B, H, W, (__nv_bfloat16*)dZ, ldz, nz, lo_off);
+  tap_scatter_kernel<<<pnx_cdiv(threads, 256), 256, 0, stream>>>(dout, B, H, W, (__nv_bfloat16*)dZ, ldz, nz, lo_off, pieces);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }

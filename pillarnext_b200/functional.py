@@ -20,10 +20,15 @@ from . import ops
 _PRECISION = "bf16"
 
 
+PIECES = 3   # bf16 pieces per value in "split" mode: 2 = 16 mantissa bits, 3 = 24 bits (an exact fp32)
+
+
 def set_precision(mode):
     global _PRECISION
     assert mode in ("bf16", "split")
     prev, _PRECISION = _PRECISION, mode
+    if mode == "split":
+        ops.split_pieces(PIECES)
     return prev
 
 
@@ -48,11 +53,11 @@ def _split():
     return _PRECISION == "split"
 
 
-def _to_hilo(p):
-    """fp32 packed weights [..., K] -> bf16 [..., 2K] = [hi | lo]."""
-    hi = p.to(torch.bfloat16)
-    lo = (p - hi.float()).to(torch.bfloat16)
-    return torch.cat([hi, lo], -1).contiguous()
+def _P():
+    return ops.split_pieces()
+
+
+_to_hilo = ops.to_pieces    # fp32 packed weights [..., K] -> bf16 [..., P*K] = [piece 0 | piece 1 | ...]
 
 
 # ------------------------------------------------------------------------------------------- weights
@@ -115,7 +120,7 @@ def packed(w, layout, which, flip=False, split=False):
     if not isinstance(w, torch.nn.Parameter):
         with torch.no_grad():
             return layout.pack_fwd(w, split) if which == "fwd" else layout.pack_dgrad(w, flip, split)
-    key = (id(w), which, flip, layout.kind, split)
+    key = (id(w), which, flip, layout.kind, _P() if split else 0)
     ent = _pack_cache.get(key)
     ver = w._version
     if ent is not None and ent[0] == ver and ent[1]() is w and ent[3] == w.data_ptr():
@@ -177,13 +182,13 @@ class ConvFn(torch.autograd.Function):
         out_c = cout
         if split:
             out_fp32 = True      # raw convolution outputs stay fp32 in the fp32-grade mode
-            assert not relu and x.shape[1] % 2 == 0 and x.shape[1] // 2 >= cin
+            assert not relu and x.shape[1] % _P() == 0 and x.shape[1] // _P() >= cin
         out = torch.empty(rows, out_c, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
         stats = torch.zeros(2 * cout if want_stats else 0, dtype=torch.float64, device=x.device)
         if split:
             ops.igemm(x, spec.M_out, wp, wp.shape[0], cin, n_cols, out, lda=x.stride(0), ldc=out_c, nbr=spec.nbr,
                       dense=spec.dense, bias=bias, stats=stats if want_stats else None,
-                      stats_mod=cout if want_stats else None, shuffle=spec.shuffle, nseg=3, a_lo_off=x.shape[1] // 2)
+                      stats_mod=cout if want_stats else None, shuffle=spec.shuffle, segs=ops.split_segments(), a_lo_off=x.shape[1] // _P())
         elif layout.kind == "dense" and spec.nbr is None and ops.win_eligible(spec.dense, n_cols, cin, out_fp32, spec.shuffle):
             H_, W_ = spec.dense[0], spec.dense[1]
             ops.conv3x3_win(x, spec.M_out // (H_ * W_), H_, W_, wp, cin, n_cols, out, bias=bias,
@@ -208,18 +213,18 @@ class ConvFn(torch.autograd.Function):
         spec, layout = ctx.spec, ctx.layout
         cin, cout, shape = ctx.dims
         rows = dout.shape[0]
-        assert dout.dtype == torch.bfloat16 and dout.shape[1] == 2 * cout and cout % 64 == 0, "split mode: gradient rows [M, 2*Cout]"
-        dy = dout.contiguous()
-        xlo = x.shape[1] // 2
+        assert dout.dtype == torch.float32 and dout.shape[1] == cout and cout % 64 == 0, "split mode: fp32 gradient rows [M, Cout]"
+        dy = ops.rows_split(dout.contiguous())                          # the conv output is fp32, so is its gradient
+        xlo = x.shape[1] // _P()
         dbias = None
         if ctx.has_bias:
             dbias = torch.zeros(cout, dtype=torch.float32, device=dy.device) if ctx.bias_feeds_bn else \
-                ops.rows_merge(dy, cout, cout).sum(0)
+                dout.sum(0)
         dx = None
         if ctx.needs_input_grad[0]:
-            wd = packed(w, layout, "dgrad", spec.d_flip, split=True)        # [taps_d, Cin, 2*Cout]
+            wd = packed(w, layout, "dgrad", spec.d_flip, split=True)        # [taps_d, Cin, P*Cout]
             d32 = torch.empty(spec.M_in, cin, dtype=torch.float32, device=dy.device)
-            ops.igemm(dy, spec.M_in, wd, wd.shape[0], cout, cin, d32, nbr=spec.d_nbr, dense=spec.d_dense, nseg=3, a_lo_off=cout)
+            ops.igemm(dy, spec.M_in, wd, wd.shape[0], cout, cin, d32, nbr=spec.d_nbr, dense=spec.d_dense, segs=ops.split_segments(), a_lo_off=cout)
             dx = torch.zeros(x.shape[0], x.shape[1], dtype=torch.bfloat16, device=dy.device) if xlo != cin else \
                 torch.empty(x.shape[0], x.shape[1], dtype=torch.bfloat16, device=dy.device)
             ops.rows_split(d32, cin, out=dx, lo=xlo)
@@ -331,7 +336,7 @@ class BNActFn(torch.autograd.Function):
             mean = invstd = None
         ctx.split = x_raw.dtype == torch.float32
         if ctx.split:            # fp32-grade mode: fp32 raw conv output -> split rows
-            y = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=x_raw.device)
+            y = torch.empty(M, _P() * C, dtype=torch.bfloat16, device=x_raw.device)
             ops.bn_apply_split(x_raw, M, C, scale, shift, y, C, res=residual, res_lo=C, relu=relu)
         else:
             y = torch.empty(M, C, dtype=torch.bfloat16, device=x_raw.device)
@@ -345,17 +350,19 @@ class BNActFn(torch.autograd.Function):
         x_raw, y, gamma, mean, invstd, scale, shift = ctx.saved_tensors
         M, C = x_raw.shape
         dy = dy.contiguous()
-        assert dy.shape[1] == 2 * C
+        P = _P()
+        assert dy.shape[1] == P * C
         ysrc = y if ctx.has_res else None
         red = ops.bn_bwd_reduce_split(dy, C, ysrc, C, x_raw, M, C, mean, invstd, ctx.relu, (scale, shift))
         local = red
         if ctx.sync:
             red = red.clone()
             dist.all_reduce(red)
-        dx = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=dy.device)
-        dres = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=dy.device) if ctx.has_res else None
+        dxs = torch.empty(M, P * C, dtype=torch.bfloat16, device=dy.device)
+        dres = torch.empty(M, P * C, dtype=torch.bfloat16, device=dy.device) if ctx.has_res else None
         ops.bn_bwd_apply_split(dy, C, ysrc, C, x_raw, M, C, mean, invstd, gamma, red, ctx.count, ctx.relu, (scale, shift),
-                               dx, C, dres=dres, dres_lo=C)
+                               dxs, C, dres=dres, dres_lo=C)
+        dx = ops.rows_merge(dxs, C, C)          # x_raw is an fp32 [M, C] tensor: its gradient has the same shape / dtype
         r = local.float()
         return dx, None, r[C:], r[:C], dres, None, None, None
 
@@ -398,7 +405,7 @@ def bn_act(x_raw, stats, bn, relu=True, residual=None, count=None):
 
 # ------------------------------------------------------------------------------------------- fp32 <-> split rows
 class SplitFn(torch.autograd.Function):
-    """fp32 rows [M, C] -> split rows [M, 2C] (fp32-grade mode); backward merges the gradient halves."""
+    """fp32 rows [M, C] -> split rows [M, P*C] (fp32-grade mode); backward merges the gradient pieces."""
 
     @staticmethod
     def forward(ctx, x):
@@ -415,12 +422,43 @@ class MergeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
-        C = x.shape[1] // 2
+        C = x.shape[1] // _P()
         return ops.rows_merge(x.contiguous(), C, C)
 
     @staticmethod
     def backward(ctx, d):
         return ops.rows_split(d.contiguous())
+
+
+class FanOutFn(torch.autograd.Function):
+    """A split activation with several consumers: autograd would add the consumers' gradients piece by piece in bf16
+    (each piece sum rounded to 8 bits -- bf16-level error at every residual junction); this node hands every consumer
+    its own copy and accumulates the incoming gradients in fp32 before splitting the sum again."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.C = x.shape[1] // _P()
+        return tuple(x.clone() for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *ds):
+        acc = None
+        for d in ds:
+            if d is None:
+                continue
+            d = d.contiguous()
+            if acc is None:
+                acc = ops.rows_merge(d, ctx.C, ctx.C)
+            else:
+                ops.rows_merge(d, ctx.C, ctx.C, out=acc, accumulate=True)
+        return (ops.rows_split(acc) if acc is not None else None), None
+
+
+def fanout(x, n=2):
+    """n handles of an activation that has n consumers (identity in the bf16 mode, FanOutFn in the split mode)."""
+    if _split() and torch.is_grad_enabled() and x.requires_grad:
+        return FanOutFn.apply(x, n)
+    return (x,) * n
 
 
 # ------------------------------------------------------------------------------------------- dense()
@@ -454,18 +492,18 @@ class ASPPBranchesFn(torch.autograd.Function):
 
     @staticmethod
     def _forward_split(ctx, o, idt, w1x1, wshared, B, H, W):
-        """fp32-grade mode: cat buffer [M, 12C] = six hi slots then six lo slots (a split matrix with lo = 6C)."""
-        M, C = o.shape[0], o.shape[1] // 2
-        C6, ld = 6 * C, 12 * C
+        """fp32-grade mode: cat buffer [M, P*6C] = six piece-0 slots, six piece-1 slots, ... (a split matrix, lo = 6C)."""
+        M, C = o.shape[0], o.shape[1] // _P()
+        C6, ld = 6 * C, _P() * 6 * C
         cat_buf = torch.empty(M, ld, dtype=torch.bfloat16, device=o.device)
         l = WLayout("dense")
         ops.add_relu_split(o, C, idt, C, M, C, cat_buf, C6)
         tmp = torch.empty(M, C, dtype=torch.float32, device=o.device)
-        ops.igemm(cat_buf, M, packed(w1x1, l, "fwd", split=True), 1, C, C, tmp, lda=ld, nseg=3, a_lo_off=C6)
+        ops.igemm(cat_buf, M, packed(w1x1, l, "fwd", split=True), 1, C, C, tmp, lda=ld, segs=ops.split_segments(), a_lo_off=C6)
         ops.rows_split(tmp, C, out=cat_buf[:, C:], lo=C6)
         wp = packed(wshared, l, "fwd", split=True)
         for j, d in enumerate(ASPPBranchesFn.DILS):
-            ops.igemm(cat_buf, M, wp, 9, C, C, tmp, lda=ld, dense=(H, W, H, W, 3, 1, d, d), nseg=3, a_lo_off=C6)
+            ops.igemm(cat_buf, M, wp, 9, C, C, tmp, lda=ld, dense=(H, W, H, W, 3, 1, d, d), segs=ops.split_segments(), a_lo_off=C6)
             ops.rows_split(tmp, C, out=cat_buf[:, (2 + j) * C:], lo=C6)
         ctx.save_for_backward(cat_buf, w1x1, wshared)
         ctx.geo = (B, H, W, C)
@@ -477,23 +515,23 @@ class ASPPBranchesFn(torch.autograd.Function):
         cat_buf, w1x1, wshared = ctx.saved_tensors
         B, H, W, C = ctx.geo
         M = cat_buf.shape[0]
-        C6, ld = 6 * C, 12 * C
+        C6, ld = 6 * C, _P() * 6 * C
         l = WLayout("dense")
         dcat = dcat.contiguous()
         dx = ops.rows_merge(dcat, C, C6)                                   # fp32 accumulator of the five branches
         nxt = torch.empty_like(dx)
-        ops.igemm(dcat[:, C:], M, packed(w1x1, l, "dgrad", True, split=True), 1, C, C, nxt, lda=ld, addend=dx, nseg=3, a_lo_off=C6)
+        ops.igemm(dcat[:, C:], M, packed(w1x1, l, "dgrad", True, split=True), 1, C, C, nxt, lda=ld, addend=dx, segs=ops.split_segments(), a_lo_off=C6)
         dx, nxt = nxt, dx
         wd = packed(wshared, l, "dgrad", True, split=True)
         for j, d in enumerate(ASPPBranchesFn.DILS):
-            ops.igemm(dcat[:, (2 + j) * C:], M, wd, 9, C, C, nxt, lda=ld, dense=(H, W, H, W, 3, 1, d, d), addend=dx, nseg=3, a_lo_off=C6)
+            ops.igemm(dcat[:, (2 + j) * C:], M, wd, 9, C, C, nxt, lda=ld, dense=(H, W, H, W, 3, 1, d, d), addend=dx, segs=ops.split_segments(), a_lo_off=C6)
             dx, nxt = nxt, dx
         g1 = torch.zeros(1, C, C, dtype=torch.float32, device=dcat.device)
         ops.wgrad_split(dcat[:, C:], C6, C, cat_buf, C6, C, M, 1, g1)
         gs = torch.zeros(9, C, C, dtype=torch.float32, device=dcat.device)
         for j, d in enumerate(ASPPBranchesFn.DILS):
             ops.wgrad_split(dcat[:, (2 + j) * C:], C6, C, cat_buf, C6, C, M, 9, gs, dense=(H, W, H, W, 3, 1, d, d))
-        g = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=dcat.device)
+        g = torch.empty(M, _P() * C, dtype=torch.bfloat16, device=dcat.device)
         ops.relu_bwd_split(dx, cat_buf, C6, M, C, g, C)
         return g, g, l.unpack_grad(g1, tuple(w1x1.shape)), l.unpack_grad(gs, tuple(wshared.shape)), None, None, None
 
@@ -637,14 +675,14 @@ class HeadFinalConvFn(torch.autograd.Function):
     def forward(ctx, y, wb, bias, B, H, W):
         from ._lib import check, lib, ptr, stream
         split = _split()
-        M, cin = y.shape[0], y.shape[1] // (2 if split else 1)
+        M, cin = y.shape[0], y.shape[1] // (_P() if split else 1)
         assert wb.shape[0] == 16 and wb.shape[2] == 3
         with torch.no_grad():
             wz = torch.zeros(1, HeadFinalConvFn.NZ, cin, dtype=torch.float32, device=y.device)
             wz[0, :144] = wb.permute(2, 3, 0, 1).reshape(144, cin)                          # row = tap*16 + j
             wz = _to_hilo(wz) if split else wz.to(torch.bfloat16)
         Z = torch.empty(M, HeadFinalConvFn.NZ, dtype=torch.float32, device=y.device)
-        ops.igemm(y, M, wz, 1, cin, HeadFinalConvFn.NZ, Z, block_n=192, nseg=3 if split else 1, a_lo_off=cin if split else 0)
+        ops.igemm(y, M, wz, 1, cin, HeadFinalConvFn.NZ, Z, block_n=192, segs=ops.split_segments() if split else None, a_lo_off=cin if split else 0)
         ctx.split = split
         out = torch.empty(M, 16, dtype=torch.float32, device=y.device)
         ops._count(1)
@@ -661,13 +699,14 @@ class HeadFinalConvFn(torch.autograd.Function):
         M, NZ = y.shape[0], HeadFinalConvFn.NZ
         dout = dout.contiguous().float()
         if ctx.split:
-            dZ = torch.empty(M, 2 * NZ, dtype=torch.bfloat16, device=dout.device)
+            P = _P()
+            dZ = torch.empty(M, P * NZ, dtype=torch.bfloat16, device=dout.device)
             ops._count(1)
-            check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), 2 * NZ, NZ, NZ, stream()))
+            check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), P * NZ, NZ, NZ, stream()))
             dbias = dout.sum(0)
-            wzf = wz[0, :, :cin].float() + wz[0, :, cin:].float()                           # [NZ, cin] (hi + lo)
+            wzf = sum(wz[0, :, q * cin:(q + 1) * cin].float() for q in reversed(range(P)))  # [NZ, cin] (sum of the pieces)
             d32 = torch.empty(M, cin, dtype=torch.float32, device=dout.device)
-            ops.igemm(dZ, M, _to_hilo(wzf.t().contiguous().unsqueeze(0)), 1, NZ, cin, d32, nseg=3, a_lo_off=NZ)
+            ops.igemm(dZ, M, _to_hilo(wzf.t().contiguous().unsqueeze(0)), 1, NZ, cin, d32, segs=ops.split_segments(), a_lo_off=NZ)
             dy = ops.rows_split(d32)
             g = torch.zeros(1, cin, NZ, dtype=torch.float32, device=dout.device)
             ops.wgrad_split(y, cin, cin, dZ, NZ, NZ, M, 1, g)

@@ -166,9 +166,10 @@ class SparseBasicBlock(nn.Module):
         self.act2 = nn.ReLU()
 
     def run(self, x, spec):
+        x, idt = Fn.fanout(x)
         out = self.block1.run(x, spec)
         raw, stats = Fn.conv(out, self.conv2.weight, None, spec, Fn.WLayout("sp"), want_stats=True)
-        return Fn.bn_act(raw, stats, self.norm2, relu=True, residual=x)      # relu(bn(conv) + identity)
+        return Fn.bn_act(raw, stats, self.norm2, relu=True, residual=idt)    # relu(bn(conv) + identity)
 
 
 class _Stage(nn.Sequential):
@@ -295,9 +296,10 @@ class ASPPNeck(nn.Module):
         _require_cuda(x, "ASPPNeck")
         rows, B, H, W = _to_rows(x)
         C = self.in_channels
+        rows, idt = Fn.fanout(rows)
         o = self.pre_conv.block1.run(rows, B, H, W)
         o = self.pre_conv.block2.run(o, B, H, W)
-        cat = Fn.ASPPBranchesFn.apply(o, rows, self.conv1x1.weight, self.weight, B, H, W)
+        cat = Fn.ASPPBranchesFn.apply(o, idt, self.conv1x1.weight, self.weight, B, H, W)
         y = self.post_conv.run(cat, B, H, W)
         if Fn.get_precision() == "split":
             y = Fn.MergeFn.apply(y)
@@ -443,7 +445,7 @@ class CenterHead(nn.Module):
         raw, stats = Fn.conv(rows, self.shared_conv[0].weight, self.shared_conv[0].bias, Fn.dense_spec(B, H, W, 3),
                              Fn.WLayout("dense"), want_stats=True, bias_feeds_bn=self.training)
         y = Fn.bn_act(raw, stats, self.shared_conv[1], relu=True)
-        return [task.run(y, B, H, W) for task in self.tasks]
+        return [task.run(yt, B, H, W) for task, yt in zip(self.tasks, Fn.fanout(y, len(self.tasks)))]
 
     def loss(self, example, preds_dicts, **kwargs):
         """centerhead.py:142-229, including the Waymo `iou` head branch (:210-215) on the fused-head path."""

@@ -340,12 +340,19 @@ def pick_block_n(cout):
 
 
 def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None, dense=None, bias=None, stats=None,
-          stats_mod=None, shuffle=False, relu=False, block_n=None, addend=None, nseg=1, a_lo_off=0):
+          stats_mod=None, shuffle=False, relu=False, block_n=None, addend=None, segs=None, a_lo_off=0):
     """out[m, :cout] = sum_t A[nbr(m,t)] @ W[t]^T.  w_packed [taps, cout, cin] bf16.
     dense = (Hout, Wout, Hin, Win, kw, mul, dil, pad) or None.
-    nseg > 1: fp32-grade split mode -- A rows are (hi | lo at +a_lo_off) bf16 pairs, w_packed [taps, cout, 2*cin]."""
+    segs: fp32-grade split mode -- list of (A piece, W piece) K segments in execution order; A rows hold piece p at
+    column p*a_lo_off + c, w_packed is [taps, cout, pieces*cin] (see include/pnx.h "split rows")."""
     assert A.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous()
-    assert tuple(w_packed.shape) == (taps, cout, cin * (2 if nseg > 1 else 1)), (tuple(w_packed.shape), (taps, cout, cin), nseg)
+    nseg, seg_code = 1, 0
+    if segs:
+        nseg = len(segs)
+        for i, (ap, wp) in enumerate(segs):
+            seg_code |= ((ap << 2) | wp) << (4 * i)
+    w_pieces = (max(wp for _, wp in segs) + 1) if segs else 1
+    assert tuple(w_packed.shape) == (taps, cout, cin * w_pieces), (tuple(w_packed.shape), (taps, cout, cin), segs)
     lda = A.stride(0) if lda is None else lda
     ldc = out.stride(-2) if ldc is None else ldc
     bn = block_n or pick_block_n(cout)
@@ -362,7 +369,7 @@ def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None,
                           ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None, sC,
                           stats_mod or (sC if sC else 1), 1 if shuffle else 0, 1 if relu else 0,
                           ptr(addend) if addend is not None else None, addend.stride(0) if addend is not None else 0,
-                          int(nseg), int(a_lo_off), add_f32, sm_count(), stream()))
+                          int(nseg), int(a_lo_off), int(seg_code), add_f32, sm_count(), stream()))
     return out
 
 
@@ -475,15 +482,40 @@ def relu_bwd(dy, y, M, C, g, accumulate=False):
 
 
 # --------------------------------------------------------------------------------- fp32-grade split rows
-# A "split" activation is a bf16 tensor [M, 2C]: hi = bf16(v) in columns [0, C), lo = bf16(v - hi) in [C, 2C)
-# (include/pnx.h, "split rows").  The wrappers take (tensor-or-view, lo offset in elements) per operand.
+# A "split" activation is a bf16 tensor [M, P*C]: piece 0 = bf16(v) in columns [0, C), piece 1 = bf16(v - piece 0) in
+# [C, 2C), ... (include/pnx.h, "split rows"; P = split_pieces(), 2 or 3).  The wrappers take (tensor-or-view, piece
+# offset in elements) per operand.
+SEGMENTS = {2: [(1, 1), (1, 0), (0, 1), (0, 0)],                       # (A piece, W piece), smallest products first
+            3: [(2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0)]}       # 2^-16-sized terms, 2^-8-sized terms, hi*hi
+
+
+def split_pieces(set_to=None):
+    if set_to is not None:
+        lib().pnx_split_set_pieces(int(set_to))
+    return lib().pnx_split_get_pieces()
+
+
+def split_segments():
+    return SEGMENTS[split_pieces()]
+
+
+def to_pieces(p):
+    """fp32 [..., K] -> bf16 [..., P*K] = [piece 0 | piece 1 | ...] (packed weights of the split mode)."""
+    out, rem = [], p.float()
+    for _ in range(split_pieces()):
+        q = rem.to(torch.bfloat16)
+        out.append(q)
+        rem = rem - q.float()
+    return torch.cat(out, -1).contiguous()
+
+
 def rows_split(x, C=None, out=None, lo=None):
     """fp32 rows [M, >=C] -> split rows.  out/lo: write into an existing buffer (view) with the lo half at +lo."""
     assert x.dtype == torch.float32 and x.stride(-1) == 1
     M = x.shape[0]
     C = x.shape[1] if C is None else C
     if out is None:
-        out = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=x.device)
+        out = torch.empty(M, split_pieces() * C, dtype=torch.bfloat16, device=x.device)
         lo = C
     _count(1)
     check(lib().pnx_rows_split(ptr(x), x.stride(0), M, C, ptr(out), out.stride(0), int(lo), stream()))
@@ -548,12 +580,10 @@ def relu_bwd_split(dy_f32, y, y_lo, M, C, g, g_lo):
 
 
 def wgrad_split(X, x_lo, x_channels, Y, y_lo, y_channels, M, taps, dW, **kw):
-    """Weight gradient of split operands: hi*hi + lo*hi + hi*lo, three launches accumulating into the same fp32 dW."""
-    Xh, Xl = X[:, :x_channels], X[:, x_lo:x_lo + x_channels]
-    Yh, Yl = Y[:, :y_channels], Y[:, y_lo:y_lo + y_channels]
-    wgrad(Xh, x_channels, Yh, y_channels, M, taps, dW, **kw)
-    wgrad(Xl, x_channels, Yh, y_channels, M, taps, dW, **kw)
-    wgrad(Xh, x_channels, Yl, y_channels, M, taps, dW, **kw)
+    """Weight gradient of split operands: one launch per (X piece, Y piece) segment, smallest products first, all
+    accumulating (fp32 red.global.add) into the same dW."""
+    for xp, yp in split_segments():
+        wgrad(X[:, xp * x_lo:xp * x_lo + x_channels], x_channels, Y[:, yp * y_lo:yp * y_lo + y_channels], y_channels, M, taps, dW, **kw)
     return dW
 
 

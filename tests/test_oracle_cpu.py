@@ -140,6 +140,12 @@ def test_abi_library_loads_and_exports_header_symbols():
         assert hasattr(l, name), name
     l.pnx_abi_version.restype = ctypes.c_int
     assert l.pnx_abi_version() == 1
+    # arity: every declaration's parameter count equals the ctypes binding's (a mismatch shifts arguments silently)
+    code = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    for name, params in re.findall(r"\b(pnx_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", code):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib._SIGS[name]), (name, n, len(_lib._SIGS[name]))
 
 
 def test_product_never_imports_oracle():
