@@ -27,8 +27,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec PillarNeXt-B fwd+bwd"
-WORKLOAD = "PillarNeXt-B nuScenes-shape synthetic, bf16, fwd+loss+bwd+AdamW (BASELINE.json configs[1]): " \
-           "%d pts/frame, 0.075 m pillars, 1344^2 BEV, %d frames/GPU/step"
+
+
+def workload(sel, points, frames):
+    return (sel["label"] % points) + ", bf16, fwd+loss+bwd+AdamW, %d frames/GPU/step" % frames
 
 
 def peaks():
@@ -124,16 +126,17 @@ def cpu_reference_step(cfg, sd, ex, frames):
     p = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
     preds = O.detector_forward(ex["points"], p, cfg, frames, train=True, backbone="gather")
     loss, _ = O.center_loss(ex, preds, cfg["weight"], cfg["code_weights"], cfg["with_reg_iou"], cfg["voxel_size"],
-                            cfg["pc_range"], cfg["out_size_factor"])
+                            cfg["pc_range"], cfg["out_size_factor"], with_iou="iou" in cfg["common_heads"])
     loss.backward()
     return float(loss)
 
 
-def run_cpu_baseline(cfg, n_points, steps, warmup):
+def run_cpu_baseline(cfg, n_points, steps, warmup, sel=None):
     from pillarnext_b200 import modules, synth
     torch.manual_seed(0)
     sd = {k: v.detach().clone() for k, v in modules.build_pillarnext_b(cfg).state_dict().items()}
-    exs = [synth.make_batch([100 + i], n_points, cfg, kind="lidar", n_boxes=40, sweeps=10) for i in range(2)]
+    sw, rg = (sel["sweeps"], sel["rings"]) if sel else (10, 32)
+    exs = [synth.make_batch([100 + i], n_points, cfg, kind="lidar", n_boxes=40, sweeps=sw, rings=rg) for i in range(2)]
     for i in range(warmup):
         cpu_reference_step(cfg, sd, exs[i % 2], 1)
     t0 = time.perf_counter()
@@ -148,14 +151,18 @@ def main_reference(args):
     if rank != 0:
         return
     from pillarnext_b200 import synth
-    cfg = synth.NUSC
+    sel = synth.BENCH_CONFIGS[args.config]
+    cfg = sel["cfg"]
+    args.points = args.points or sel["points"]
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "OMP_NUM_THREADS" in os.environ:
+        torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1: rank 0 alone runs this arm, on all cores
     steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    fps, spf = run_cpu_baseline(cfg, args.points, steps, warmup)
+    fps, spf = run_cpu_baseline(cfg, args.points, steps, warmup, sel)
     cores = torch.get_num_threads()
-    sample = "%d timed single-frame fwd+loss+bwd steps (%d pts, 1344^2) of the fp32 oracle port, %d torch CPU threads" % (steps, args.points, cores)
+    sample = "%d timed single-frame fwd+loss+bwd steps (%d pts) of the fp32 oracle port, %d torch CPU threads" % (steps, args.points, cores)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": spf * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD % (args.points, 1), "note": "CPU port of the reference algorithm (spconv/torch_scatter absent: oracle restatement)"},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload(sel, args.points, 1), "note": "CPU port of the reference algorithm (spconv/torch_scatter absent: oracle restatement)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -168,8 +175,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=6, help="frames per GPU per step (reference: 6/GPU, docs/RUN.md:9)")
-    ap.add_argument("--points", type=int, default=30000)
+    ap.add_argument("--config", default="nusc", choices=["nusc", "waymo180k", "waymo540k"],
+                    help="BASELINE.json configs[1] (default, the config the metric is quoted on) / [3] / [4]")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the reference's 6 nuScenes / 3 Waymo, docs/RUN.md:9,34)")
+    ap.add_argument("--points", type=int, default=0, help="points per frame (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--voxelize-sweep", action="store_true", help="also report voxelizer GB/s over batch sizes")
     args = ap.parse_args()
@@ -186,17 +195,23 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (some boxes default to VERSION)
+        # NCCL's own log (ring/tree/NVLS setup, nranks) goes to stderr so stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
-    cfg = synth.NUSC
+    sel = synth.BENCH_CONFIGS[args.config]
+    cfg = sel["cfg"]
+    args.frames = args.frames or cfg["frames_per_gpu"]
+    args.points = args.points or sel["points"]
     torch.manual_seed(0)
     model = modules.build_pillarnext_b(cfg).to(dev).train()
     params = [p for p in model.parameters()]
     opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.01, fused=True)
     nb = 4                                                     # distinct synthetic batches, rotated
     host = [pin(synth.make_batch([rank * 1000 + b * args.frames + f for f in range(args.frames)], args.points, cfg,
-                                 kind="lidar", n_boxes=40, sweeps=10)) for b in range(nb)]
+                                 kind="lidar", n_boxes=40, sweeps=sel["sweeps"], rings=sel["rings"])) for b in range(nb)]
     resident = [to_device(h, dev) for h in host]
     from pillarnext_b200.parallel import FlatGradAllReduce
     allreduce_grads = FlatGradAllReduce(params)
@@ -212,8 +227,6 @@ def main():
     copy_stream = torch.cuda.Stream(device=dev)
     loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
-    nocopy = bool(os.environ.get("PNX_E2E_NOCOPY"))
-    noitem = bool(os.environ.get("PNX_E2E_NOITEM"))
 
     def timed(n, e2e):
         if world > 1:
@@ -229,31 +242,27 @@ def main():
             nxt = None
             prev_loss = None
             for i in range(n):
-                if nocopy:
-                    ex = resident[i % nb]
-                else:
-                    if nxt is None:
-                        with torch.cuda.stream(copy_stream):
-                            nxt = (to_device(host[i % nb], dev, non_blocking=True), torch.cuda.Event())
-                            nxt[1].record(copy_stream)
-                    ex, ev = nxt
-                    torch.cuda.current_stream().wait_event(ev)
-                    if i + 1 < n:
-                        copy_stream.wait_stream(torch.cuda.current_stream())   # buffers of step i-1 are free again
-                        with torch.cuda.stream(copy_stream):
-                            nxt = (to_device(host[(i + 1) % nb], dev, non_blocking=True), torch.cuda.Event())
-                            nxt[1].record(copy_stream)
+                if nxt is None:
+                    with torch.cuda.stream(copy_stream):
+                        nxt = (to_device(host[i % nb], dev, non_blocking=True), torch.cuda.Event())
+                        nxt[1].record(copy_stream)
+                ex, ev = nxt
+                torch.cuda.current_stream().wait_event(ev)
+                if i + 1 < n:
+                    copy_stream.wait_stream(torch.cuda.current_stream())   # buffers of step i-1 are free again
+                    with torch.cuda.stream(copy_stream):
+                        nxt = (to_device(host[(i + 1) % nb], dev, non_blocking=True), torch.cuda.Event())
+                        nxt[1].record(copy_stream)
                 loss = step(ex)
-                if not noitem:
-                    # device -> host read of the step's result: async copy into pinned memory + event, consumed one step
-                    # later (a plain .item() would synchronise the whole stream, i.e. also the step just enqueued)
-                    slot = i & 1
-                    loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
-                    loss_ev[slot].record()
-                    if prev_loss is not None:
-                        loss_ev[prev_loss].synchronize()
-                        _ = float(loss_host[prev_loss][0])
-                    prev_loss = slot
+                # device -> host read of the step's result: async copy into pinned memory + event, consumed one step
+                # later (a plain .item() would synchronise the whole stream, i.e. also the step just enqueued)
+                slot = i & 1
+                loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_ev[slot].record()
+                if prev_loss is not None:
+                    loss_ev[prev_loss].synchronize()
+                    _ = float(loss_host[prev_loss][0])
+                prev_loss = slot
             if prev_loss is not None:
                 loss_ev[prev_loss].synchronize()
                 _ = float(loss_host[prev_loss][0])
@@ -330,20 +339,20 @@ def main():
     # ---- voxelizer HBM roofline (second half of the BASELINE metric): many frames per launch so bytes >= 64 MB
     vox = None
     if rank == 0:
-        vox = voxelize_roofline(dev, cfg, pk)
+        vox = voxelize_roofline(dev, sel, pk)
 
     line = None
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
             torch.cuda.synchronize()
-            fps, spf = run_cpu_baseline(cfg, args.points, 1, 0)
+            fps, spf = run_cpu_baseline(cfg, args.points, 1, 0, sel)
             cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": "1 single-frame fwd+loss+bwd step (%d pts, 1344^2 grid) of the fp32 oracle port on the host CPU (%.1f s)" % (args.points, spf)}
+                   "sample": "1 single-frame fwd+loss+bwd step (%d pts) of the fp32 oracle port on the host CPU (%.1f s)" % (args.points, spf)}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD % (args.points, args.frames), "global_batch": args.frames * world,
+                "config": {"workload": workload(sel, args.points, args.frames), "name": args.config, "global_batch": args.frames * world,
                            "parallelism": "dp%d (frames sharded, NCCL gradient all-reduce, local BatchNorm)" % world,
                            "l2": "per-step activation working set (GBs) >> 126 MB L2; 4 distinct input batches rotated",
                            "timed_step": "reader+backbone+neck+head fwd, loss, bwd, grad all-reduce (N>1), AdamW"},
@@ -358,15 +367,18 @@ def main():
         dist.destroy_process_group()
 
 
-def voxelize_roofline(dev, cfg, pk):
-    """Index-generation voxelizer (pnx_voxelize: V1-V2, 4 kernels) swept over frames per launch.
-    Algorithmic bytes: 24*N + 4*Nv + 12*P; the headline entry is the largest launch (>= 64 MB)."""
+def voxelize_roofline(dev, sel, pk):
+    """Index-generation voxelizer (pnx_voxelize: V1-V2) swept over frames per launch on the selected config's point
+    clouds.  Algorithmic bytes: 24*N + 4*Nv + 12*P; the headline entry is the largest launch (>= 64 MB of
+    algorithmic bytes, input larger than the 126 MB L2 so every timed iteration streams from HBM)."""
     from pillarnext_b200 import ops, synth
-    n = 30000
-    base = [synth.make_frame(5000 + i, n, cfg, "lidar", sweeps=10) for i in range(16)]
+    cfg, n = sel["cfg"], sel["points"]
+    nbase = 16 if n <= 60000 else 4
+    base = [synth.make_frame(5000 + i, n, cfg, "lidar", sweeps=sel["sweeps"], rings=sel["rings"]) for i in range(nbase)]
     sweep = []
-    for frames in (16, 64, 256):
-        pts = synth.collate_points([base[i % 16] for i in range(frames)]).to(dev)
+    for total in (480000, 1920000, 7680000):
+        frames = max(1, total // n)
+        pts = synth.collate_points([base[i % nbase] for i in range(frames)]).to(dev)
         v = ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False)
         P = int(v.counts[0].item())
         Nv = int((v.pillar_of_point[:pts.shape[0]] >= 0).sum().item())
@@ -386,9 +398,10 @@ def voxelize_roofline(dev, cfg, pk):
                       "achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm"]})
         del pts, v
     best = sweep[-1]
-    return {"bound": "hbm", "kernel": "pnx_voxelize (mark | block scan | coords | rank)", "achieved": best["achieved"], "peak": pk["hbm"],
+    return {"bound": "hbm", "kernel": "pnx_voxelize", "achieved": best["achieved"], "peak": pk["hbm"],
             "unit": "GB/s", "frac": best["frac"], "peak_source": pk["src"], "sweep": sweep,
-            "note": "index generation only (pillar ids + coords); bitmap zeroing/reading (B*Gx*Gy/8 bytes x2) is real traffic not in the algorithmic count"}
+            "note": "index generation (pillar id per point + sorted-unique coords); bytes = 24*N + 4*Nv + 12*P; the largest launch reads "
+                    "%.0f MB of points (> L2), back-to-back launches, CUDA events" % (24.0 * best["points"] / 1e6)}
 
 
 if __name__ == "__main__":

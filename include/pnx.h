@@ -61,7 +61,8 @@ int pnx_scan_blocks(const int* counts, int n_blocks, int* out, int* total_out, c
  *   bucket_cnt    [2*(cap_pillars+1)] OUT (optional, may be NULL): points per pillar + zeroed cursors for
  *                 pnx_bucketize
  *   counts        [2] device ints: counts[0] = #pillars P (counts[1] = #kept points, set by pnx_bucketize)
- * cap_pillars must be >= min(n_points, batch*gx*gy).  Kernels: mark (RED.OR) | block popcounts | scan | coords | rank. */
+ * cap_pillars must be >= min(n_points, batch*gx*gy).  Kernels: mark (persistent, points staged through shared memory by
+ * TMA bulk copies, one fire-and-forget RED.OR per point) | block popcounts | scan | coords | rank. */
 size_t pnx_voxelize_bitmap_words(int batch, int gx, int gy);
 int pnx_voxelize(const float* points, int n_points, int batch, float min_x, float min_y, float vs_x,
                  float vs_y, int gx, int gy, uint32_t* bitmap, uint16_t* inblk, int* blockcnt, int* blockpref,
@@ -252,6 +253,21 @@ int pnx_tap_gather_sum(const float* Z, long long ldz, const float* bias16, int B
                        cudaStream_t stream);
 int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, int nz, long long lo_off,
                     cudaStream_t stream);   /* nz = GEMM columns (>= 144); lo_off > 0: also write the lo halves (split rows) */
+
+/* ---------------------------------------------------------------- F3: label assignment on the GPU
+ * One task of AssignLabel.__call__ (det3d/datasets/pipelines/assign.py:23-116; gaussian_radius / draw_gaussian:
+ * center_utils.py:12-60) for a whole batch, i.e. also the stacking of loader/collate.py:23-33:
+ *   boxes [B, N, 9] fp32 (x, y, z, dx, dy, dz, vx, vy, yaw), cls [B, N] int32 global class index (< 0: ignored),
+ *   cls_task / cls_id [n_classes] int32 (task of a class, index of the class inside its task)
+ *   -> hm [B, C, H, W] fp32, anno_box [B, M, 10] fp32, ind [B, M] i64, mask [B, M] u8, cat [B, M] i64,
+ *      gt_boxes [B, M, 7] fp32 (all zeroed by the caller; M = max_objs).
+ * Objects keep their order (slot = accepted objects of the task before it); radius/centre/gaussian in float64 and
+ * stored as float32 like the numpy reference.  (pc_x, pc_y) = pc_range[0:2], osf = out_size_factor of the task. */
+int pnx_assign_labels(const float* boxes, const int* cls, int B, int N, const int* cls_task, const int* cls_id,
+                      int n_classes, int task, double vs_x, double vs_y, double pc_x, double pc_y, int osf,
+                      double gaussian_overlap, int min_radius, int max_objs, int C, int H, int W, float* hm,
+                      float* anno_box, long long* ind, unsigned char* mask, long long* cat, float* gt_boxes,
+                      cudaStream_t stream);
 
 /* ---------------------------------------------------------------- L1 fused CenterPoint loss (forward + gradient)
  * One task: out/dout [B*H*W, npad] fp32 channels-last head output (columns reg2|height1|dim3|rot2|vel2|hm C|pad)

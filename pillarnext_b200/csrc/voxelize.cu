@@ -176,30 +176,24 @@ struct VoxGeom {
   int gx, gy, vwords, batch;
 };
 
-// V1: cell index per point + occupancy bitmap + per-block pillar counts.  One thread per point; the block
-// stages its 256 points (6 KB) through shared memory with 128-bit coalesced loads.
-__global__ void __launch_bounds__(256) vox_mark_kernel(const float* __restrict__ points, int n, VoxGeom g,
-                                                       uint32_t* __restrict__ bitmap,
-                                                       int* __restrict__ cell_of_point) {
-  __shared__ float4 stage[256 * 6 / 4];
-  const long long first = (long long)blockIdx.x * 256;
-  const int n_here = (int)min((long long)256, (long long)n - first);
-  const float4* src = reinterpret_cast<const float4*>(points + first * 6);  // 256*24 B blocks stay 16B aligned
-  const int n_vec = (n_here * 6 + 3) / 4;
-  const long long total_floats = (long long)n * 6;
-  for (int v = threadIdx.x; v < n_vec; v += 256) {
-    long long f0 = first * 6 + (long long)v * 4;
-    if (f0 + 4 <= total_floats) {
-      stage[v] = __ldg(src + v);
-    } else {  // ragged tail of the whole array
-      float t[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k = 0; k < 4 && f0 + k < total_floats; ++k) t[k] = points[f0 + k];
-      stage[v] = make_float4(t[0], t[1], t[2], t[3]);
-    }
-  }
-  __syncthreads();
-  if ((int)threadIdx.x >= n_here) return;
-  const float* p = reinterpret_cast<const float*>(stage) + threadIdx.x * 6;
+// V1: cell index per point + occupancy bitmap.  Persistent kernel, one CTA of 1024 threads per SM: every CTA streams a
+// contiguous chunk of the points through a 3-stage shared-memory ring filled by TMA bulk copies (cp.async.bulk,
+// 24 KB = 1024 points per stage, one elected thread issues, mbarrier completion), so HBM requests stay in flight while
+// the previous stage is being processed.  One point per thread per stage: bit-exact cell arithmetic, one
+// fire-and-forget RED.OR into the bitmap, the cell id stored for the rank pass.
+constexpr int kVoxThreads = 1024;
+constexpr int kVoxStagePts = 1024;
+constexpr int kVoxStages = 3;
+constexpr int kVoxStageBytes = kVoxStagePts * 24;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   pnx::smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(pnx::smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ int vox_cell(const float* p, const VoxGeom& g) {
   const float bf = p[0], x = p[1], y = p[2];
   // pillar_encoder.py:95-96 -- fp32 subtract then true fp32 division (no reciprocal, no FMA)
   const float cx = __fdiv_rn(__fsub_rn(x, g.min_x), g.vs_x);
@@ -208,26 +202,77 @@ __global__ void __launch_bounds__(256) vox_mark_kernel(const float* __restrict__
   bool keep = (cx >= 0.f) && (cx < (float)g.gx) && (cy >= 0.f) && (cy < (float)g.gy);
   const int b = (int)bf;  // :107 .long() truncation
   keep = keep && (b >= 0) && (b < g.batch);
-  int cell = -1;
-  if (keep) {
-    const int xi = (int)cx, yi = (int)cy;  // :106 trunc
-    const int word = (b * g.gx + xi) * g.vwords + (yi >> 5);
-    const uint32_t bit = 1u << (yi & 31);
-    atomicOr(&bitmap[word], bit);  // fire-and-forget RED.OR: the per-block pillar counts come from vox_blockcnt_kernel
-    cell = word * 32 + (yi & 31);
-  }
-  cell_of_point[first + threadIdx.x] = cell;
+  if (!keep) return -1;
+  const int xi = (int)cx, yi = (int)cy;  // :106 trunc
+  return ((b * g.gx + xi) * g.vwords + (yi >> 5)) * 32 + (yi & 31);
 }
 
-// pillars per 32-word block = popcount of the block (one warp per block, one coalesced 128-byte read)
+__global__ void __launch_bounds__(kVoxThreads, 1) vox_mark_kernel(const float* __restrict__ points, int n, int pts_per_cta,
+                                                                  VoxGeom g, uint32_t* __restrict__ bitmap,
+                                                                  int* __restrict__ cell_of_point) {
+  extern __shared__ __align__(128) uint8_t vsm[];
+  float* ring = reinterpret_cast<float*>(vsm);                                         // [kVoxStages][1024 pts][6]
+  uint64_t* full = reinterpret_cast<uint64_t*>(vsm + kVoxStages * kVoxStageBytes);     // [kVoxStages]
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kVoxStages; ++s) pnx::mbar_init(&full[s], 1);
+    pnx::fence_barrier_init();
+  }
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * pts_per_cta;
+  const long long p1 = min((long long)n, p0 + pts_per_cta);
+  const int n_stage = p1 > p0 ? (int)((p1 - p0 + kVoxStagePts - 1) / kVoxStagePts) : 0;
+  auto stage_pts = [&](int it) { return (int)min((long long)kVoxStagePts, p1 - (p0 + (long long)it * kVoxStagePts)); };
+  auto issue = [&](int it) {   // thread 0: a full stage = one bulk copy
+    const int s = it % kVoxStages;
+    pnx::mbar_arrive_expect_tx(&full[s], kVoxStageBytes);
+    bulk_g2s(ring + (size_t)s * kVoxStagePts * 6, points + (p0 + (long long)it * kVoxStagePts) * 6, kVoxStageBytes, &full[s]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < min(n_stage, kVoxStages); ++it)
+      if (stage_pts(it) == kVoxStagePts) issue(it);
+  for (int it = 0; it < n_stage; ++it) {
+    const int s = it % kVoxStages;
+    const int np = stage_pts(it);
+    float* st = ring + (size_t)s * kVoxStagePts * 6;
+    if (np == kVoxStagePts) {
+      pnx::mbar_wait(&full[s], (uint32_t)((it / kVoxStages) & 1));
+    } else {  // ragged tail of the whole array (at most one stage of one CTA): plain coalesced loads
+      const float* src = points + (p0 + (long long)it * kVoxStagePts) * 6;
+      for (int q = tid; q < np * 6; q += kVoxThreads) st[q] = __ldg(src + q);
+      __syncthreads();
+    }
+    if (tid < np) {
+      const int cell = vox_cell(st + tid * 6, g);
+      // fire-and-forget reduction: `atomicOr` with an unused result still compiles to ATOMG (a round trip per point,
+      // measured 3x slower for this pass); red.* is the REDG instruction
+      if (cell >= 0) asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(bitmap + (cell >> 5)), "r"(1u << (cell & 31)) : "memory");
+      cell_of_point[p0 + (long long)it * kVoxStagePts + tid] = cell;
+    }
+    __syncthreads();  // everyone has read stage s
+    if (tid == 0 && it + kVoxStages < n_stage && stage_pts(it + kVoxStages) == kVoxStagePts) issue(it + kVoxStages);
+  }
+}
+
+// pillars per 32-word block = popcount of the block, and the in-block exclusive prefix of every word (inblk: used by the
+// rank kernel and the rulebook).  One warp per group of kCntU blocks: kCntU coalesced 128-byte reads in flight per warp.
+constexpr int kCntU = 4;
 __global__ void __launch_bounds__(256) vox_blockcnt_kernel(const uint32_t* __restrict__ bitmap, int n_blocks,
-                                                           int* __restrict__ blockcnt) {
-  const int blk = (int)(((long long)blockIdx.x * 256 + threadIdx.x) >> 5);
-  if (blk >= n_blocks) return;
-  int c = __popc(bitmap[(size_t)blk * 32 + (threadIdx.x & 31)]);
+                                                           int* __restrict__ blockcnt, uint16_t* __restrict__ inblk) {
+  const int lane = threadIdx.x & 31;
+  const long long blk0 = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * kCntU;
+  if (blk0 >= n_blocks) return;
+  uint32_t w[kCntU];
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) blockcnt[blk] = c;
+  for (int u = 0; u < kCntU; ++u) w[u] = blk0 + u < n_blocks ? __ldg(bitmap + (size_t)(blk0 + u) * 32 + lane) : 0u;
+#pragma unroll
+  for (int u = 0; u < kCntU; ++u) {
+    if (blk0 + u >= n_blocks) break;
+    const int c = __popc(w[u]);
+    const int incl = warp_incl_scan(c);
+    inblk[(size_t)(blk0 + u) * 32 + lane] = (uint16_t)(incl - c);
+    if (lane == 31) blockcnt[blk0 + u] = incl;
+  }
 }
 
 // per-superblock (1024 blocks) totals of the block counts (only ~B*100 counters: atomics from the marking kernel
@@ -259,33 +304,56 @@ __global__ void vox_rank_kernel(const int* __restrict__ cell_of_point, int n, co
   if (cell >= 0) {
     const int word = cell >> 5, bit = cell & 31;
     pid = blockpref[word >> 5] + (int)inblk[word] + __popc(bitmap[word] & ((1u << bit) - 1u));
-    if (bucket_cnt) atomicAdd(&bucket_cnt[pid], 1u);  // integer count: order-independent
+    if (bucket_cnt)  // integer count: order-independent; red.* = REDG (atomicAdd with an unused result compiles to ATOMG)
+      asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bucket_cnt + pid) : "memory");
   }
   pillar_of_point[i] = pid;
 }
 
-// V2c: coords (b, yi, xi) of every pillar in sorted-unique order.  One warp per 32-word block (one coalesced
-// 128-byte read), lanes = words, in-block offsets by a warp scan of the popcounts.
-__global__ void vox_coords_kernel(const uint32_t* __restrict__ bitmap, const int* __restrict__ blockpref, int n_words,
-                                  VoxGeom g, int* __restrict__ coords, int cap, uint16_t* __restrict__ inblk) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t bits = w < n_words ? bitmap[w] : 0u;
-  const int cnt = __popc(bits);
-  const int incl = warp_incl_scan(cnt);
-  if (w < n_words) inblk[w] = (uint16_t)(incl - cnt);  // in-block prefix: used by the rank kernel and the rulebook
-  if (!bits) return;
-  int idx = blockpref[w >> 5] + incl - cnt;
-  int row = w / g.vwords, vw = w - row * g.vwords;
-  int b = row / g.gx, xi = row - b * g.gx;
-  while (bits) {
-    int bit = __ffs(bits) - 1;
-    bits &= bits - 1;
-    if (idx < cap) {
-      coords[idx * 3 + 0] = b;
-      coords[idx * 3 + 1] = vw * 32 + bit;  // yi
-      coords[idx * 3 + 2] = xi;
+// V2c: coords (b, yi, xi) of every pillar in sorted-unique order.  One warp per 32-word block (one coalesced 128-byte
+// read); empty blocks (known from blockpref) are skipped without touching the bitmap.  The pillars of a block are
+// consecutive rows of `coords`: they are staged in shared memory and written with coalesced stores.
+constexpr int kCoordStage = 128;   // pillars of one block staged per warp (3 ints each); denser blocks take the direct path
+__global__ void __launch_bounds__(256) vox_coords_kernel(const uint32_t* __restrict__ bitmap, const int* __restrict__ blockpref,
+                                                         int n_blocks, VoxGeom g, int* __restrict__ coords, int cap,
+                                                         const uint16_t* __restrict__ inblk) {
+  __shared__ int s_stage[8 * kCoordStage * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int blk = (int)(((long long)blockIdx.x * 256 + threadIdx.x) >> 5);
+  if (blk >= n_blocks) return;
+  const int base_idx = __ldg(blockpref + blk), total = __ldg(blockpref + blk + 1) - base_idx;
+  if (total == 0) return;
+  const int w = blk * 32 + lane;
+  uint32_t bits = __ldg(bitmap + w);
+  const int pre = (int)__ldg(inblk + w);
+  const int row = w / g.vwords, vw = w - row * g.vwords;
+  const int b = row / g.gx, xi = row - b * g.gx;
+  if (total <= kCoordStage && base_idx + total <= cap) {
+    int* cs = s_stage + warp * (kCoordStage * 3);
+    int k = pre;
+    while (bits) {
+      const int bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      cs[k * 3 + 0] = b;
+      cs[k * 3 + 1] = vw * 32 + bit;  // yi
+      cs[k * 3 + 2] = xi;
+      ++k;
     }
-    ++idx;
+    __syncwarp();
+    int* dst = coords + (size_t)base_idx * 3;
+    for (int q = lane; q < total * 3; q += 32) dst[q] = cs[q];
+  } else {
+    int idx = base_idx + pre;
+    while (bits) {
+      const int bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (idx < cap) {
+        coords[idx * 3 + 0] = b;
+        coords[idx * 3 + 1] = vw * 32 + bit;  // yi
+        coords[idx * 3 + 2] = xi;
+      }
+      ++idx;
+    }
   }
 }
 
@@ -337,17 +405,34 @@ extern "C" int pnx_voxelize(const float* points, int n_points, int batch, float 
   int* supercnt = blockcnt + super_offset(n_blocks);
   if (bucket_cnt) PNX_CUDA(cudaMemsetAsync(bucket_cnt, 0, (size_t)(cap_pillars + 1) * 4 * 2, stream));  // counts + cursors
   if (n_points > 0) {
-    vox_mark_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(points, n_points, g, bitmap, cell_of_point);
+    static int sm_count = 0;
+    constexpr int kMarkSmem = kVoxStages * kVoxStageBytes + kVoxStages * 8 + 128;
+    if (!sm_count) {
+      int dev = 0;
+      PNX_CUDA(cudaGetDevice(&dev));
+      PNX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+      PNX_CUDA(cudaFuncSetAttribute(vox_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMarkSmem));
+    }
+    PNX_CHECK_ARG((reinterpret_cast<uintptr_t>(points) & 15) == 0, "points must be 16-byte aligned");
+    // two CTAs' worth of chunks per SM keeps the tail short; chunks are whole stages so every bulk copy is 16-byte aligned
+    int ctas = 2 * sm_count;
+    int pts_per_cta = (int)((((long long)n_points + ctas - 1) / ctas + kVoxStagePts - 1) / kVoxStagePts * kVoxStagePts);
+    ctas = (int)(((long long)n_points + pts_per_cta - 1) / pts_per_cta);
+    vox_mark_kernel<<<ctas, kVoxThreads, kMarkSmem, stream>>>(points, n_points, pts_per_cta, g, bitmap, cell_of_point);
     PNX_CHECK_LAUNCH();
-    vox_blockcnt_kernel<<<pnx_cdiv((long long)n_blocks * 32, 256), 256, 0, stream>>>(bitmap, n_blocks, blockcnt);
+    vox_blockcnt_kernel<<<pnx_cdiv((long long)pnx_cdiv(n_blocks, kCntU) * 32, 256), 256, 0, stream>>>(bitmap, n_blocks, blockcnt, inblk);
     PNX_CHECK_LAUNCH();
   }
   super_reduce_kernel<<<(n_blocks + 1023) / 1024, 256, 0, stream>>>(blockcnt, n_blocks, supercnt);
   PNX_CHECK_LAUNCH();
   int rc = pnx_scan_blocks(blockcnt, n_blocks, blockpref, counts, stream);
   if (rc) return rc;
-  vox_coords_kernel<<<pnx_cdiv(n_words, 256), 256, 0, stream>>>(bitmap, blockpref, n_words, g, coords, cap_pillars,
-                                                                inblk);
+  if (n_points > 0) {
+    vox_coords_kernel<<<pnx_cdiv((long long)n_blocks * 32, 256), 256, 0, stream>>>(bitmap, blockpref, n_blocks, g, coords,
+                                                                                  cap_pillars, inblk);
+  } else {
+    PNX_CUDA(cudaMemsetAsync(inblk, 0, (size_t)n_words * 2, stream));
+  }
   PNX_CHECK_LAUNCH();
   if (n_points > 0) {
     vox_rank_kernel<<<pnx_cdiv(n_points, 256), 256, 0, stream>>>(cell_of_point, n_points, bitmap, blockpref, inblk,

@@ -619,5 +619,7 @@ def build_pillarnext_b(cfg, sync_batchnorm=False):
     neck = ASPPNeck(256)
     head = CenterHead(256, cfg["tasks"], cfg["weight"], cfg["code_weights"], cfg["common_heads"], cfg["head_strides"],
                       with_reg_iou=cfg["with_reg_iou"], voxel_size=cfg["voxel_size"], pc_range=cfg["pc_range"],
-                      out_size_factor=cfg["out_size_factor"])
-    return SingleStageDetector(reader, backbone, neck, head, sync_batchnorm=sync_batchnorm)
+                      out_size_factor=cfg["out_size_factor"],
+                      rectifier=cfg.get("rectifier", [[0.0] * len(t) for t in cfg["tasks"]]))
+    return SingleStageDetector(reader, backbone, neck, head, post_processing=cfg.get("post_processing"),
+                               sync_batchnorm=sync_batchnorm)

@@ -587,6 +587,48 @@ def wgrad_split(X, x_lo, x_channels, Y, y_lo, y_channels, M, taps, dW, **kw):
     return dW
 
 
+# --------------------------------------------------------------------------------- F3: label assignment
+_cls_tables = {}
+
+
+def assign_labels(gt_boxes, gt_cls, tasks, voxel_size, pc_range, out_size_factor, max_objs=500, gaussian_overlap=0.1,
+                  min_radius=2):
+    """AssignLabel + collate on the GPU (pnx_assign_labels): gt_boxes [B, N, 9] fp32 cuda, gt_cls [B, N] int32 cuda
+    (index into the flattened class list of `tasks`, < 0 = ignored) -> dict of per-task lists hm / anno_box / ind /
+    mask / cat / gt_boxes in the reference's collate format (det3d/datasets/pipelines/assign.py, loader/collate.py)."""
+    assert gt_boxes.is_cuda and gt_boxes.dtype == torch.float32 and gt_boxes.dim() == 3 and gt_boxes.shape[2] == 9
+    assert gt_cls.is_cuda and gt_cls.dtype == torch.int32 and tuple(gt_cls.shape) == tuple(gt_boxes.shape[:2])
+    gt_boxes, gt_cls = gt_boxes.contiguous(), gt_cls.contiguous()
+    dev = gt_boxes.device
+    B, N = gt_cls.shape
+    key = (tuple(tuple(t) for t in tasks), dev)
+    if key not in _cls_tables:
+        ct = [ti for ti, t in enumerate(tasks) for _ in t]
+        ci = [ni for t in tasks for ni, _ in enumerate(t)]
+        _cls_tables[key] = (torch.tensor(ct, dtype=torch.int32, device=dev), torch.tensor(ci, dtype=torch.int32, device=dev))
+    cls_task, cls_id = _cls_tables[key]
+    g = grid_size_xy(voxel_size, pc_range)
+    out = {k: [] for k in ("hm", "anno_box", "ind", "mask", "cat", "gt_boxes")}
+    L = lib()
+    for t, task in enumerate(tasks):
+        osf = int(out_size_factor[t])
+        W, H = int(g[0]) // osf, int(g[1]) // osf
+        hm = torch.zeros(B, len(task), H, W, dtype=torch.float32, device=dev)
+        anno = torch.zeros(B, max_objs, 10, dtype=torch.float32, device=dev)
+        ind = torch.zeros(B, max_objs, dtype=torch.int64, device=dev)
+        mask = torch.zeros(B, max_objs, dtype=torch.uint8, device=dev)
+        cat = torch.zeros(B, max_objs, dtype=torch.int64, device=dev)
+        gtb = torch.zeros(B, max_objs, 7, dtype=torch.float32, device=dev)
+        _count(1)
+        check(L.pnx_assign_labels(ptr(gt_boxes), ptr(gt_cls), B, N, ptr(cls_task), ptr(cls_id), cls_task.numel(), t,
+                                  float(voxel_size[0]), float(voxel_size[1]), float(pc_range[0]), float(pc_range[1]), osf,
+                                  float(gaussian_overlap), int(min_radius), int(max_objs), len(task), H, W, ptr(hm), ptr(anno),
+                                  ptr(ind), ptr(mask), ptr(cat), ptr(gtb), stream()))
+        for k, v in (("hm", hm), ("anno_box", anno), ("ind", ind), ("mask", mask), ("cat", cat), ("gt_boxes", gtb)):
+            out[k].append(v)
+    return out
+
+
 # --------------------------------------------------------------------------------- F1: decode + rotated NMS
 def _host_floats(vals, n):
     import ctypes

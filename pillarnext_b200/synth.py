@@ -17,14 +17,41 @@ NUSC = dict(
     out_size_factor=[4, 4, 4, 4, 4, 4], head_strides=[2, 2, 2, 2, 2, 2], with_reg_iou=True,
     intensity_max=255.0, xy_extent=54.0, z_range=(-5.0, 3.0),
 )
+NUSC["post_processing"] = dict(          # configs/experiments/nusc_det_pp18_aspp_iou_sp.yaml:39-50
+    post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], score_threshold=0.1,
+    nms=dict(nms_pre_max_size=1000, nms_post_max_size=83,
+             nms_iou_threshold=[[0.2], [0.2, 0.2], [0.2, 0.2], [0.2], [0.2, 0.2], [0.2, 0.2]]),
+    pc_range=NUSC["pc_range"], voxel_size=NUSC["voxel_size"], out_size_factor=NUSC["out_size_factor"])
+NUSC["frames_per_gpu"] = 6               # docs/RUN.md:9
+
+# BASELINE.json configs[3]/[4]: the reference's Waymo experiment (configs/experiments/waymo_det_pp18_aspp_iou_car_sp.yaml:
+# 2 tasks, `iou` head, weight 1, rectifier, nms_pre_max_size 4096) at the benchmark shape 0.1 m / +-75.2 m -> 1504^2 BEV
+# (the reference yaml itself says 0.075 m / +-76.8 m -> 2048^2 = WAYMO_REF below).
 WAYMO_BENCH = dict(
     voxel_size=[0.1, 0.1, 20], pc_range=[-75.2, -75.2, -10.0, 75.2, 75.2, 10.0],
     tasks=[["vehicle"], ["pedestrian", "cyclist"]],
-    common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+    common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2), "iou": (1, 2)},
     strides=[1, 2, 2, 2], weight=1.0, code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2, 1.0, 1.0],
-    out_size_factor=[4, 4], head_strides=[2, 2], with_reg_iou=True,
-    intensity_max=1.0, xy_extent=80.0, z_range=(-3.0, 5.0),
+    out_size_factor=[4, 4], head_strides=[2, 2], with_reg_iou=True, rectifier=[[0.68], [0.71, 0.65]],
+    intensity_max=1.0, xy_extent=80.0, z_range=(-3.0, 5.0), frames_per_gpu=3,          # docs/RUN.md:34
 )
+WAYMO_BENCH["post_processing"] = dict(
+    post_center_limit_range=[-80.0, -80.0, -10.0, 80.0, 80.0, 10.0], score_threshold=0.1,
+    nms=dict(nms_pre_max_size=4096, nms_post_max_size=500, nms_iou_threshold=[[0.7], [0.2, 0.25]]),
+    pc_range=WAYMO_BENCH["pc_range"], voxel_size=WAYMO_BENCH["voxel_size"], out_size_factor=WAYMO_BENCH["out_size_factor"])
+WAYMO_REF = dict(WAYMO_BENCH)
+WAYMO_REF.update(voxel_size=[0.075, 0.075, 20], pc_range=[-76.8, -76.8, -10.0, 76.8, 76.8, 10.0])
+WAYMO_REF["post_processing"] = dict(WAYMO_BENCH["post_processing"], pc_range=WAYMO_REF["pc_range"], voxel_size=WAYMO_REF["voxel_size"])
+
+# bench.py --config: BASELINE.json configs[1..4]
+BENCH_CONFIGS = {
+    "nusc": dict(cfg=NUSC, points=30000, sweeps=10, rings=32, label="PillarNeXt-B nuScenes-shape synthetic (BASELINE.json configs[1]): "
+                 "%d pts/frame, 0.075 m pillars, 1344^2 BEV, 6 tasks"),
+    "waymo180k": dict(cfg=WAYMO_BENCH, points=180000, sweeps=1, rings=64, label="PillarNeXt-B Waymo-shape synthetic (BASELINE.json "
+                      "configs[3]): %d pts/frame, 0.1 m pillars, 1504^2 BEV, 2 tasks + iou head"),
+    "waymo540k": dict(cfg=WAYMO_BENCH, points=540000, sweeps=3, rings=64, label="PillarNeXt-B Waymo 3-frame multi-sweep concat "
+                      "(BASELINE.json configs[4]): %d pts/frame, 0.1 m pillars, 1504^2 BEV, 2 tasks + iou head"),
+}
 
 
 def tiny_config(grid=64, tasks=None):
@@ -35,19 +62,25 @@ def tiny_config(grid=64, tasks=None):
     cfg.update(voxel_size=[vs, vs, 8], pc_range=[-half, -half, -5.0, half, half, 3.0], xy_extent=half * 1.08)
     if tasks is not None:
         cfg.update(tasks=tasks, out_size_factor=[4] * len(tasks), head_strides=[2] * len(tasks))
+    cfg["post_processing"] = dict(post_center_limit_range=[-half * 1.2, -half * 1.2, -10.0, half * 1.2, half * 1.2, 10.0],
+                                  score_threshold=0.1, pc_range=cfg["pc_range"], voxel_size=cfg["voxel_size"],
+                                  out_size_factor=cfg["out_size_factor"],
+                                  nms=dict(nms_pre_max_size=1000, nms_post_max_size=83,
+                                           nms_iou_threshold=[[0.2] * len(t) for t in cfg["tasks"]]))
     return cfg
 
 
-def make_frame(seed, n_points, cfg=NUSC, kind="uniform", sweeps=1):
+def make_frame(seed, n_points, cfg=NUSC, kind="uniform", sweeps=1, rings=32):
     """[n,5] fp32 (x,y,z,intensity,time).  'uniform': x,y ~ U(+-extent) (some out of range);
-    'lidar': 32 rings hitting a ground plane + box clutter."""
+    'lidar': `rings` beams hitting a ground plane + box clutter; sweeps > 1 with rings = 64 (Waymo multi-sweep concat,
+    det3d/datasets/waymo/waymo.py:49-67): every sweep is the same scan rigidly shifted, time = 0.1 * sweep."""
     g = np.random.default_rng(1234 + seed)
     ext = cfg["xy_extent"]
     if kind == "uniform":
         xy = g.uniform(-ext, ext, size=(n_points, 2))
         z = g.uniform(cfg["z_range"][0], cfg["z_range"][1], size=(n_points, 1))
     else:
-        n_ring = 32
+        n_ring = rings
         per = n_points // n_ring
         elev = np.deg2rad(np.linspace(-30.0, -0.6, n_ring))
         rng_ = np.clip(1.84 / np.tan(-elev), 1.5, ext * 1.1)
@@ -65,7 +98,13 @@ def make_frame(seed, n_points, cfg=NUSC, kind="uniform", sweeps=1):
             p = np.concatenate([p, q], 0)
         xy, z = p[:, :2], p[:, 2:3]
     inten = g.uniform(0, cfg["intensity_max"], size=(n_points, 1))
-    t = g.integers(0, sweeps, size=(n_points, 1)).astype(np.float64) * 0.05
+    sw = g.integers(0, sweeps, size=(n_points, 1))
+    if rings == 64 and sweeps > 1:                                   # Waymo: past sweeps pose-aligned = rigid shift of the scan
+        xy = xy + sw * g.normal(0, 0.4, size=(1, 2))
+        t = sw.astype(np.float64) * 0.1
+        inten = np.tanh(inten * 3.0)                                 # waymo_convert.py:31
+    else:
+        t = sw.astype(np.float64) * 0.05
     return np.concatenate([xy, z, inten, t], 1).astype(np.float32)
 
 
@@ -169,9 +208,21 @@ def assign_labels(gt_boxes, gt_names, cfg=NUSC, max_objs=500, gaussian_overlap=0
     return dict(hm=hms, anno_box=annos, ind=inds, mask=masks, cat=cats, gt_boxes=gtbs)
 
 
-def make_batch(seeds, n_points, cfg=NUSC, kind="uniform", n_boxes=40, sweeps=1, with_labels=True):
+def make_gt_batch(seeds, n_boxes, cfg=NUSC):
+    """Raw ground truth of a batch for the GPU label assignment (ops.assign_labels): gt_boxes [B, N, 9] fp32 and
+    gt_cls [B, N] int32 (index into the flattened class list of cfg['tasks'])."""
+    names_all = [n for t in cfg["tasks"] for n in t]
+    boxes, cls = [], []
+    for s in seeds:
+        b, names = make_gt(s, n_boxes, cfg)
+        boxes.append(b)
+        cls.append(np.array([names_all.index(n) for n in names], dtype=np.int32))
+    return torch.tensor(np.stack(boxes)), torch.tensor(np.stack(cls))
+
+
+def make_batch(seeds, n_points, cfg=NUSC, kind="uniform", n_boxes=40, sweeps=1, with_labels=True, rings=32):
     """A collated `example` dict in the reference's format (collate.py): points [sumN, 6] + per-task label lists."""
-    frames = [make_frame(s, n_points, cfg, kind, sweeps) for s in seeds]
+    frames = [make_frame(s, n_points, cfg, kind, sweeps, rings) for s in seeds]
     ex = {"points": collate_points(frames), "token": ["synthetic_%d" % s for s in seeds]}
     if with_labels:
         labs = [assign_labels(*make_gt(s, n_boxes, cfg), cfg=cfg) for s in seeds]
