@@ -158,8 +158,15 @@ int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void
               int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
               int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
               double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
-              long long ld_add, int nseg, long long a_lo_off, long long seg_code, int addend_fp32, int sm_count,
+              long long ld_add, int nseg, long long a_lo_off, long long seg_code, int addend_fp32,
+              const void* bnr_raw, long long bnr_ld, const float* bnr_scale, const float* bnr_shift,
+              const float* bnr_mean, const float* bnr_invstd, double* bnr_red, int bnr_C, int sm_count,
               cudaStream_t stream);
+/* bnr_raw != NULL fuses the REDUCE pass of a BatchNorm backward into this GEMM (bf16 output, no pixel shuffle, no forward
+ * statistics): `out` is dy, the gradient of y = relu(raw*scale + shift) -- the epilogue recomputes the ReLU gate from
+ * raw [M, bnr_ld] bf16 with the forward affine, stores g = dy*gate instead of dy and accumulates
+ * bnr_red[c] += sum_m g, bnr_red[bnr_C + c] += sum_m g*(raw - mean[c])*invstd[c]  (fp64; zero it first; bnr_C == Cout).
+ * pnx_bn_bwd_apply is then called with relu = 0 on g.  Same trailing arguments on pnx_conv3x3_win. */
 /* nseg > 1 selects the fp32-grade SPLIT mode (see "split rows" below): every value is a sum of bf16 PIECES, A rows
  * hold piece p of channel c at column p*a_lo_off + c, W is packed [taps, Cout, pieces*Cin] = [piece 0 | piece 1 | ..],
  * and the K loop accumulates nseg (A piece, W piece) segments into the same fp32 TMEM accumulator in the order given
@@ -175,7 +182,9 @@ int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void
  * pnx_igemm's dense mode (aspp.py/conv.py/centerhead.py 3x3 convs, dilation 1) and their data gradients. */
 int pnx_conv3x3_win(const void* A, long long lda, int B, int H, int W, int Cin, const void* Wpacked, int Cout,
                     int block_n, void* out, long long ldc, const float* bias, double* stats, int stats_C, int relu,
-                    int base_off_mode, int sm_count, cudaStream_t stream);
+                    int base_off_mode, const void* bnr_raw, long long bnr_ld, const float* bnr_scale,
+                    const float* bnr_shift, const float* bnr_mean, const float* bnr_invstd, double* bnr_red, int bnr_C,
+                    int sm_count, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- tcgen05 weight gradient
  * dW[t, x, y] += sum_m X[m, x] * Y[g(m,t), y]   (fp32, red.global.add; zero dW first)

@@ -44,7 +44,26 @@ struct IgemmParams {
   int nseg, a_lo_off;
   unsigned long long seg_code;  // 4 bits per segment, in execution order: (A piece << 2) | W piece
   const float* addend_f32;      // fp32 addend (split mode: gradients are accumulated in fp32)
+  // Fused BatchNorm-backward reduction (bf16 staged store only): this GEMM produces dy, the gradient of y = relu(bn(raw)).
+  // The epilogue re-creates the ReLU gate from `raw` with the forward affine, stores g = dy * gate instead of dy and
+  // accumulates red[c] += sum g, red[C + c] += sum g * xhat (xhat = (raw - mean) * invstd) -- the reduce pass of the
+  // BatchNorm backward (elementwise.cu bn_bwd_reduce_kernel) without a separate sweep over dy and raw.
+  const __nv_bfloat16* bnr_raw;
+  long long bnr_ld;
+  const float* bnr_scale; const float* bnr_shift; const float* bnr_mean; const float* bnr_invstd;
+  double* bnr_red;
+  int bnr_C;
 };
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
 
 // threads = TMA warp + MMA warp + PW gather warps + 2 index warps + EW epilogue warps.
 constexpr uint32_t kABytes = 128 * 128;
@@ -60,7 +79,7 @@ struct Cfg {
   static constexpr int kStages = kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw;
   static constexpr int kAccSets = 512 / (MT * BN) >= 2 ? 2 : 1;  // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   static constexpr int kTblSlots = MT == 1 ? 2 : 3;  // ring of per-tile index tables [9 taps][128 rows] (smem budget: 3 for MT = 2)
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kAStage + kBBytes) + kTblSlots * 128 * 9 * 4 + 256 + EW * 4096 + 2 * BN * 4 + BN * 4;
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * (kAStage + kBBytes) + kTblSlots * 128 * 9 * 4 + 256 + EW * 4096 + 2 * BN * 4 + BN * 4 + 4 * BN * 4;
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
@@ -85,7 +104,11 @@ __device__ __forceinline__ float colsum32(float (&v)[32]) {
 
 // EW = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating 64-column block pairs) for the
 // short-K wide-N layers whose epilogue is longer than their MMA loop
-template <int BN, int PW, int MT, int SPLIT, int EW>
+// F = compile-time feature set of the epilogue (the epilogue shares the instruction cache with the producer / MMA warps:
+// the lean production variant must not carry the rarely used paths -- measured 10-25 % on the 3x3 layers):
+//   0 production: bf16 (or unstaged fp32) output, bias / ReLU / bf16 addend / forward BatchNorm statistics / pixel shuffle
+//   1 + fused BatchNorm-backward reduce (bnr_*)          2 fp32-grade paths: staged fp32 store + statistics, fp32 addend
+template <int BN, int PW, int MT, int SPLIT, int EW, int F>
 __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
                                                                   IgemmParams p) {
   using C = Cfg<BN, MT, EW>;
@@ -119,6 +142,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
   float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [4 warps][4 KB] store staging slabs
   float* s_stat = s_tr + EW * 1024;                                                      // [2][BN] per-channel sum / sumsq (smem atomics)
   float* s_bias = s_stat + 2 * BN;                                                // [BN] bias of this CTA's column block
+  float* s_bnc = s_bias + BN;                                                     // [4][BN] fused BN-backward: scale, shift, mean, invstd
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,6 +168,11 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
   if (p.bias)
     for (int c = threadIdx.x; c < BN; c += blockDim.x) s_bias[c] = p.bias[blockIdx.y * BN + c];
   for (int c = threadIdx.x; c < 2 * BN; c += blockDim.x) s_stat[c] = 0.f;
+  if (F == 1)
+    for (int c = threadIdx.x; c < BN; c += blockDim.x) {
+      const int gc = blockIdx.y * BN + c;
+      s_bnc[c] = p.bnr_scale[gc]; s_bnc[BN + c] = p.bnr_shift[gc]; s_bnc[2 * BN + c] = p.bnr_mean[gc]; s_bnc[3 * BN + c] = p.bnr_invstd[gc];
+    }
   pnx::tc_fence_before();
   __syncthreads();
   pnx::tc_fence_after();
@@ -316,7 +345,11 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
     float* st_sq = s_stat + BN;
     uint8_t* slab = reinterpret_cast<uint8_t*>(s_tr) + (warp - kEpiWarp0) * 4096;
     const int hw = p.Hout * p.Wout;
-    const bool staged = (BN % 64 == 0) && !p.shuffle;
+    // the staged (coalesced) store also serves the ConvTranspose2d pixel-shuffle when a 64-column pair of blocks is one
+    // output pixel (BN % 64 == 0, bf16): the 128-byte row of the slab goes to pixel (2y + q/2, 2x + q%2)
+    // F = 0 / 1 only ever see bf16 outputs (the host dispatch sends fp32 outputs to F = 2): always staged when BN % 64 == 0
+    constexpr bool kHasUnstaged = (BN % 64 != 0) || F == 2;   // the per-thread store path is compiled only where reachable
+    const bool staged = (BN % 64 == 0) && !(F == 2 && p.shuffle);
     for (int pt = blockIdx.x; pt < num_pairs; pt += gridDim.x) {
       while (!pnx::mbar_try_wait(&tfull[acc], acc_phase)) __nanosleep(64);  // leave the issue slots to the producers
       pnx::tc_fence_after();
@@ -369,7 +402,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
             }
           }
         }
-        if (p.addend_f32 && active) {
+        if (F == 2 && p.addend_f32 && active) {
           const float4* ap = reinterpret_cast<const float4*>(p.addend_f32 + (long long)m * p.ld_add + ncol0);
 #pragma unroll
           for (int k = 0; k < kColBlk / 4; ++k) {
@@ -381,7 +414,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
 #pragma unroll
           for (int k = 0; k < kColBlk; ++k) v[k] = fmaxf(v[k], 0.f);
         }
-        if (staged && p.out_fp32) {
+        if (F == 2 && staged) {
           // fp32 output: one 32-column block = [32 rows x 128 B] slab, flushed as full 128-byte lines
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -427,13 +460,71 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
             __syncwarp();
             const int ch = lane & 7;
             const long long row0 = (long long)tile * 128 + quarter * 32;
+            // pixel-shuffle: output row of this lane's own input row m (quadrant q = 64-column pair), fetched by shuffle below
+            long long sh_base = 0;
+            if (p.shuffle) {
+              const int q = (ncol0 - 32) >> 6;
+              sh_base = ((long long)(sh_b * 2 * p.Hout + 2 * sh_y + (q >> 1))) * (2 * p.Wout) + 2 * sh_x + (q & 1);
+            }
+            if (F == 1) {
+              // fused BatchNorm-backward reduce: lane = (row group, 8-channel chunk); gate from raw, g = dy * gate
+              const int c8 = (cb - 1) * 32 + ch * 8;  // first of this lane's 8 columns inside the CTA's column block
+              float sg[8], sgx[8], csc[8], csh[8], cmu[8], cis[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                sg[k] = sgx[k] = 0.f;
+                csc[k] = s_bnc[c8 + k]; csh[k] = s_bnc[BN + c8 + k]; cmu[k] = s_bnc[2 * BN + c8 + k]; cis[k] = s_bnc[3 * BN + c8 + k];
+              }
+              uint4 rws[8];
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {  // the eight raw loads of this lane are in flight together
+                const int row = it * 4 + (lane >> 3);
+                rws[it] = make_uint4(0u, 0u, 0u, 0u);
+                if (row0 + row < p.M) rws[it] = __ldg(reinterpret_cast<const uint4*>(p.bnr_raw + (row0 + row) * p.bnr_ld + n0 + c8));
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int row = it * 4 + (lane >> 3);
+                if (row0 + row < p.M) {
+                  float d[8], rw[8];
+                  unpack_bf16x8(*reinterpret_cast<const uint4*>(slab + row * 128 + ((ch ^ (row & 7)) << 4)), d);
+                  unpack_bf16x8(rws[it], rw);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float g = fmaf(rw[k], csc[k], csh[k]) > 0.f ? d[k] : 0.f;
+                    d[k] = g;
+                    sg[k] += g;
+                    sgx[k] = fmaf(g, (rw[k] - cmu[k]) * cis[k], sgx[k]);
+                  }
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (row0 + row) * p.ldc + (ncol0 - 32) + ch * 8) =
+                      make_uint4(pnx::pack_bf16x2(d[0], d[1]), pnx::pack_bf16x2(d[2], d[3]), pnx::pack_bf16x2(d[4], d[5]), pnx::pack_bf16x2(d[6], d[7]));
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {  // the four lanes that share a channel chunk (lane ^ 8, lane ^ 16)
+                sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], 8);
+                sgx[k] += __shfl_xor_sync(0xffffffffu, sgx[k], 8);
+                sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], 16);
+                sgx[k] += __shfl_xor_sync(0xffffffffu, sgx[k], 16);
+              }
+              if (lane < 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  atomicAdd(&st_sum[c8 + k], sg[k]);
+                  atomicAdd(&st_sq[c8 + k], sgx[k]);
+                }
+              }
+            } else {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = it * 4 + (lane >> 3);
+              const long long orow = p.shuffle ? __shfl_sync(0xffffffffu, sh_base, row) : row0 + row;
               if (row0 + row < p.M) {
                 const uint4 val = *reinterpret_cast<const uint4*>(slab + row * 128 + ((ch ^ (row & 7)) << 4));
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (row0 + row) * p.ldc + (ncol0 - 32) + ch * 8) = val;
+                const int ocol = p.shuffle ? 0 : ncol0 - 32;
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + ocol + ch * 8) = val;
               }
+            }
             }
             if (p.stats) {
               const int nrows = (int)min((long long)32, (long long)p.M - row0);  // rows past M hold bias-only garbage
@@ -462,7 +553,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
             }
             __syncwarp();
           }
-        } else {
+        } else if constexpr (kHasUnstaged) {
           if (!p.out_fp32) {
 #pragma unroll
             for (int k = 0; k < kColBlk; ++k) v[k] = pnx::bf16_round(v[k]);
@@ -518,6 +609,12 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
         atomicAdd(&p.stats[ch], (double)st_sum[c]);
         atomicAdd(&p.stats[p.stats_C + ch], (double)st_sq[c]);
       }
+    } else if (F == 1) {
+      named_bar_sync(2, EW * 32);
+      for (int c = threadIdx.x - (kThreadsTotal - EW * 32); c < BN; c += EW * 32) {
+        atomicAdd(&p.bnr_red[n0 + c], (double)st_sum[c]);
+        atomicAdd(&p.bnr_red[p.bnr_C + n0 + c], (double)st_sq[c]);
+      }
     }
   }
 
@@ -527,12 +624,12 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
   if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int BN, int PW, int MT, int SPLIT, int EW>
-int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmParams& p, int n_blocks, int sm_count,
-                 cudaStream_t stream) {
+template <int BN, int PW, int MT, int SPLIT, int EW, int F>
+int launch_igemm_f(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmParams& p, int n_blocks, int sm_count,
+                   cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, PW, MT, SPLIT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PNX_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, PW, MT, SPLIT, EW, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg<BN, MT, EW>::kSmem));
     attr_set = true;
   }
@@ -542,9 +639,19 @@ int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmPa
   if (gx < 1) gx = 1;
   if (gx > num_pairs) gx = num_pairs;
   dim3 grid(gx, n_blocks);
-  igemm_kernel<BN, PW, MT, SPLIT, EW><<<grid, 64 + PW * 32 + 64 + EW * 32, Cfg<BN, MT, EW>::kSmem, stream>>>(wmap, amap, p);
+  igemm_kernel<BN, PW, MT, SPLIT, EW, F><<<grid, 64 + PW * 32 + 64 + EW * 32, Cfg<BN, MT, EW>::kSmem, stream>>>(wmap, amap, p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
+}
+
+template <int BN, int PW, int MT, int SPLIT, int EW>
+int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmParams& p, int n_blocks, int sm_count,
+                 cudaStream_t stream) {
+  if (p.bnr_raw) {
+    if constexpr (BN % 64 == 0) return launch_igemm_f<BN, PW, MT, SPLIT, EW, 1>(wmap, amap, p, n_blocks, sm_count, stream);
+  }
+  if (p.out_fp32 || p.addend_f32) return launch_igemm_f<BN, PW, MT, SPLIT, EW, 2>(wmap, amap, p, n_blocks, sm_count, stream);
+  return launch_igemm_f<BN, PW, MT, SPLIT, EW, 0>(wmap, amap, p, n_blocks, sm_count, stream);
 }
 
 }  // namespace
@@ -555,7 +662,9 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
                          int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
                          double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
                          long long ld_add, int nseg, long long a_lo_off, long long seg_code, int addend_fp32,
-                         int sm_count, cudaStream_t stream) {
+                         const void* bnr_raw, long long bnr_ld, const float* bnr_scale, const float* bnr_shift,
+                         const float* bnr_mean, const float* bnr_invstd, double* bnr_red, int bnr_C, int sm_count,
+                         cudaStream_t stream) {
   PNX_CHECK_ARG(M >= 0, "M");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(taps >= 1 && taps <= 9, "taps in [1,9]");
@@ -596,6 +705,13 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   PNX_CHECK_ARG(a_pieces == 1 || (a_lo_off >= Cin && a_lo_off % 64 == 0 && (a_pieces - 1) * a_lo_off + Cin <= lda), "split mode: a_lo_off");
   PNX_CHECK_ARG(!addend_fp32 || out_fp32, "an fp32 addend needs an fp32 output");
   p.nseg = nseg; p.a_lo_off = (int)a_lo_off; p.seg_code = (unsigned long long)seg_code;
+  p.bnr_raw = (const __nv_bfloat16*)bnr_raw; p.bnr_ld = bnr_ld; p.bnr_scale = bnr_scale; p.bnr_shift = bnr_shift;
+  p.bnr_mean = bnr_mean; p.bnr_invstd = bnr_invstd; p.bnr_red = bnr_red; p.bnr_C = bnr_C;
+  if (bnr_raw) {
+    PNX_CHECK_ARG(!out_fp32 && !shuffle && !stats && block_n % 64 == 0, "fused BN-backward reduce: bf16 staged store without forward statistics");
+    PNX_CHECK_ARG(bnr_scale && bnr_shift && bnr_mean && bnr_invstd && bnr_red && bnr_C == Cout && bnr_ld % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(bnr_raw) & 15) == 0, "fused BN-backward reduce: arguments");
+  }
   const int wcols = w_pieces * Cin;  // split mode: W rows are [piece 0 | piece 1 | ...]
   CUtensorMap wmap;
   int rc = pnx_encode_tmap_2d_bf16(&wmap, Wpacked, (uint64_t)taps * Cout, (uint64_t)wcols, (uint64_t)wcols * 2,
@@ -620,6 +736,8 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
     case 256:
       // (MT = 2, two tiles per weight stage, measured slower on every layer of the step: exposed epilogue of the single
       // accumulator set and only 3 stages -- not instantiated)
+      // short K (1x1 convs, ConvTranspose2d): the 256-column epilogue outlasts the <= 4-stage MMA loop -> 8 epilogue warps
+      if (taps * (Cin / 64) * nseg <= 4) return launch_igemm<256, 4, 1, 2, 8>(wmap, amap, p, n_blocks, sm_count, stream);
       return launch_igemm<256, 8, 1, 4, 4>(wmap, amap, p, n_blocks, sm_count, stream);
     default:
       pnx_set_error("pnx_igemm: unsupported block_n %d (16/32/64/128/192/256)", block_n);

@@ -24,7 +24,23 @@ struct WinParams {
   int stats_C;
   int relu;
   int base_off_mode;        // 1: descriptor base offset = (start >> 7) & 7 (PTX ISA), 0: leave 0
+  // fused BatchNorm-backward reduction (see igemm.cu IgemmParams): this conv produces dy of y = relu(bn(raw))
+  const __nv_bfloat16* bnr_raw;
+  long long bnr_ld;
+  const float* bnr_scale; const float* bnr_shift; const float* bnr_mean; const float* bnr_invstd;
+  double* bnr_red;
+  int bnr_C;
 };
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
 
 constexpr uint32_t kWinRows = 130;
 constexpr uint32_t kWinBytes = kWinRows * 128;     // bytes written by one window load
@@ -38,7 +54,7 @@ struct WCfgWin {
   static constexpr uint32_t kBTap = BN * 128;
   static constexpr uint32_t kWBytes = WS ? 9 * kBTap : 0;
   static constexpr uint32_t kStageBytes = WS ? kWinSlot : kWinSlot + 3 * kBTap;
-  static constexpr int kFixed = 1024 + 256 + 8 * 4096 + 3 * BN * 4;
+  static constexpr int kFixed = 1024 + 256 + 8 * 4096 + 3 * BN * 4 + 4 * BN * 4;
   static constexpr int kStagesRaw = WS ? (227 * 1024 - kFixed - (int)kWBytes) / (int)kStageBytes : (180 * 1024) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr size_t kSmem = kFixed + kWBytes + (size_t)kStages * kStageBytes;
@@ -75,6 +91,7 @@ __global__ void __launch_bounds__(320, 1) igemm_win_kernel(const __grid_constant
   uint8_t* s_slab = reinterpret_cast<uint8_t*>(full) + 256;
   float* s_stat = reinterpret_cast<float*>(s_slab + 8 * 4096);
   float* s_bias = s_stat + 2 * BN;
+  float* s_bnc = s_bias + BN;   // [4][BN] fused BN-backward: scale, shift, mean, invstd of this CTA's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && pnx::elect_one()) {
@@ -95,6 +112,11 @@ __global__ void __launch_bounds__(320, 1) igemm_win_kernel(const __grid_constant
   if (p.bias)
     for (int c = threadIdx.x; c < BN; c += blockDim.x) s_bias[c] = p.bias[blockIdx.y * BN + c];
   for (int c = threadIdx.x; c < 2 * BN; c += blockDim.x) s_stat[c] = 0.f;
+  if (p.bnr_raw)
+    for (int c = threadIdx.x; c < BN; c += blockDim.x) {
+      const int gc = blockIdx.y * BN + c;
+      s_bnc[c] = p.bnr_scale[gc]; s_bnc[BN + c] = p.bnr_shift[gc]; s_bnc[2 * BN + c] = p.bnr_mean[gc]; s_bnc[3 * BN + c] = p.bnr_invstd[gc];
+    }
   pnx::tc_fence_before();
   __syncthreads();
   pnx::tc_fence_after();
@@ -209,6 +231,55 @@ __global__ void __launch_bounds__(320, 1) igemm_win_kernel(const __grid_constant
         if (half == 1) {
           __syncwarp();
           const int ch = lane & 7;
+          if (p.bnr_raw) {
+            // fused BatchNorm-backward reduce (igemm.cu): gate from raw, store g = dy * gate, accumulate sum g / sum g*xhat
+            const int c8 = (cb - 1) * 32 + ch * 8;
+            float sg[8], sgx[8], csc[8], csh[8], cmu[8], cis[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              sg[k] = sgx[k] = 0.f;
+              csc[k] = s_bnc[c8 + k]; csh[k] = s_bnc[BN + c8 + k]; cmu[k] = s_bnc[2 * BN + c8 + k]; cis[k] = s_bnc[3 * BN + c8 + k];
+            }
+            uint4 rws[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + (lane >> 3);
+              rws[it] = make_uint4(0u, 0u, 0u, 0u);
+              if (row < nrows) rws[it] = __ldg(reinterpret_cast<const uint4*>(p.bnr_raw + (row0 + quarter * 32 + row) * p.bnr_ld + n0 + c8));
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + (lane >> 3);
+              if (row < nrows) {
+                float d[8], rw[8];
+                unpack_bf16x8(*reinterpret_cast<const uint4*>(slab + row * 128 + ((ch ^ (row & 7)) << 4)), d);
+                unpack_bf16x8(rws[it], rw);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float g = fmaf(rw[k], csc[k], csh[k]) > 0.f ? d[k] : 0.f;
+                  d[k] = g;
+                  sg[k] += g;
+                  sgx[k] = fmaf(g, (rw[k] - cmu[k]) * cis[k], sgx[k]);
+                }
+                *reinterpret_cast<uint4*>(p.out + (row0 + quarter * 32 + row) * p.ldc + n0 + (cb - 1) * 32 + ch * 8) =
+                    make_uint4(pnx::pack_bf16x2(d[0], d[1]), pnx::pack_bf16x2(d[2], d[3]), pnx::pack_bf16x2(d[4], d[5]), pnx::pack_bf16x2(d[6], d[7]));
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], 8);
+              sgx[k] += __shfl_xor_sync(0xffffffffu, sgx[k], 8);
+              sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], 16);
+              sgx[k] += __shfl_xor_sync(0xffffffffu, sgx[k], 16);
+            }
+            if (lane < 8) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                atomicAdd(&s_stat[c8 + k], sg[k]);
+                atomicAdd(&s_stat[BN + c8 + k], sgx[k]);
+              }
+            }
+          } else {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int row = it * 4 + (lane >> 3);
@@ -216,6 +287,7 @@ __global__ void __launch_bounds__(320, 1) igemm_win_kernel(const __grid_constant
               const uint4 val = *reinterpret_cast<const uint4*>(slab + row * 128 + ((ch ^ (row & 7)) << 4));
               *reinterpret_cast<uint4*>(p.out + (row0 + quarter * 32 + row) * p.ldc + n0 + (cb - 1) * 32 + ch * 8) = val;
             }
+          }
           }
           if (p.stats) {
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -256,6 +328,12 @@ __global__ void __launch_bounds__(320, 1) igemm_win_kernel(const __grid_constant
         atomicAdd(&p.stats[n0 + c], (double)s_stat[c]);
         atomicAdd(&p.stats[p.stats_C + n0 + c], (double)s_stat[BN + c]);
       }
+    } else if (p.bnr_raw) {
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      for (int c = threadIdx.x - 64; c < BN; c += 256) {
+        atomicAdd(&p.bnr_red[n0 + c], (double)s_stat[c]);
+        atomicAdd(&p.bnr_red[p.bnr_C + n0 + c], (double)s_stat[BN + c]);
+      }
     }
   }
   pnx::tc_fence_before();
@@ -289,7 +367,9 @@ int pnx_encode_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t d
 // Contract: include/pnx.h (pnx_conv3x3_win).
 extern "C" int pnx_conv3x3_win(const void* A, long long lda, int B, int H, int W, int Cin, const void* Wpacked, int Cout,
                                int block_n, void* out, long long ldc, const float* bias, double* stats, int stats_C,
-                               int relu, int base_off_mode, int sm_count, cudaStream_t stream) {
+                               int relu, int base_off_mode, const void* bnr_raw, long long bnr_ld, const float* bnr_scale,
+                               const float* bnr_shift, const float* bnr_mean, const float* bnr_invstd, double* bnr_red,
+                               int bnr_C, int sm_count, cudaStream_t stream) {
   PNX_CHECK_ARG(B > 0 && H > 0 && W > 0, "shape");
   PNX_CHECK_ARG(Cin % 64 == 0 && Cout % block_n == 0, "Cin % 64, Cout % block_n");
   PNX_CHECK_ARG(lda % 8 == 0 && ldc % 8 == 0, "lda/ldc % 8");
@@ -300,6 +380,11 @@ extern "C" int pnx_conv3x3_win(const void* A, long long lda, int B, int H, int W
   p.Cin = Cin; p.Cout_total = Cout;
   p.out = (__nv_bfloat16*)out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.stats_C = stats_C; p.relu = relu;
   p.base_off_mode = base_off_mode;
+  p.bnr_raw = (const __nv_bfloat16*)bnr_raw; p.bnr_ld = bnr_ld; p.bnr_scale = bnr_scale; p.bnr_shift = bnr_shift;
+  p.bnr_mean = bnr_mean; p.bnr_invstd = bnr_invstd; p.bnr_red = bnr_red; p.bnr_C = bnr_C;
+  if (bnr_raw)
+    PNX_CHECK_ARG(!stats && bnr_scale && bnr_shift && bnr_mean && bnr_invstd && bnr_red && bnr_C == Cout && bnr_ld % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(bnr_raw) & 15) == 0, "fused BN-backward reduce: arguments");
   CUtensorMap amap, wmap;
   const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)lda * 2, (uint64_t)W * lda * 2, (uint64_t)H * W * lda * 2};

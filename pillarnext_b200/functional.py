@@ -161,13 +161,45 @@ def convT_spec(B, H, W):
                     d_taps=4, shuffle=True)
 
 
+# ------------------------------------------------------------------------------------------- fused BN-backward reduce
+class BNInfo:
+    """Link between a BatchNorm(+ReLU) layer and the GEMM that produces the gradient of its output.  BNActFn.forward
+    fills the forward quantities; the consumer's backward passes them to the GEMM epilogue (pnx_igemm / pnx_conv3x3_win
+    `bnr_*` arguments), which gates dy with the ReLU mask and accumulates the two per-channel sums into `red`;
+    BNActFn.backward then only runs the apply pass."""
+    __slots__ = ("raw", "scale", "shift", "mean", "invstd", "C", "M", "red", "fused")
+
+    def __init__(self):
+        self.raw = self.red = None
+        self.fused = False
+
+
+# The fused reduce adds ~7 instructions per output element to the GEMM epilogue.  Measured on the B200 (round 2): for the
+# 3x3 convolutions (K = 9 * C >= 576 MMA steps per tile) it hides under the MMA loop (+4 % on the head's 384 -> 64 data
+# gradient) and removes a full sweep over dy and raw; for the thin GEMMs (the head's final-conv data gradient, K = 192,
+# and the ConvTranspose2d one, K = 256) the epilogue is already the bottleneck and the fusion costs more than the
+# separate pass (0.99 -> 3.6 ms per step) -- so it is applied only above this K.
+FUSE_BN_REDUCE_MIN_K = 512
+
+
+def _claim_bn_reduce(info, M, C, k_total):
+    """The BNInfo to hand to the GEMM producing a [M, C] gradient (K = k_total), or None when the fused path does not
+    apply.  All consumers of one BatchNorm output must make the same decision: they share the shape, so they do."""
+    if info is None or info.raw is None or info.C != C or info.M != M or not ops.bnr_eligible(C) or k_total < FUSE_BN_REDUCE_MIN_K:
+        return None
+    if info.red is None:
+        info.red = torch.zeros(2 * C, dtype=torch.float64, device=info.raw.device)
+    info.fused = True
+    return info
+
+
 # ------------------------------------------------------------------------------------------- conv
 class ConvFn(torch.autograd.Function):
     """out = conv(x; w) (+bias) (relu) through pnx_igemm; optional BatchNorm statistics of the output.
     x bf16 [M_in, >=Cin]; returns (out [M_out(*4 if shuffle), Cout], stats fp64 [2*Cs] or empty)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, spec, layout, want_stats, out_fp32, relu, bias_feeds_bn):
+    def forward(ctx, x, w, bias, spec, layout, want_stats, out_fp32, relu, bias_feeds_bn, bn_src=None):
         shape = tuple(w.shape)
         if layout.kind == "dense":
             cout, cin = shape[0], shape[1]
@@ -202,6 +234,7 @@ class ConvFn(torch.autograd.Function):
         ctx.has_bias, ctx.relu, ctx.out_fp32 = bias is not None, relu, out_fp32
         ctx.bias_feeds_bn = bool(bias_feeds_bn)
         ctx.split = split
+        ctx.bn_src = bn_src if (bn_src is not None and not split) else None
         ctx.mark_non_differentiable(stats)
         return out, stats
 
@@ -237,7 +270,7 @@ class ConvFn(torch.autograd.Function):
                 g = torch.zeros(spec.taps, cout, cin, dtype=torch.float32, device=dy.device)
                 ops.wgrad_split(dy, cout, cout, x, xlo, cin, spec.M_out, spec.taps, g, nbr=spec.nbr, dense=spec.dense)
             dw = layout.unpack_grad(g, shape)
-        return dx, dw, dbias, None, None, None, None, None, None
+        return dx, dw, dbias, None, None, None, None, None, None, None
 
     @staticmethod
     def backward(ctx, dout, _dstats):
@@ -273,11 +306,12 @@ class ConvFn(torch.autograd.Function):
             if cpad != cout:
                 wd = torch.nn.functional.pad(wd, (0, cpad - cout))
             dx = torch.empty(spec.M_in, cin, dtype=torch.bfloat16, device=dy.device)
+            bnr = _claim_bn_reduce(ctx.bn_src, spec.M_in, cin, wd.shape[0] * cpad) if x.shape[1] == cin else None
             if layout.kind == "dense" and spec.d_nbr is None and ops.win_eligible(spec.d_dense, cin, cpad):
                 H_, W_ = spec.d_dense[0], spec.d_dense[1]
-                ops.conv3x3_win(dy, spec.M_in // (H_ * W_), H_, W_, wd, cpad, cin, dx)
+                ops.conv3x3_win(dy, spec.M_in // (H_ * W_), H_, W_, wd, cpad, cin, dx, bnr=bnr)
             else:
-                ops.igemm(dy, spec.M_in, wd, wd.shape[0], cpad, cin, dx, nbr=spec.d_nbr, dense=spec.d_dense)
+                ops.igemm(dy, spec.M_in, wd, wd.shape[0], cpad, cin, dx, nbr=spec.d_nbr, dense=spec.d_dense, bnr=bnr)
             if x.shape[1] != cin:                                   # x was a column slice of a wider buffer
                 full = torch.zeros(x.shape[0], x.shape[1], dtype=torch.bfloat16, device=dy.device)
                 full[:, :cin] = dx
@@ -294,11 +328,13 @@ class ConvFn(torch.autograd.Function):
                 if cpad != cout:
                     g = g[:, :cout].contiguous()
             dw = layout.unpack_grad(g, shape)
-        return dx, dw, dbias, None, None, None, None, None, None
+        return dx, dw, dbias, None, None, None, None, None, None, None
 
 
-def conv(x, w, bias, spec, layout, want_stats=False, out_fp32=False, relu=False, bias_feeds_bn=False):
-    return ConvFn.apply(x, w, bias, spec, layout, want_stats, out_fp32, relu, bias_feeds_bn)
+def conv(x, w, bias, spec, layout, want_stats=False, out_fp32=False, relu=False, bias_feeds_bn=False, bn_src=None):
+    """bn_src: the BNInfo of `x` when x = relu(bn(.)) is consumed by this convolution ONLY (or only by convolutions that
+    all pass it): the data-gradient GEMM then also performs the reduce pass of that BatchNorm's backward."""
+    return ConvFn.apply(x, w, bias, spec, layout, want_stats, out_fp32, relu, bias_feeds_bn, bn_src)
 
 
 # ------------------------------------------------------------------------------------------- batch norm
@@ -319,7 +355,7 @@ class BNActFn(torch.autograd.Function):
     pnx_sync (SyncBatchNorm semantics, reference tools/train.py:55-56): statistics all-reduced over ranks."""
 
     @staticmethod
-    def forward(ctx, x_raw, stats, gamma, beta, residual, bn, relu, count):
+    def forward(ctx, x_raw, stats, gamma, beta, residual, bn, relu, count, info=None):
         M, C = x_raw.shape
         if bn.training:
             if _sync_enabled(bn):
@@ -343,6 +379,11 @@ class BNActFn(torch.autograd.Function):
             ops.bn_apply(x_raw, M, C, scale, shift, y, res=residual, relu=relu)
         ctx.save_for_backward(x_raw, y, gamma, mean, invstd, scale, shift)
         ctx.relu, ctx.count, ctx.has_res, ctx.sync, ctx.training = relu, count, residual is not None, _sync_enabled(bn), bn.training
+        ctx.info = None
+        if info is not None and bn.training and relu and residual is None and not ctx.split:
+            info.raw, info.scale, info.shift, info.mean, info.invstd, info.C, info.M = x_raw, scale, shift, mean, invstd, C, M
+            info.red, info.fused = None, False
+            ctx.info = info
         return y
 
     @staticmethod
@@ -364,7 +405,7 @@ class BNActFn(torch.autograd.Function):
                                dxs, C, dres=dres, dres_lo=C)
         dx = ops.rows_merge(dxs, C, C)          # x_raw is an fp32 [M, C] tensor: its gradient has the same shape / dtype
         r = local.float()
-        return dx, None, r[C:], r[:C], dres, None, None, None
+        return dx, None, r[C:], r[:C], dres, None, None, None, None
 
     @staticmethod
     def backward(ctx, dy):
@@ -377,30 +418,40 @@ class BNActFn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty(M, C, dtype=torch.bfloat16, device=dy.device)
         dres = torch.empty(M, C, dtype=torch.bfloat16, device=dy.device) if ctx.has_res else None
-        if not ctx.training:
-            raise RuntimeError("pillarnext_b200: backward through eval-mode BatchNorm is not supported")
-        if ctx.sync:
-            red = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
-            from ._lib import check, lib, ptr, stream
-            check(lib().pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), ptr(y), y.stride(0), ptr(x_raw), x_raw.stride(0), M, C,
-                                          ptr(mean), ptr(invstd), 1 if ctx.relu else 0, None, None, ptr(red), stream()))
-            local = red.clone()
-            dist.all_reduce(red)
-            check(lib().pnx_bn_bwd_apply(ptr(dy), dy.stride(0), ptr(y), y.stride(0), ptr(x_raw), x_raw.stride(0), M, C,
-                                         ptr(mean), ptr(invstd), ptr(gamma), ptr(red), float(max(ctx.count, 1)),
-                                         1 if ctx.relu else 0, None, None, ptr(dx), dx.stride(0), ptr(dres) if dres is not None else None,
-                                         dres.stride(0) if dres is not None else 8, 0, stream()))
-            red = local
+        from ._lib import check, lib, ptr, stream
+        info = ctx.info
+        fused = info is not None and info.fused
+        # without a residual the ReLU mask is recomputed from x_raw (one row-matrix read less per pass)
+        ysrc = y if ctx.has_res else None
+        yp, ys = (ptr(ysrc), ysrc.stride(0)) if ysrc is not None else (None, 8)
+        if fused:
+            local = info.red          # the reduce pass ran in the epilogue of the GEMM that produced dy (= gated g)
+            info.red, info.fused = None, False
         else:
-            # without a residual the ReLU mask is recomputed from x_raw (one row-matrix read less per pass)
-            red = ops.bn_bwd(dy, y if ctx.has_res else None, x_raw, M, C, mean, invstd, gamma, ctx.count, ctx.relu, dx,
-                             dres=dres, affine=(scale, shift))
-        r = red.float()
-        return dx, None, r[C:], r[:C], dres, None, None, None
+            local = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
+            ops._count(1)
+            check(lib().pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), yp, ys, ptr(x_raw), x_raw.stride(0), M, C, ptr(mean), ptr(invstd),
+                                          1 if ctx.relu else 0, ptr(scale), ptr(shift), ptr(local), stream()))
+        red = local
+        if ctx.sync:                  # SyncBatchNorm: the two sums over all ranks (dgamma / dbeta stay local, DDP averages them)
+            red = local.clone()
+            dist.all_reduce(red)
+        ops._count(1)
+        check(lib().pnx_bn_bwd_apply(ptr(dy), dy.stride(0), yp, ys, ptr(x_raw), x_raw.stride(0), M, C, ptr(mean), ptr(invstd),
+                                     ptr(gamma), ptr(red), float(max(ctx.count, 1)), 1 if (ctx.relu and not fused) else 0,
+                                     ptr(scale), ptr(shift), ptr(dx), dx.stride(0), ptr(dres) if dres is not None else None,
+                                     dres.stride(0) if dres is not None else 8, 0, stream()))
+        r = local.float()
+        return dx, None, r[C:], r[:C], dres, None, None, None, None
 
 
-def bn_act(x_raw, stats, bn, relu=True, residual=None, count=None):
-    return BNActFn.apply(x_raw, stats, bn.weight, bn.bias, residual, bn, relu, x_raw.shape[0] if count is None else count)
+def bn_info():
+    return BNInfo()
+
+
+def bn_act(x_raw, stats, bn, relu=True, residual=None, count=None, info=None):
+    """info: a BNInfo to fill (see conv(bn_src=...)): pass it when the output has a single, convolution consumer."""
+    return BNActFn.apply(x_raw, stats, bn.weight, bn.bias, residual, bn, relu, x_raw.shape[0] if count is None else count, info)
 
 
 # ------------------------------------------------------------------------------------------- fp32 <-> split rows
@@ -672,9 +723,10 @@ class HeadFinalConvFn(torch.autograd.Function):
     NZ = 192   # 9*16 = 144 GEMM columns, padded to a tile / K multiple
 
     @staticmethod
-    def forward(ctx, y, wb, bias, B, H, W):
+    def forward(ctx, y, wb, bias, B, H, W, bn_src=None):
         from ._lib import check, lib, ptr, stream
         split = _split()
+        ctx.bn_src = bn_src if not split else None
         M, cin = y.shape[0], y.shape[1] // (_P() if split else 1)
         assert wb.shape[0] == 16 and wb.shape[2] == 3
         with torch.no_grad():
@@ -711,14 +763,15 @@ class HeadFinalConvFn(torch.autograd.Function):
             g = torch.zeros(1, cin, NZ, dtype=torch.float32, device=dout.device)
             ops.wgrad_split(y, cin, cin, dZ, NZ, NZ, M, 1, g)
             dwb = g[0, :, :144].reshape(cin, 3, 3, 16).permute(3, 0, 1, 2).contiguous()
-            return dy, dwb, dbias, None, None, None
+            return dy, dwb, dbias, None, None, None, None
         dZ = torch.empty(M, NZ, dtype=torch.bfloat16, device=dout.device)
         ops._count(1)
         check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), NZ, NZ, 0, stream()))
         dbias = dout.sum(0)
         dy = torch.empty(M, cin, dtype=torch.bfloat16, device=dout.device)
-        ops.igemm(dZ, M, wz.transpose(1, 2).contiguous(), 1, NZ, cin, dy)          # dy = dZ . Wz
+        ops.igemm(dZ, M, wz.transpose(1, 2).contiguous(), 1, NZ, cin, dy,         # dy = dZ . Wz (+ the sibling BN's reduce pass)
+                  bnr=_claim_bn_reduce(ctx.bn_src, M, cin, NZ))
         g = torch.zeros(1, cin, NZ, dtype=torch.float32, device=dout.device)
         ops.wgrad(y, cin, dZ, NZ, M, 1, g)                                        # [1, Cin, NZ] = y^T . dZ
         dwb = g[0, :, :144].reshape(cin, 3, 3, 16).permute(3, 0, 1, 2).contiguous()
-        return dy, dwb, dbias, None, None, None
+        return dy, dwb, dbias, None, None, None, None

@@ -150,9 +150,9 @@ class SparseConvBlock(nn.Module):
         self.act = nn.ReLU()
         self.stride, self.subm = stride, (stride == 1 and use_subm)
 
-    def run(self, x, spec):
+    def run(self, x, spec, info=None):
         raw, stats = Fn.conv(x, self.conv.weight, None, spec, Fn.WLayout("sp"), want_stats=True)
-        return Fn.bn_act(raw, stats, self.norm, relu=True)
+        return Fn.bn_act(raw, stats, self.norm, relu=True, info=info)
 
 
 class SparseBasicBlock(nn.Module):
@@ -167,8 +167,9 @@ class SparseBasicBlock(nn.Module):
 
     def run(self, x, spec):
         x, idt = Fn.fanout(x)
-        out = self.block1.run(x, spec)
-        raw, stats = Fn.conv(out, self.conv2.weight, None, spec, Fn.WLayout("sp"), want_stats=True)
+        info = Fn.bn_info()                     # block1's output feeds conv2 only: conv2's dgrad does block1's BN reduce
+        out = self.block1.run(x, spec, info)
+        raw, stats = Fn.conv(out, self.conv2.weight, None, spec, Fn.WLayout("sp"), want_stats=True, bn_src=info)
         return Fn.bn_act(raw, stats, self.norm2, relu=True, residual=idt)    # relu(bn(conv) + identity)
 
 
@@ -251,13 +252,15 @@ class ConvBlock(nn.Module):
         self.is_transpose = conv_layer is nn.ConvTranspose2d
         self.kernel_size = kernel_size
 
-    def run(self, x, B, H, W):
+    def run(self, x, B, H, W, bn_src=None, info=None):
+        """bn_src: BNInfo of x (this conv is the only kind of consumer of x); info: BNInfo to fill for this block's output."""
         if self.is_transpose:
-            raw, stats = Fn.conv(x, self.conv.conv.weight, None, Fn.convT_spec(B, H, W), Fn.WLayout("convT"), want_stats=True)
+            raw, stats = Fn.conv(x, self.conv.conv.weight, None, Fn.convT_spec(B, H, W), Fn.WLayout("convT"), want_stats=True,
+                                 bn_src=bn_src)
         else:
             raw, stats = Fn.conv(x, self.conv.conv.weight, None, Fn.dense_spec(B, H, W, self.kernel_size),
-                                 Fn.WLayout("dense"), want_stats=True)
-        return Fn.bn_act(raw, stats, self.norm, relu=True)
+                                 Fn.WLayout("dense"), want_stats=True, bn_src=bn_src)
+        return Fn.bn_act(raw, stats, self.norm, relu=True, info=info)
 
 
 class BasicBlock(nn.Module):
@@ -297,8 +300,9 @@ class ASPPNeck(nn.Module):
         rows, B, H, W = _to_rows(x)
         C = self.in_channels
         rows, idt = Fn.fanout(rows)
-        o = self.pre_conv.block1.run(rows, B, H, W)
-        o = self.pre_conv.block2.run(o, B, H, W)
+        info = Fn.bn_info()
+        o = self.pre_conv.block1.run(rows, B, H, W, info=info)
+        o = self.pre_conv.block2.run(o, B, H, W, bn_src=info)
         cat = Fn.ASPPBranchesFn.apply(o, idt, self.conv1x1.weight, self.weight, B, H, W)
         y = self.post_conv.run(cat, B, H, W)
         if Fn.get_precision() == "split":
@@ -355,11 +359,13 @@ class SepHead(nn.Module):
             bn.running_var.copy_(torch.cat([getattr(self, n)[1].running_var for n in names]))
         return bn
 
-    def run(self, x, B, H, W):
+    def run(self, x, B, H, W, bn_src=None):
         names = list(self.heads.keys())
         hc = self.head_conv
+        info_x = None
         if self.stride > 1:
-            x = self.deblock.run(x, B, H, W)
+            info_x = Fn.bn_info()
+            x = self.deblock.run(x, B, H, W, bn_src=bn_src, info=info_x)
             H, W = 2 * H, 2 * W
         wa = torch.cat([getattr(self, n)[0].weight for n in names], 0)
         ba = torch.cat([getattr(self, n)[0].bias for n in names], 0)
@@ -367,8 +373,9 @@ class SepHead(nn.Module):
         be = torch.cat([getattr(self, n)[1].bias for n in names], 0)
         bn = self._cat_bn(names)
         raw, stats = Fn.conv(x, wa, ba, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), want_stats=True,
-                             bias_feeds_bn=self.training)
-        y = Fn.BNActFn.apply(raw, stats, ga, be, None, bn, True, raw.shape[0])
+                             bias_feeds_bn=self.training, bn_src=info_x)
+        info_y = Fn.bn_info()
+        y = Fn.BNActFn.apply(raw, stats, ga, be, None, bn, True, raw.shape[0], info_y)
         if self.training:
             with torch.no_grad():
                 for i, n in enumerate(names):
@@ -390,7 +397,7 @@ class SepHead(nn.Module):
         wb = torch.cat(rows_w + ([wb[tot:]] if npad > tot else []), 0)
         bb = torch.cat(rows_b + ([bb[tot:]] if npad > tot else []), 0)
         if npad == 16:
-            out = Fn.HeadFinalConvFn.apply(y, wb, bb, B, H, W)       # 1x1 GEMM + stencil (gather-free)
+            out = Fn.HeadFinalConvFn.apply(y, wb, bb, B, H, W, info_y)       # 1x1 GEMM + stencil (gather-free)
         else:
             out, _ = Fn.conv(y, wb, bb, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), out_fp32=True)
         out4 = out.view(B, H, W, npad)
@@ -444,8 +451,11 @@ class CenterHead(nn.Module):
         rows, B, H, W = _to_rows(x)
         raw, stats = Fn.conv(rows, self.shared_conv[0].weight, self.shared_conv[0].bias, Fn.dense_spec(B, H, W, 3),
                              Fn.WLayout("dense"), want_stats=True, bias_feeds_bn=self.training)
-        y = Fn.bn_act(raw, stats, self.shared_conv[1], relu=True)
-        return [task.run(yt, B, H, W) for task, yt in zip(self.tasks, Fn.fanout(y, len(self.tasks)))]
+        # y feeds the deblock ConvTranspose2d of every task and nothing else: each of their data-gradient GEMMs gates its
+        # part of dy and accumulates into the same two sums (the reduce is linear), when all tasks have a deblock
+        info = Fn.bn_info() if all(t.stride > 1 for t in self.tasks) else None
+        y = Fn.bn_act(raw, stats, self.shared_conv[1], relu=True, info=info)
+        return [task.run(yt, B, H, W, bn_src=info) for task, yt in zip(self.tasks, Fn.fanout(y, len(self.tasks)))]
 
     def loss(self, example, preds_dicts, **kwargs):
         """centerhead.py:142-229, including the Waymo `iou` head branch (:210-215) on the fused-head path."""

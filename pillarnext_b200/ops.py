@@ -332,6 +332,19 @@ def scatter_dense(feat, lv, channels, canvas=None, gather=False):
 
 
 # --------------------------------------------------------------------------------- implicit GEMM
+def _bnr_args(bnr, cout):
+    """Trailing C-ABI arguments of the fused BatchNorm-backward reduce (None: off).  bnr: functional.BNInfo."""
+    if bnr is None:
+        return (None, 0, None, None, None, None, None, 0)
+    assert bnr.raw.dtype == torch.bfloat16 and bnr.C == cout and bnr.red.numel() == 2 * cout
+    return (ptr(bnr.raw), bnr.raw.stride(0), ptr(bnr.scale), ptr(bnr.shift), ptr(bnr.mean), ptr(bnr.invstd), ptr(bnr.red), cout)
+
+
+def bnr_eligible(cout, out_fp32=False, shuffle=False):
+    """The fused reduce lives in the bf16 staged (coalesced) store of the GEMM epilogues: 64-column granularity."""
+    return (not out_fp32) and (not shuffle) and cout % 64 == 0
+
+
 def pick_block_n(cout):
     for bn in (256, 192, 128, 64, 32, 16):
         if cout % bn == 0:
@@ -340,7 +353,7 @@ def pick_block_n(cout):
 
 
 def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None, dense=None, bias=None, stats=None,
-          stats_mod=None, shuffle=False, relu=False, block_n=None, addend=None, segs=None, a_lo_off=0):
+          stats_mod=None, shuffle=False, relu=False, block_n=None, addend=None, segs=None, a_lo_off=0, bnr=None):
     """out[m, :cout] = sum_t A[nbr(m,t)] @ W[t]^T.  w_packed [taps, cout, cin] bf16.
     dense = (Hout, Wout, Hin, Win, kw, mul, dil, pad) or None.
     segs: fp32-grade split mode -- list of (A piece, W piece) K segments in execution order; A rows hold piece p at
@@ -369,7 +382,7 @@ def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None,
                           ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None, sC,
                           stats_mod or (sC if sC else 1), 1 if shuffle else 0, 1 if relu else 0,
                           ptr(addend) if addend is not None else None, addend.stride(0) if addend is not None else 0,
-                          int(nseg), int(a_lo_off), int(seg_code), add_f32, sm_count(), stream()))
+                          int(nseg), int(a_lo_off), int(seg_code), add_f32, *_bnr_args(bnr, cout), sm_count(), stream()))
     return out
 
 
@@ -390,7 +403,7 @@ def win_eligible(dense, n_cols, k_cols, out_fp32=False, shuffle=False):
     return xc * 128 <= 1.15 * Wo
 
 
-def conv3x3_win(A, B, H, W, w_packed, cin, cout, out, *, bias=None, stats=None, relu=False, block_n=None, base_off=None):
+def conv3x3_win(A, B, H, W, w_packed, cin, cout, out, *, bias=None, stats=None, relu=False, block_n=None, base_off=None, bnr=None):
     """Dense 3x3 'same' conv with TMA-folded im2col (pnx_conv3x3_win). A bf16 rows [B*H*W, >=cin]; out bf16."""
     assert A.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and tuple(w_packed.shape) == (9, cout, cin)
     if block_n:
@@ -405,7 +418,7 @@ def conv3x3_win(A, B, H, W, w_packed, cin, cout, out, *, bias=None, stats=None, 
       check(lib().pnx_conv3x3_win(ptr(A), A.stride(0), B, H, W, cin, ptr(w_packed), cout, bn, ptr(out), out.stride(0),
                                 ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None,
                                 stats.numel() // 2 if stats is not None else 0, 1 if relu else 0,
-                                WIN_BASE_OFF if base_off is None else base_off, sm_count(), stream()))
+                                WIN_BASE_OFF if base_off is None else base_off, *_bnr_args(bnr, cout), sm_count(), stream()))
     return out
 
 
@@ -443,17 +456,23 @@ def bn_apply(x, M, C, scale, shift, y, res=None, relu=True):
     return y
 
 
-def bn_bwd(dy, y, x, M, C, mean, invstd, gamma, count, relu, dx, dres=None, dres_accumulate=False, affine=None):
+def bn_bwd(dy, y, x, M, C, mean, invstd, gamma, count, relu, dx, dres=None, dres_accumulate=False, affine=None, red=None):
     """Returns red (fp64 [2C]: sum g = dbeta, sum g*xhat = dgamma); writes dx (and dres).
-    y=None (no residual): the ReLU mask is recomputed from x with affine=(scale, shift) of the forward."""
-    red = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
+    y=None (no residual): the ReLU mask is recomputed from x with affine=(scale, shift) of the forward.
+    red given: the reduce pass already happened in the epilogue of the GEMM that produced dy (which is then the gated
+    g, so the apply pass runs without a ReLU mask)."""
     L = lib()
     fs, fh = (affine if affine is not None else (None, None))
     yp, ys = (ptr(y), y.stride(0)) if y is not None else (None, 8)
-    _count(2)
-    check(L.pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), yp, ys, ptr(x), x.stride(0), M, C, ptr(mean), ptr(invstd),
-                              1 if relu else 0, ptr(fs) if fs is not None else None, ptr(fh) if fh is not None else None,
-                              ptr(red), stream()))
+    if red is None:
+        red = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
+        _count(1)
+        check(L.pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), yp, ys, ptr(x), x.stride(0), M, C, ptr(mean), ptr(invstd),
+                                  1 if relu else 0, ptr(fs) if fs is not None else None, ptr(fh) if fh is not None else None,
+                                  ptr(red), stream()))
+    else:
+        relu = False
+    _count(1)
     check(L.pnx_bn_bwd_apply(ptr(dy), dy.stride(0), yp, ys, ptr(x), x.stride(0), M, C, ptr(mean), ptr(invstd),
                              ptr(gamma), ptr(red), float(max(count, 1)), 1 if relu else 0,
                              ptr(fs) if fs is not None else None, ptr(fh) if fh is not None else None, ptr(dx),

@@ -288,3 +288,60 @@ def test_fused_center_loss_matches_oracle_directly():
         assert torch.allclose(rets[t]["loc_loss_elem"].cpu(), rets_o[t]["loc_loss_elem"], rtol=1e-4, atol=1e-6)
         g, o = gf[t].cpu().view_as(go[t]), go[t]
         assert (g - o).abs().max().item() < 1e-4 * o.abs().max().item(), (t, (g - o).abs().max().item(), o.abs().max().item())
+
+
+@pytest.mark.parametrize("kind", ["igemm_dense", "win", "convT_fanout"])
+def test_fused_bn_backward_reduce_matches_separate_pass(kind):
+    """The reduce pass of a BatchNorm backward folded into the epilogue of the GEMM that produces dy (pnx_igemm /
+    pnx_conv3x3_win `bnr_*`) against the stand-alone pnx_bn_bwd_reduce: same parameter / input gradients up to the
+    summation order of the two per-channel sums (fp32 partials, fp64 totals)."""
+    torch.manual_seed(3)
+    if kind == "win":
+        B, H, W, c0, c1, c2 = 2, 40, 256, 64, 64, 128        # 3x3 convs 64 -> 64 -> 128 at a width that takes the window kernel
+    else:
+        B, H, W, c0, c1, c2 = 2, 24, 40, 64, 128, 64
+    M = B * H * W
+    x0 = torch.randn(M, c0, device="cuda").bfloat16()
+    w1 = (torch.randn(c1, c0, 3, 3, device="cuda") * 0.05)
+    R = torch.randn(M * (4 if kind == "convT_fanout" else 1), c2, device="cuda").bfloat16()
+    if kind == "convT_fanout":
+        w2s = [torch.randn(c1, c2, 2, 2, device="cuda") * 0.1 for _ in range(3)]
+    else:
+        w2s = [torch.randn(c2, c1, 3, 3, device="cuda") * 0.05]
+
+    base_launches = [0]
+
+    def run(fused):
+        l0 = ops.LAUNCHES
+        x = x0.clone().requires_grad_()
+        wa = w1.clone().requires_grad_()
+        wbs = [w.clone().requires_grad_() for w in w2s]
+        bn = torch.nn.BatchNorm2d(c1).cuda().train()
+        info = Fn.bn_info() if fused else None
+        raw, stats = Fn.conv(x, wa, None, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), want_stats=True)
+        y = Fn.bn_act(raw, stats, bn, relu=True, info=info)
+        tot = 0
+        for wb in wbs:
+            if kind == "convT_fanout":
+                o, _ = Fn.conv(y, wb, None, Fn.convT_spec(B, H, W), Fn.WLayout("convT"), bn_src=info)
+            else:
+                o, _ = Fn.conv(y, wb, None, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), bn_src=info)
+            tot = tot + (o.float() * R.float()).sum()
+        tot.backward()
+        assert (info is None) or (info.red is None and not info.fused)     # consumed by the BatchNorm backward
+        if fused and Fn.FUSE_BN_REDUCE_MIN_K == 0:
+            assert ops.LAUNCHES - l0 < base_launches[0] or base_launches[0] == 0
+        return x.grad.float(), wa.grad, bn.weight.grad, bn.bias.grad, [w.grad for w in wbs]
+
+    prev, Fn.FUSE_BN_REDUCE_MIN_K = Fn.FUSE_BN_REDUCE_MIN_K, 0       # exercise the kernel path for every shape
+    try:
+        a = run(True)
+    finally:
+        Fn.FUSE_BN_REDUCE_MIN_K = prev
+    b = run(False)
+    # fan-out: the separate pass reduces the bf16-rounded SUM of the consumers' gradients, the fused one each part
+    tol = 5e-3 if kind == "convT_fanout" else 1e-4
+    assert rel(a[0], b[0]) < 5e-3 and rel(a[1], b[1]) < 5e-3, (rel(a[0], b[0]), rel(a[1], b[1]))
+    assert rel(a[2], b[2]) < tol and rel(a[3], b[3]) < tol, (rel(a[2], b[2]), rel(a[3], b[3]))
+    for ga, gb in zip(a[4], b[4]):
+        assert rel(ga, gb) < 1e-5                                            # untouched by the fusion (fp32 atomics: order only)
