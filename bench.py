@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the reference's 6 nuScenes / 3 Waymo, docs/RUN.md:9,34)")
     ap.add_argument("--points", type=int, default=0, help="points per frame (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true", help="SyncBatchNorm semantics (reference default sync_batchnorm: True) instead of local BN")
     ap.add_argument("--voxelize-sweep", action="store_true", help="also report voxelizer GB/s over batch sizes")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -206,20 +207,26 @@ def main():
     args.frames = args.frames or cfg["frames_per_gpu"]
     args.points = args.points or sel["points"]
     torch.manual_seed(0)
-    model = modules.build_pillarnext_b(cfg).to(dev).train()
+    model = modules.build_pillarnext_b(cfg, sync_batchnorm=args.sync_bn and world > 1).to(dev).train()
     params = [p for p in model.parameters()]
     opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.01, fused=True)
     nb = 4                                                     # distinct synthetic batches, rotated
     host = [pin(synth.make_batch([rank * 1000 + b * args.frames + f for f in range(args.frames)], args.points, cfg,
                                  kind="lidar", n_boxes=40, sweeps=sel["sweeps"], rings=sel["rings"])) for b in range(nb)]
     resident = [to_device(h, dev) for h in host]
-    from pillarnext_b200.parallel import FlatGradAllReduce
-    allreduce_grads = FlatGradAllReduce(params)
+    # end-to-end arm: the host ships the raw ground truth (36 B/object) and the targets are built on the GPU (row F3:
+    # pnx_assign_labels), instead of the dense heat-map labels the reference's loader workers produce (5.5 MB/frame)
+    host_raw = []
+    for b in range(nb):
+        gb, gc = synth.make_gt_batch([rank * 1000 + b * args.frames + f for f in range(args.frames)], 40, cfg)
+        host_raw.append(pin({"points": host[b]["points"], "token": host[b]["token"], "gt_boxes_raw": gb, "gt_classes": gc}))
+    from pillarnext_b200.parallel import BucketedGradAllReduce, default_buckets
+    reducer = BucketedGradAllReduce(default_buckets(model))     # head | neck | backbone+reader, overlapped with the backward
 
     def step(ex):
         loss, _ = model(ex)
         loss.backward()
-        allreduce_grads()
+        reducer.finish()
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -244,14 +251,14 @@ def main():
             for i in range(n):
                 if nxt is None:
                     with torch.cuda.stream(copy_stream):
-                        nxt = (to_device(host[i % nb], dev, non_blocking=True), torch.cuda.Event())
+                        nxt = (to_device(host_raw[i % nb], dev, non_blocking=True), torch.cuda.Event())
                         nxt[1].record(copy_stream)
                 ex, ev = nxt
                 torch.cuda.current_stream().wait_event(ev)
                 if i + 1 < n:
                     copy_stream.wait_stream(torch.cuda.current_stream())   # buffers of step i-1 are free again
                     with torch.cuda.stream(copy_stream):
-                        nxt = (to_device(host[(i + 1) % nb], dev, non_blocking=True), torch.cuda.Event())
+                        nxt = (to_device(host_raw[(i + 1) % nb], dev, non_blocking=True), torch.cuda.Event())
                         nxt[1].record(copy_stream)
                 loss = step(ex)
                 # device -> host read of the step's result: async copy into pinned memory + event, consumed one step
@@ -353,13 +360,14 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload(sel, args.points, args.frames), "name": args.config, "global_batch": args.frames * world,
-                           "parallelism": "dp%d (frames sharded, NCCL gradient all-reduce, local BatchNorm)" % world,
+                           "parallelism": "dp%d (frames sharded, bucketed NCCL gradient all-reduce overlapped with the backward, %s BatchNorm)" % (world, "synchronised" if (args.sync_bn and world > 1) else "local"),
                            "l2": "per-step activation working set (GBs) >> 126 MB L2; 4 distinct input batches rotated",
                            "timed_step": "reader+backbone+neck+head fwd, loss, bwd, grad all-reduce (N>1), AdamW"},
-                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": nbytes(host[0]), "d2h_bytes_per_step": 4,
+                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": nbytes(host_raw[0]), "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps,
-                        "pipeline": "inside the timed region every step: pinned-host -> device copy of its inputs (side stream, "
-                                    "overlapping the previous step) and a 4-byte loss read-back (async copy to pinned memory + event, consumed one step late)"},
+                        "pipeline": "inside the timed region every step: pinned-host -> device copy of its inputs = points + raw ground-truth "
+                                    "boxes (side stream, overlapping the previous step), label assignment on the GPU (pnx_assign_labels), "
+                                    "and a 4-byte loss read-back (async copy to pinned memory + event, consumed one step late)"},
                 "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof, "voxelize": vox, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

@@ -206,12 +206,14 @@ int pnx_bn_apply(const void* x, long long ldx, long long M, int C, const float* 
 int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
                       long long ldx, long long M, int C, const float* mean, const float* invstd, int relu,
                       const float* fscale, const float* fshift, double* red, cudaStream_t stream);
-/* ... dx = gamma*invstd*(g - red[c]/count - xhat*red[C+c]/count); optional dres (+)= g (residual branch). */
+/* ... dx = gamma*invstd*(g - red[c]/count - xhat*red[C+c]/count); optional dres (+)= g (residual branch).
+ * count_dev != NULL: the population is read from device memory (SyncBatchNorm: the all-reduced site count of a sparse
+ * layer is only known on the device) and `count` is ignored. */
 int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
                      long long ldx, long long M, int C, const float* mean, const float* invstd,
-                     const float* gamma, const double* red, double count, int relu, const float* fscale,
-                     const float* fshift, void* dx, long long lddx, void* dres, long long lddres,
-                     int dres_accumulate, cudaStream_t stream);
+                     const float* gamma, const double* red, double count, const int* count_dev, int relu,
+                     const float* fscale, const float* fshift, void* dx, long long lddx, void* dres,
+                     long long lddres, int dres_accumulate, cudaStream_t stream);
 int pnx_add_rows(void* a, long long lda, const void* b, long long ldb, long long M, int C, cudaStream_t stream);
 /* y = relu(a + b) (BasicBlock tail, conv.py:48-50) and its backward g (+)= dy*(y>0). */
 int pnx_add_relu(const void* a, long long lda, const void* b, long long ldb, long long M, int C, void* y,

@@ -51,7 +51,7 @@ _SIGS = {
     "pnx_wgrad": [P, L, I, P, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, P, I, P],
     "pnx_bn_apply": [P, L, L, I, P, P, P, L, I, P, L, P],
     "pnx_bn_bwd_reduce": [P, L, P, L, P, L, L, I, P, P, I, P, P, P, P],
-    "pnx_bn_bwd_apply": [P, L, P, L, P, L, L, I, P, P, P, P, ctypes.c_double, I, P, P, P, L, P, L, I, P],
+    "pnx_bn_bwd_apply": [P, L, P, L, P, L, L, I, P, P, P, P, ctypes.c_double, P, I, P, P, P, L, P, L, I, P],
     "pnx_add_rows": [P, L, P, L, L, I, P],
     "pnx_add_relu": [P, L, P, L, L, I, P, L, P],
     "pnx_relu_bwd": [P, L, P, L, L, I, P, L, I, P],

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(256)
     bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ y,
                         long long ldy, const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                        const float* __restrict__ gamma, const double* __restrict__ red, float inv_n, int relu,
+                        const float* __restrict__ gamma, const double* __restrict__ red, float inv_n,
+                        const int* __restrict__ count_dev, int relu,
                         const float* __restrict__ fscale, const float* __restrict__ fshift,
                         __nv_bfloat16* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dres,
                         long long lddres, int dres_accumulate) {
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(256)
   if (my_row >= rpb) return;
   const int c0 = my_cg << 3;
   float ca[8], cb[8], cc[8], mu[8], is[8], fs[8], fh[8];
+  if (count_dev) inv_n = 1.f / (float)max(*count_dev, 1);   // SyncBatchNorm: population of all ranks, known on the device only
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = c0 + k;
@@ -337,9 +339,9 @@ extern "C" int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, 
 
 extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const void* x,
                                 long long ldx, long long M, int C, const float* mean, const float* invstd,
-                                const float* gamma, const double* red, double count, int relu, const float* fscale,
-                                const float* fshift, void* dx, long long lddx, void* dres, long long lddres,
-                                int dres_accumulate, cudaStream_t stream) {
+                                const float* gamma, const double* red, double count, const int* count_dev, int relu,
+                                const float* fscale, const float* fshift, void* dx, long long lddx, void* dres,
+                                long long lddres, int dres_accumulate, cudaStream_t stream) {
   PNX_CHECK_ARG(!relu || y || (fscale && fshift), "relu backward needs y or the forward affine (scale, shift)");
   PNX_CHECK_ARG(C % 8 == 0, "C % 8");
   if (M == 0) return PNX_OK;
@@ -347,7 +349,7 @@ extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, l
   constexpr int u = 2;  // measured best: 4 rows in flight costs occupancy (161 registers)
   PNX_DISPATCH_U(u, bn_bwd_apply_kernel<U><<<row_blocks(M, C), 256, 0, stream>>>(
                         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M,
-                        C, mean, invstd, gamma, red, (float)(1.0 / count), relu, fscale, fshift, (__nv_bfloat16*)dx,
+                        C, mean, invstd, gamma, red, (float)(1.0 / count), count_dev, relu, fscale, fshift, (__nv_bfloat16*)dx,
                         lddx, (__nv_bfloat16*)dres, lddres, dres_accumulate));
   PNX_CHECK_LAUNCH();
   return PNX_OK;

@@ -99,15 +99,18 @@ class WLayout:
         return _to_hilo(p.float()) if split else p.to(torch.bfloat16).contiguous()
 
     def unpack_grad(self, g, shape):
-        """g fp32 [taps, Cout, Cin] (convT: [4, Cin, Cout]) -> gradient in the parameter's layout."""
+        """g fp32 [taps, Cout, Cin] (convT: [4, Cin, Cout]) -> gradient in the parameter's layout (always a fresh
+        tensor: the accumulator may live in the per-step zero arena)."""
         if self.kind == "dense":
             co, ci, kh, kw = shape
-            return g.view(kh, kw, co, ci).permute(2, 3, 0, 1).contiguous()
-        if self.kind == "sp":
+            out = g.view(kh, kw, co, ci).permute(2, 3, 0, 1)
+        elif self.kind == "sp":
             co, kh, kw, ci = shape
-            return g.view(kw, kh, co, ci).permute(2, 1, 0, 3).contiguous()
-        ci, co, kh, kw = shape
-        return g.view(kh, kw, ci, co).permute(2, 3, 0, 1).contiguous()
+            out = g.view(kw, kh, co, ci).permute(2, 1, 0, 3)
+        else:
+            ci, co, kh, kw = shape
+            out = g.view(kh, kw, ci, co).permute(2, 3, 0, 1)
+        return out.clone(memory_format=torch.contiguous_format)
 
 
 _pack_cache = {}
@@ -188,7 +191,7 @@ def _claim_bn_reduce(info, M, C, k_total):
     if info is None or info.raw is None or info.C != C or info.M != M or not ops.bnr_eligible(C) or k_total < FUSE_BN_REDUCE_MIN_K:
         return None
     if info.red is None:
-        info.red = torch.zeros(2 * C, dtype=torch.float64, device=info.raw.device)
+        info.red = ops.zeros(2 * C, torch.float64, info.raw.device)
     info.fused = True
     return info
 
@@ -216,7 +219,7 @@ class ConvFn(torch.autograd.Function):
             out_fp32 = True      # raw convolution outputs stay fp32 in the fp32-grade mode
             assert not relu and x.shape[1] % _P() == 0 and x.shape[1] // _P() >= cin
         out = torch.empty(rows, out_c, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
-        stats = torch.zeros(2 * cout if want_stats else 0, dtype=torch.float64, device=x.device)
+        stats = ops.zeros(2 * cout if want_stats else 0, torch.float64, x.device)
         if split:
             ops.igemm(x, spec.M_out, wp, wp.shape[0], cin, n_cols, out, lda=x.stride(0), ldc=out_c, nbr=spec.nbr,
                       dense=spec.dense, bias=bias, stats=stats if want_stats else None,
@@ -319,11 +322,11 @@ class ConvFn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             if layout.kind == "convT":
-                g = torch.zeros(4, cin, cout, dtype=torch.float32, device=dy.device)
+                g = ops.zeros((4, cin, cout), torch.float32, dy.device)
                 ops.wgrad(x, cin, dy, cout, spec.M_out, 4, g, dense=spec.d_dense, shuffle=True)
             else:
                 # X = output gradient (direct), Y = layer input (gathered): result is [tap, Cout(pad), Cin]
-                g = torch.zeros(spec.taps, cpad, cin, dtype=torch.float32, device=dy.device)
+                g = ops.zeros((spec.taps, cpad, cin), torch.float32, dy.device)
                 ops.wgrad(dy, cpad, x, cin, spec.M_out, spec.taps, g, nbr=spec.nbr, dense=spec.dense)
                 if cpad != cout:
                     g = g[:, :cout].contiguous()
@@ -345,6 +348,18 @@ def wants_sync(bn):
     return bool(getattr(bn, "pnx_sync", False)) or isinstance(bn, torch.nn.SyncBatchNorm)
 
 
+NBT_PENDING = None     # when a list: num_batches_tracked buffers to bump with ONE foreach add at the end of the forward
+
+
+def bump_batches_tracked(bn):
+    if bn.num_batches_tracked is None:
+        return
+    if NBT_PENDING is not None:
+        NBT_PENDING.append(bn.num_batches_tracked)
+    else:
+        bn.num_batches_tracked += 1
+
+
 def _sync_enabled(bn):
     return wants_sync(bn) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
@@ -357,16 +372,18 @@ class BNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_raw, stats, gamma, beta, residual, bn, relu, count, info=None):
         M, C = x_raw.shape
+        count_dev = None
         if bn.training:
             if _sync_enabled(bn):
-                pack = torch.cat([stats, torch.tensor([float(count)], dtype=torch.float64, device=stats.device)])
+                # SyncBatchNorm (reference tools/train.py:55-56): sums and population of all ranks in one small all-reduce;
+                # the global count stays on the device (no host synchronisation)
+                pack = torch.cat([stats, torch.full((1,), float(count), dtype=torch.float64, device=stats.device)])
                 dist.all_reduce(pack)
-                stats, count = pack[:-1], float(pack[-1].item())
+                stats, count_dev = pack[:-1], pack[-1:].round().to(torch.int32)
             mom = bn.momentum if bn.momentum is not None else 0.1
-            scale, shift, mean, invstd = ops.bn_finalize(stats, C, None, int(count), gamma, beta, bn.eps, mom,
-                                                         bn.running_mean, bn.running_var)
-            if bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+            scale, shift, mean, invstd = ops.bn_finalize(stats, C, count_dev, 1 if count_dev is not None else int(count), gamma, beta,
+                                                         bn.eps, mom, bn.running_mean, bn.running_var)
+            bump_batches_tracked(bn)
         else:
             scale, shift = ops.bn_eval_affine(gamma, beta, bn.running_mean, bn.running_var, bn.eps)
             mean = invstd = None
@@ -379,6 +396,7 @@ class BNActFn(torch.autograd.Function):
             ops.bn_apply(x_raw, M, C, scale, shift, y, res=residual, relu=relu)
         ctx.save_for_backward(x_raw, y, gamma, mean, invstd, scale, shift)
         ctx.relu, ctx.count, ctx.has_res, ctx.sync, ctx.training = relu, count, residual is not None, _sync_enabled(bn), bn.training
+        ctx.count_dev = count_dev if bn.training else None
         ctx.info = None
         if info is not None and bn.training and relu and residual is None and not ctx.split:
             info.raw, info.scale, info.shift, info.mean, info.invstd, info.C, info.M = x_raw, scale, shift, mean, invstd, C, M
@@ -397,8 +415,7 @@ class BNActFn(torch.autograd.Function):
         red = ops.bn_bwd_reduce_split(dy, C, ysrc, C, x_raw, M, C, mean, invstd, ctx.relu, (scale, shift))
         local = red
         if ctx.sync:
-            red = red.clone()
-            dist.all_reduce(red)
+            raise NotImplementedError("SyncBatchNorm backward is not available in the fp32-grade split mode (single-GPU parity tool)")
         dxs = torch.empty(M, P * C, dtype=torch.bfloat16, device=dy.device)
         dres = torch.empty(M, P * C, dtype=torch.bfloat16, device=dy.device) if ctx.has_res else None
         ops.bn_bwd_apply_split(dy, C, ysrc, C, x_raw, M, C, mean, invstd, gamma, red, ctx.count, ctx.relu, (scale, shift),
@@ -428,7 +445,7 @@ class BNActFn(torch.autograd.Function):
             local = info.red          # the reduce pass ran in the epilogue of the GEMM that produced dy (= gated g)
             info.red, info.fused = None, False
         else:
-            local = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
+            local = ops.zeros(2 * C, torch.float64, dy.device)
             ops._count(1)
             check(lib().pnx_bn_bwd_reduce(ptr(dy), dy.stride(0), yp, ys, ptr(x_raw), x_raw.stride(0), M, C, ptr(mean), ptr(invstd),
                                           1 if ctx.relu else 0, ptr(scale), ptr(shift), ptr(local), stream()))
@@ -438,7 +455,8 @@ class BNActFn(torch.autograd.Function):
             dist.all_reduce(red)
         ops._count(1)
         check(lib().pnx_bn_bwd_apply(ptr(dy), dy.stride(0), yp, ys, ptr(x_raw), x_raw.stride(0), M, C, ptr(mean), ptr(invstd),
-                                     ptr(gamma), ptr(red), float(max(ctx.count, 1)), 1 if (ctx.relu and not fused) else 0,
+                                     ptr(gamma), ptr(red), float(max(ctx.count, 1)), ptr(ctx.count_dev) if ctx.count_dev is not None else None,
+                                     1 if (ctx.relu and not fused) else 0,
                                      ptr(scale), ptr(shift), ptr(dx), dx.stride(0), ptr(dres) if dres is not None else None,
                                      dres.stride(0) if dres is not None else 8, 0, stream()))
         r = local.float()
@@ -623,9 +641,9 @@ class ASPPBranchesFn(torch.autograd.Function):
             nxt = torch.empty_like(dx)
             ops.igemm(dcat[:, (2 + j) * C:(3 + j) * C], M, wd, 9, C, C, nxt, lda=C6, dense=(H, W, H, W, 3, 1, d, d), addend=dx)
             dx = nxt
-        g1 = torch.zeros(1, C, C, dtype=torch.float32, device=dcat.device)
+        g1 = ops.zeros((1, C, C), torch.float32, dcat.device)
         ops.wgrad(dcat[:, C:2 * C], C, x, C, M, 1, g1)
-        gs = torch.zeros(9, C, C, dtype=torch.float32, device=dcat.device)
+        gs = ops.zeros((9, C, C), torch.float32, dcat.device)
         for j, d in enumerate(ASPPBranchesFn.DILS):
             ops.wgrad(dcat[:, (2 + j) * C:(3 + j) * C], C, x, C, M, 9, gs, dense=(H, W, H, W, 3, 1, d, d))
         g = torch.empty(M, C, dtype=torch.bfloat16, device=dcat.device)
@@ -645,8 +663,7 @@ class PFNFn(torch.autograd.Function):
                               sync=_sync_enabled(bn0) or _sync_enabled(bn1))
         if training:
             for bn in (bn0, bn1):
-                if bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked += 1
+                bump_batches_tracked(bn)
         ctx.voxels, ctx.fwd, ctx.training = voxels, fwd, training
         ctx.save_for_backward(w1, g0, g1)
         voxels.feat_bf16 = fwd["feat_bf16"]
@@ -684,7 +701,7 @@ class CenterLossFn(torch.autograd.Function):
         from ._lib import check, lib, ptr, stream
         T = len(outs)
         dev = outs[0].device
-        acc = torch.zeros(T, 16, dtype=torch.float64, device=dev)
+        acc = ops.zeros((T, 16), torch.float64, dev)
         res = torch.empty(T, 16, dtype=torch.float32, device=dev)
         total = torch.empty(1, dtype=torch.float32, device=dev)
         douts = []
@@ -771,7 +788,7 @@ class HeadFinalConvFn(torch.autograd.Function):
         dy = torch.empty(M, cin, dtype=torch.bfloat16, device=dout.device)
         ops.igemm(dZ, M, wz.transpose(1, 2).contiguous(), 1, NZ, cin, dy,         # dy = dZ . Wz (+ the sibling BN's reduce pass)
                   bnr=_claim_bn_reduce(ctx.bn_src, M, cin, NZ))
-        g = torch.zeros(1, cin, NZ, dtype=torch.float32, device=dout.device)
+        g = ops.zeros((1, cin, NZ), torch.float32, dout.device)
         ops.wgrad(y, cin, dZ, NZ, M, 1, g)                                        # [1, Cin, NZ] = y^T . dZ
         dwb = g[0, :, :144].reshape(cin, 3, 3, 16).permute(3, 0, 1, 2).contiguous()
         return dy, dwb, dbias, None, None, None, None

@@ -343,20 +343,36 @@ class SepHead(nn.Module):
         self._bn_cat = None
 
     def _cat_bn(self, names):
-        """One BatchNorm2d-like holder over the concatenated sibling channels; running stats are views that are
-        copied back to the per-head buffers after each forward."""
+        """One BatchNorm2d-like holder over the concatenated sibling channels.  The per-head running_mean / running_var
+        buffers (the reference's state-dict entries `<head>.1.running_*`) are made VIEWS of one concatenated tensor
+        each, so the fused BatchNorm updates all of them in place with no per-step copies; `.to()` / `.cuda()` give
+        every buffer its own storage again, which is detected (data_ptr) and repaired here."""
         hc = self.head_conv
+        members = [getattr(self, n)[1] for n in names]
+        dev = members[0].running_mean.device
+        cat = getattr(self, "_stat_cat", None)
+        ok = cat is not None and cat[0].device == dev and all(
+            m.running_mean.data_ptr() == cat[0][i * hc:].data_ptr() and m.running_var.data_ptr() == cat[1][i * hc:].data_ptr()
+            for i, m in enumerate(members))
+        if not ok:
+            with torch.no_grad():
+                rm = torch.cat([m.running_mean for m in members]).contiguous()
+                rv = torch.cat([m.running_var for m in members]).contiguous()
+            for i, m in enumerate(members):
+                m.running_mean = rm[i * hc:(i + 1) * hc]
+                m.running_var = rv[i * hc:(i + 1) * hc]
+            cat = (rm, rv)
+            object.__setattr__(self, "_stat_cat", cat)
         bn = self._bn_cat
-        if bn is None or bn.running_mean.device != getattr(self, names[0])[1].running_mean.device:
-            bn = nn.BatchNorm2d(hc * len(names)).to(getattr(self, names[0])[1].running_mean.device)
+        if bn is None or bn.weight.device != dev:
+            bn = nn.BatchNorm2d(hc * len(names)).to(dev)
             object.__setattr__(self, "_bn_cat", bn)   # not a registered submodule: no extra state-dict keys
+        bn.running_mean, bn.running_var = cat
+        bn.num_batches_tracked = None                 # the members' own counters are bumped below
         bn.training = self.training
-        ref = getattr(self, names[0])[1]
+        ref = members[0]
         bn.eps, bn.momentum = ref.eps, ref.momentum
         bn.pnx_sync = Fn.wants_sync(ref)
-        with torch.no_grad():
-            bn.running_mean.copy_(torch.cat([getattr(self, n)[1].running_mean for n in names]))
-            bn.running_var.copy_(torch.cat([getattr(self, n)[1].running_var for n in names]))
         return bn
 
     def run(self, x, B, H, W, bn_src=None):
@@ -377,12 +393,8 @@ class SepHead(nn.Module):
         info_y = Fn.bn_info()
         y = Fn.BNActFn.apply(raw, stats, ga, be, None, bn, True, raw.shape[0], info_y)
         if self.training:
-            with torch.no_grad():
-                for i, n in enumerate(names):
-                    m = getattr(self, n)[1]
-                    m.running_mean.copy_(bn.running_mean[i * hc:(i + 1) * hc])
-                    m.running_var.copy_(bn.running_var[i * hc:(i + 1) * hc])
-                    m.num_batches_tracked += 1
+            for n in names:
+                Fn.bump_batches_tracked(getattr(self, n)[1])
         classes = [self.heads[n][0] for n in names]
         tot = sum(classes)
         npad = (tot + 15) // 16 * 16
@@ -593,9 +605,36 @@ class SingleStageDetector(nn.Module):
     def forward(self, example):
         return self.training_step(example) if self.training else self.validation_step(example)
 
+    label_cfg = dict(gaussian_overlap=0.1, max_objs=500, min_radius=2)     # configs/dataset/base/base_det_train.yaml:11-13
+
+    def assign_labels(self, example):
+        """Row F3: CenterPoint targets on the GPU.  An example that carries the raw ground truth (`gt_boxes_raw`
+        [B, N, 9] fp32, `gt_classes` [B, N] int32 index into the flattened class list) instead of the dense label
+        tensors gets hm / anno_box / ind / mask / cat / gt_boxes from pnx_assign_labels -- what the reference's
+        data-loader workers compute in numpy (AssignLabel + collate) and ship over PCIe."""
+        h = self.head
+        vs = h.voxel_size if hasattr(h, "voxel_size") else self.reader.voxel_size
+        pr = h.pc_range if hasattr(h, "pc_range") else self.reader.pc_range
+        osf = h.out_size_factor if hasattr(h, "out_size_factor") else [4] * len(h.class_names)
+        lab = ops.assign_labels(example["gt_boxes_raw"], example["gt_classes"], h.class_names, vs, pr, osf, **self.label_cfg)
+        out = dict(example)
+        out.update(lab)
+        return out
+
     def training_step(self, example):
-        preds = self._forward(example)
-        return self.head.loss(example, preds)
+        if "hm" not in example and "gt_boxes_raw" in example:
+            example = self.assign_labels(example)
+        if torch.is_grad_enabled():
+            ops.ARENA.begin_step(example["points"].device)        # one memset for the step's small accumulators
+        Fn.NBT_PENDING = []
+        try:
+            preds = self._forward(example)
+            out = self.head.loss(example, preds)
+        finally:
+            pending, Fn.NBT_PENDING = Fn.NBT_PENDING, None
+        if pending:
+            torch._foreach_add_(pending, 1)                        # every BatchNorm's num_batches_tracked, one launch
+        return out
 
     @torch.no_grad()
     def validation_step(self, example):

@@ -1,4 +1,5 @@
-"""World-size-2 gloo test of the data-parallel host logic (frame sharding + flat gradient all-reduce)."""
+"""World-size-2 gloo tests of the data-parallel host logic: frame sharding, the flat gradient all-reduce and the
+bucketed reducer that overlaps the reduction with the backward (hooks, bucket readiness, unused parameters)."""
 import os
 import sys
 
@@ -13,7 +14,7 @@ def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from pillarnext_b200.parallel import FlatGradAllReduce, shard_frames
+    from pillarnext_b200.parallel import BucketedGradAllReduce, FlatGradAllReduce, shard_frames
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
     data = torch.randn(6, 8, generator=torch.Generator().manual_seed(1))
@@ -22,6 +23,18 @@ def _worker(rank, world, port, q):
     loss.backward()
     FlatGradAllReduce(net.parameters())()
     grads = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    # the bucketed, hook-driven reducer: two buckets in backward order + one parameter that never gets a gradient
+    net.zero_grad(set_to_none=True)
+    unused = torch.nn.Parameter(torch.ones(3))
+    red = BucketedGradAllReduce([list(net[2].parameters()), list(net[0].parameters()) + [unused]])
+    for _ in range(2):                                     # twice: the bookkeeping resets between steps
+        net.zero_grad(set_to_none=True)
+        loss = net(data[mine]).pow(2).sum() / 6 * world
+        loss.backward()
+        red.finish()
+    g2 = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    assert torch.allclose(g2, grads, atol=1e-6) and unused.grad is not None and float(unused.grad.abs().sum()) == 0.0
+    red.remove()
     q.put((rank, mine, grads.tolist()))   # plain floats: a tensor would travel as a shared fd that dies with the worker
     dist.barrier()
     dist.destroy_process_group()
