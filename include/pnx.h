@@ -258,12 +258,14 @@ int pnx_relu_bwd_split(const float* dy, long long lddy, const void* y, long long
 /* ---------------------------------------------------------------- head final 3x3 convs as GEMM + stencil
  * out[m, j] = bias16[j] + sum_{t<9} Z[m + off_t, t*16 + j] on a B x H x W channels-last image (zero padding),
  * Z [M, ldz] fp32 = y . Wz^T from pnx_igemm (taps=1); pnx_tap_scatter is the mirrored backward gather
- * dZ[m', t*16+j] = dout[m' - off_t, j] (bf16, columns >= 144 zeroed).  Replaces the `<head>.3` Conv2d(64, c, 3)
+ * dZ[m', t*cpt+j] = dout[m' - off_t, j] (bf16, columns >= 9*cpt zeroed).  Replaces the `<head>.3` Conv2d(64, c, 3)
  * of SepHead (centerhead.py:44-46) for all sibling heads at once. */
-int pnx_tap_gather_sum(const float* Z, long long ldz, const float* bias16, int B, int H, int W, float* out,
+int pnx_tap_gather_sum(const float* Z, long long ldz, int cpt, const float* bias16, int B, int H, int W, float* out,
                        cudaStream_t stream);
-int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, int nz, long long lo_off,
-                    cudaStream_t stream);   /* nz = GEMM columns (>= 144); lo_off > 0: also write the lo halves (split rows) */
+/* cpt = channels per tap (4/8/12/16): Z / dZ column = tap*cpt + j; nz = GEMM columns (>= 9*cpt, multiple of 8);
+ * lo_off > 0: write all pieces of the split-rows mode (piece q at column q*lo_off + c) */
+int pnx_tap_scatter(const float* dout, int B, int H, int W, void* dZ, long long ldz, int nz, int cpt, long long lo_off,
+                    cudaStream_t stream);
 
 /* ---------------------------------------------------------------- F3: label assignment on the GPU
  * One task of AssignLabel.__call__ (det3d/datasets/pipelines/assign.py:23-116; gaussian_radius / draw_gaussian:
@@ -278,7 +280,7 @@ int pnx_assign_labels(const float* boxes, const int* cls, int B, int N, const in
                       int n_classes, int task, double vs_x, double vs_y, double pc_x, double pc_y, int osf,
                       double gaussian_overlap, int min_radius, int max_objs, int C, int H, int W, float* hm,
                       float* anno_box, long long* ind, unsigned char* mask, long long* cat, float* gt_boxes,
-                      cudaStream_t stream);
+                      int* obj_scratch /* [B, N, 4] int32 */, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- L1 fused CenterPoint loss (forward + gradient)
  * One task: out/dout [B*H*W, npad] fp32 channels-last head output (columns reg2|height1|dim3|rot2|vel2|hm C|pad)

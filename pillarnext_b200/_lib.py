@@ -36,8 +36,8 @@ _SIGS = {
     "pnx_pfn_lin1": [P, P, P, P, P, I, P, P, P, P, P, I, P],
     "pnx_pfn_max1": [P, P, P, I, P, P, P, P, P],
     "pnx_pfn_backward": [P, P, P, P, P, P, I, I, F, F, F, F] + [P] * 23 + [I, P, P],
-    "pnx_tap_gather_sum": [P, L, P, I, I, I, P, P],
-    "pnx_tap_scatter": [P, I, I, I, P, L, I, L, P],
+    "pnx_tap_gather_sum": [P, L, I, P, I, I, I, P, P],
+    "pnx_tap_scatter": [P, I, I, I, P, L, I, I, L, P],
     "pnx_center_loss_task": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, F, F, F, F, F, P, I, P, P],
     "pnx_center_loss_finalize": [P, I, P, P, P, P, P, P],
     "pnx_sites_out_dim": [I, I],
@@ -67,7 +67,7 @@ _SIGS = {
     "pnx_add_relu_split": [P, L, L, P, L, L, L, I, P, L, L, P],
     "pnx_relu_bwd_split": [P, L, P, L, L, L, I, P, L, L, P],
     "pnx_assign_labels": [P, P, I, I, P, P, I, I, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, I,
-                          ctypes.c_double, I, I, I, I, I, P, P, P, P, P, P, P],
+                          ctypes.c_double, I, I, I, I, I, P, P, P, P, P, P, P, P],
     # F1: decode + rotated NMS.  common prefix = out, ld, B, H, W, C, offs, osf, vs_x, vs_y, pc_x, pc_y, score_thr, range6, rect
     "pnx_det_keys": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P],
     "pnx_det_nms": [P, L, I, I, I, I, P, F, F, F, F, F, F, P, P, P, P, P, P, I, I, P, P, P, P],

@@ -8,8 +8,8 @@
 // so the per-step host->device traffic is the boxes (36 B/object) instead of the dense heat-maps (5.5 MB/frame for
 // the six nuScenes tasks).  The reference does this in numpy on the data-loader workers: float64 for the radius, the
 // centre coordinate and the gaussian, float32 storage -- the same mix is used here (the work is a few thousand cells).
-// One CTA per (frame, task): objects are compacted in their original order (slot = number of accepted objects of the
-// task before it), exactly like the reference's running `task_nums`.
+// Kernel 1, one CTA per frame: objects are compacted in their original order (slot = number of accepted objects of the
+// task before it), exactly like the reference's running `task_nums`.  Kernel 2, one CTA per (object, frame): the splat.
 #include "pnx_common.cuh"
 
 namespace {
@@ -31,6 +31,7 @@ struct AssignParams {
   unsigned char* mask;
   long long* cat;
   float* gtb;
+  int* obj;               // [B, N, 4] scratch: (cx, cy, radius, class id) of every object, cx = -1: not drawn
 };
 
 // center_utils.py:12-34, float64
@@ -51,11 +52,9 @@ __device__ double gaussian_radius(double height, double width, double min_overla
 __global__ void __launch_bounds__(kAssignThreads) assign_kernel(AssignParams p) {
   __shared__ int s_scan[kAssignThreads / 32];
   __shared__ int s_base;
-  __shared__ int s_obj[4];   // cx, cy, radius, class id of the object being drawn
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  float* hm_b = p.hm + (size_t)b * p.C * p.H * p.W;
   for (int k0 = 0; k0 < p.N; k0 += kAssignThreads) {
     const int k = k0 + tid;
     bool ok = false;
@@ -100,29 +99,10 @@ __global__ void __launch_bounds__(kAssignThreads) assign_kernel(AssignParams p) 
       for (int q = 0; q < 6; ++q) g[q] = bx[q];
       g[6] = bx[8];
     }
-    // gaussian splat of the accepted objects of this chunk, one object at a time, cells over the threads
-    // (draw_gaussian: max with exp(-(dx^2+dy^2)/(2 sigma^2)), sigma = (2r+1)/6, entries below eps dropped)
-    __syncthreads();
-    for (int j = 0; j < kAssignThreads && k0 + j < p.N; ++j) {
-      if (tid == j) {
-        s_obj[0] = ok ? cxi : -1; s_obj[1] = cyi; s_obj[2] = radius; s_obj[3] = cid;
-      }
-      __syncthreads();
-      const int ox = s_obj[0], oy = s_obj[1], r = s_obj[2], oc = s_obj[3];
-      if (ox >= 0) {
-        const int d = 2 * r + 1;
-        const double sigma = (double)d / 6.0;
-        float* plane = hm_b + (size_t)oc * p.H * p.W;
-        for (int q = tid; q < d * d; q += kAssignThreads) {
-          const int gy = q / d - r, gx = q - (q / d) * d - r;
-          const int yy = oy + gy, xx = ox + gx;
-          if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
-          const double v = exp(-(double)(gx * gx + gy * gy) / (2 * sigma * sigma));
-          if (v < 2.220446049250313e-16) continue;                                             // np.finfo(float64).eps * max (= 1)
-          atomicMax(reinterpret_cast<int*>(plane + (size_t)yy * p.W + xx), __float_as_int((float)v));  // values >= 0
-        }
-      }
-      __syncthreads();
+    // hand the accepted objects to the splat kernel (one CTA per object)
+    if (k < p.N) {
+      int4 o = make_int4(ok ? cxi : -1, cyi, radius, cid);
+      reinterpret_cast<int4*>(p.obj)[(size_t)b * p.N + k] = o;
     }
     if (tid == 0) {
       int tot = 0;
@@ -133,6 +113,26 @@ __global__ void __launch_bounds__(kAssignThreads) assign_kernel(AssignParams p) 
   }
 }
 
+// gaussian splat, one CTA per (object, frame): draw_gaussian = max with exp(-(dx^2+dy^2)/(2 sigma^2)), sigma = (2r+1)/6,
+// entries below eps dropped; float64 like numpy, stored float32; atomicMax on the bit pattern (values >= 0)
+__global__ void __launch_bounds__(128) assign_splat_kernel(AssignParams p) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  const int4 o = reinterpret_cast<const int4*>(p.obj)[(size_t)b * p.N + k];
+  const int ox = o.x, oy = o.y, r = o.z, oc = o.w;
+  if (ox < 0) return;
+  const int d = 2 * r + 1;
+  const double sigma = (double)d / 6.0;
+  float* plane = p.hm + ((size_t)b * p.C + oc) * p.H * p.W;
+  for (int q = threadIdx.x; q < d * d; q += blockDim.x) {
+    const int gy = q / d - r, gx = q - (q / d) * d - r;
+    const int yy = oy + gy, xx = ox + gx;
+    if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+    const double v = exp(-(double)(gx * gx + gy * gy) / (2 * sigma * sigma));
+    if (v < 2.220446049250313e-16) continue;                                                   // np.finfo(float64).eps * max (= 1)
+    atomicMax(reinterpret_cast<int*>(plane + (size_t)yy * p.W + xx), __float_as_int((float)v));
+  }
+}
+
 }  // namespace
 
 // Contract: include/pnx.h (pnx_assign_labels).  hm / anno / ind / mask / cat / gtb must be zeroed by the caller.
@@ -140,15 +140,18 @@ extern "C" int pnx_assign_labels(const float* boxes, const int* cls, int B, int 
                                  int n_classes, int task, double vs_x, double vs_y, double pc_x, double pc_y, int osf,
                                  double gaussian_overlap, int min_radius, int max_objs, int C, int H, int W, float* hm,
                                  float* anno_box, long long* ind, unsigned char* mask, long long* cat, float* gt_boxes,
-                                 cudaStream_t stream) {
+                                 int* obj_scratch, cudaStream_t stream) {
   PNX_CHECK_ARG(B > 0 && N >= 0 && n_classes > 0 && C > 0 && H > 0 && W > 0 && max_objs > 0 && osf > 0, "shapes");
   if (N == 0) return PNX_OK;
   AssignParams p;
   p.boxes = boxes; p.cls = cls; p.B = B; p.N = N; p.cls_task = cls_task; p.cls_id = cls_id; p.n_classes = n_classes;
   p.task = task; p.vs_x = vs_x; p.vs_y = vs_y; p.pc_x = pc_x; p.pc_y = pc_y; p.osf = (double)osf; p.overlap = gaussian_overlap;
   p.min_radius = min_radius; p.M = max_objs; p.C = C; p.H = H; p.W = W;
-  p.hm = hm; p.anno = anno_box; p.ind = ind; p.mask = mask; p.cat = cat; p.gtb = gt_boxes;
+  p.hm = hm; p.anno = anno_box; p.ind = ind; p.mask = mask; p.cat = cat; p.gtb = gt_boxes; p.obj = obj_scratch;
+  PNX_CHECK_ARG(obj_scratch && (reinterpret_cast<uintptr_t>(obj_scratch) & 15) == 0, "obj_scratch [B, N, 4] int32, 16-byte aligned");
   assign_kernel<<<B, kAssignThreads, 0, stream>>>(p);
+  PNX_CHECK_LAUNCH();
+  assign_splat_kernel<<<dim3(N, B), 128, 0, stream>>>(p);
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }

@@ -733,62 +733,70 @@ class CenterLossFn(torch.autograd.Function):
 
 # ------------------------------------------------------------------------------------------- head final convs
 class HeadFinalConvFn(torch.autograd.Function):
-    """The sibling heads' final Conv2d(64, c, 3) (centerhead.py:44-46) as ONE 1x1 tensor-core GEMM (N = 9 taps x 16
-    padded outputs, no gather) + a 9-point stencil sum (stencil.cu), instead of a gather-bound 3x3 implicit GEMM.
-    y bf16 [M, Cin]; wb fp32 [16, Cin, 3, 3] (block-diagonal over the heads, zero rows as padding); bias fp32 [16].
-    Returns fp32 [M, 16]."""
-    NZ = 192   # 9*16 = 144 GEMM columns, padded to a tile / K multiple
+    """The sibling heads' final Conv2d(64, c, 3) (centerhead.py:44-46) as ONE 1x1 tensor-core GEMM (N = 9 taps x cpt
+    outputs, no gather) + a 9-point stencil sum (stencil.cu), instead of a gather-bound 3x3 implicit GEMM.
+    y bf16 [M, Cin]; wb fp32 [16, Cin, 3, 3] (block-diagonal over the heads, zero rows as padding, `n_used` real rows);
+    bias fp32 [16].  cpt = n_used rounded up to 4 channels per tap: the reference's heads have 11-13 outputs per task ->
+    cpt = 12 (16 for 13) -> 108 (144) GEMM columns padded to NZ = 128 (192).  Returns fp32 [M, 16]."""
 
     @staticmethod
-    def forward(ctx, y, wb, bias, B, H, W, bn_src=None):
+    def geometry(n_used):
+        cpt = max(4, (int(n_used) + 3) // 4 * 4)
+        return cpt, (128 if 9 * cpt <= 128 else 192)
+
+    @staticmethod
+    def forward(ctx, y, wb, bias, B, H, W, bn_src=None, n_used=16):
         from ._lib import check, lib, ptr, stream
         split = _split()
         ctx.bn_src = bn_src if not split else None
         M, cin = y.shape[0], y.shape[1] // (_P() if split else 1)
         assert wb.shape[0] == 16 and wb.shape[2] == 3
+        cpt, NZ = HeadFinalConvFn.geometry(n_used)
         with torch.no_grad():
-            wz = torch.zeros(1, HeadFinalConvFn.NZ, cin, dtype=torch.float32, device=y.device)
-            wz[0, :144] = wb.permute(2, 3, 0, 1).reshape(144, cin)                          # row = tap*16 + j
+            wz = torch.zeros(1, NZ, cin, dtype=torch.float32, device=y.device)
+            wz[0, :9 * cpt] = wb.permute(2, 3, 0, 1)[:, :, :cpt].reshape(9 * cpt, cin)            # row = tap*cpt + j
             wz = _to_hilo(wz) if split else wz.to(torch.bfloat16)
-        Z = torch.empty(M, HeadFinalConvFn.NZ, dtype=torch.float32, device=y.device)
-        ops.igemm(y, M, wz, 1, cin, HeadFinalConvFn.NZ, Z, block_n=192, segs=ops.split_segments() if split else None, a_lo_off=cin if split else 0)
+        Z = torch.empty(M, NZ, dtype=torch.float32, device=y.device)
+        ops.igemm(y, M, wz, 1, cin, NZ, Z, block_n=NZ, segs=ops.split_segments() if split else None, a_lo_off=cin if split else 0)
         ctx.split = split
         out = torch.empty(M, 16, dtype=torch.float32, device=y.device)
         ops._count(1)
-        check(lib().pnx_tap_gather_sum(ptr(Z), HeadFinalConvFn.NZ, ptr(bias.detach().float().contiguous()), B, H, W, ptr(out), stream()))
+        check(lib().pnx_tap_gather_sum(ptr(Z), NZ, cpt, ptr(bias.detach().float().contiguous()), B, H, W, ptr(out), stream()))
         ctx.save_for_backward(y, wz)
-        ctx.geo = (B, H, W, cin, tuple(wb.shape))
+        ctx.geo = (B, H, W, cin, cpt, NZ)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         from ._lib import check, lib, ptr, stream
         y, wz = ctx.saved_tensors
-        B, H, W, cin, wshape = ctx.geo
-        M, NZ = y.shape[0], HeadFinalConvFn.NZ
+        B, H, W, cin, cpt, NZ = ctx.geo
+        M = y.shape[0]
         dout = dout.contiguous().float()
+        dbias = dout.sum(0)
+
+        def to_wb(g):       # [1, Cin, NZ] -> gradient of wb [16, Cin, 3, 3]
+            d = g[0, :, :9 * cpt].reshape(cin, 3, 3, cpt).permute(3, 0, 1, 2)
+            return torch.nn.functional.pad(d, (0, 0, 0, 0, 0, 0, 0, 16 - cpt)).contiguous()
+
         if ctx.split:
             P = _P()
             dZ = torch.empty(M, P * NZ, dtype=torch.bfloat16, device=dout.device)
             ops._count(1)
-            check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), P * NZ, NZ, NZ, stream()))
-            dbias = dout.sum(0)
+            check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), P * NZ, NZ, cpt, NZ, stream()))
             wzf = sum(wz[0, :, q * cin:(q + 1) * cin].float() for q in reversed(range(P)))  # [NZ, cin] (sum of the pieces)
             d32 = torch.empty(M, cin, dtype=torch.float32, device=dout.device)
             ops.igemm(dZ, M, _to_hilo(wzf.t().contiguous().unsqueeze(0)), 1, NZ, cin, d32, segs=ops.split_segments(), a_lo_off=NZ)
             dy = ops.rows_split(d32)
             g = torch.zeros(1, cin, NZ, dtype=torch.float32, device=dout.device)
             ops.wgrad_split(y, cin, cin, dZ, NZ, NZ, M, 1, g)
-            dwb = g[0, :, :144].reshape(cin, 3, 3, 16).permute(3, 0, 1, 2).contiguous()
-            return dy, dwb, dbias, None, None, None, None
+            return dy, to_wb(g), dbias, None, None, None, None, None
         dZ = torch.empty(M, NZ, dtype=torch.bfloat16, device=dout.device)
         ops._count(1)
-        check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), NZ, NZ, 0, stream()))
-        dbias = dout.sum(0)
+        check(lib().pnx_tap_scatter(ptr(dout), B, H, W, ptr(dZ), NZ, NZ, cpt, 0, stream()))
         dy = torch.empty(M, cin, dtype=torch.bfloat16, device=dout.device)
         ops.igemm(dZ, M, wz.transpose(1, 2).contiguous(), 1, NZ, cin, dy,         # dy = dZ . Wz (+ the sibling BN's reduce pass)
                   bnr=_claim_bn_reduce(ctx.bn_src, M, cin, NZ))
         g = ops.zeros((1, cin, NZ), torch.float32, dout.device)
         ops.wgrad(y, cin, dZ, NZ, M, 1, g)                                        # [1, Cin, NZ] = y^T . dZ
-        dwb = g[0, :, :144].reshape(cin, 3, 3, 16).permute(3, 0, 1, 2).contiguous()
-        return dy, dwb, dbias, None, None, None, None
+        return dy, to_wb(g), dbias, None, None, None, None, None

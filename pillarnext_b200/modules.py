@@ -409,7 +409,7 @@ class SepHead(nn.Module):
         wb = torch.cat(rows_w + ([wb[tot:]] if npad > tot else []), 0)
         bb = torch.cat(rows_b + ([bb[tot:]] if npad > tot else []), 0)
         if npad == 16:
-            out = Fn.HeadFinalConvFn.apply(y, wb, bb, B, H, W, info_y)       # 1x1 GEMM + stencil (gather-free)
+            out = Fn.HeadFinalConvFn.apply(y, wb, bb, B, H, W, info_y, tot)  # 1x1 GEMM + stencil (gather-free)
         else:
             out, _ = Fn.conv(y, wb, bb, Fn.dense_spec(B, H, W, 3), Fn.WLayout("dense"), out_fp32=True)
         out4 = out.view(B, H, W, npad)

@@ -670,6 +670,7 @@ def assign_labels(gt_boxes, gt_cls, tasks, voxel_size, pc_range, out_size_factor
     g = grid_size_xy(voxel_size, pc_range)
     out = {k: [] for k in ("hm", "anno_box", "ind", "mask", "cat", "gt_boxes")}
     L = lib()
+    obj = torch.empty(B, max(N, 1), 4, dtype=torch.int32, device=dev)
     for t, task in enumerate(tasks):
         osf = int(out_size_factor[t])
         W, H = int(g[0]) // osf, int(g[1]) // osf
@@ -679,11 +680,11 @@ def assign_labels(gt_boxes, gt_cls, tasks, voxel_size, pc_range, out_size_factor
         mask = torch.zeros(B, max_objs, dtype=torch.uint8, device=dev)
         cat = torch.zeros(B, max_objs, dtype=torch.int64, device=dev)
         gtb = torch.zeros(B, max_objs, 7, dtype=torch.float32, device=dev)
-        _count(1)
+        _count(2)
         check(L.pnx_assign_labels(ptr(gt_boxes), ptr(gt_cls), B, N, ptr(cls_task), ptr(cls_id), cls_task.numel(), t,
                                   float(voxel_size[0]), float(voxel_size[1]), float(pc_range[0]), float(pc_range[1]), osf,
                                   float(gaussian_overlap), int(min_radius), int(max_objs), len(task), H, W, ptr(hm), ptr(anno),
-                                  ptr(ind), ptr(mask), ptr(cat), ptr(gtb), stream()))
+                                  ptr(ind), ptr(mask), ptr(cat), ptr(gtb), ptr(obj), stream()))
         for k, v in (("hm", hm), ("anno_box", anno), ("ind", ind), ("mask", mask), ("cat", cat), ("gt_boxes", gtb)):
             out[k].append(v)
     return out

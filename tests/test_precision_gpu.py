@@ -170,21 +170,27 @@ def test_split_ops_forward_backward_vs_fp64():
         for name, a, b in (("y", y, yd), ("draw", raw_l.grad, rawd.grad), ("dres", mgrad(rs, C), resd.grad),
                            ("dgamma", bn1.weight.grad, bn1d.weight.grad), ("dbeta", bn1.bias.grad, bn1d.bias.grad)):
             assert rel(a, b) < TOL, ("bn+res+relu", name, rel(a, b))
-        # the head's final conv: 1x1 GEMM + 9-point stencil
-        cin = 384
-        yh = torch.randn(M, cin, device="cuda", generator=g)
-        wb = (torch.randn(16, cin, 3, 3, device="cuda", generator=g) * 0.05).requires_grad_()
-        bb = torch.randn(16, device="cuda", generator=g).requires_grad_()
-        R3 = torch.randn(M, 16, device="cuda", generator=g)
-        ys = leaf(yh)
-        out = Fn.HeadFinalConvFn.apply(ys, wb, bb, B, H, W)
-        (out * R3).sum().backward()
-        yd = nchw(yh, B, H, W, cin).requires_grad_()
-        wbd, bbd = wb.detach().double().requires_grad_(), bb.detach().double().requires_grad_()
-        od = F.conv2d(yd, wbd, bbd, padding=1)
-        (od * nchw(R3, B, H, W, 16)).sum().backward()
-        for name, a, b in (("out", out, to_rows(od, 16)), ("dy", mgrad(ys, cin), to_rows(yd.grad, cin)), ("dw", wb.grad, wbd.grad), ("db", bb.grad, bbd.grad)):
-            assert rel(a, b) < TOL, ("head final conv", name, rel(a, b))
+        # the head's final conv: 1x1 GEMM + 9-point stencil; 16 outputs (9*16 = 144 GEMM columns in 192) and the reference's
+        # 11 (cpt = 12: 108 columns in 128)
+        for n_used in (16, 11):
+            cin = 384
+            yh = torch.randn(M, cin, device="cuda", generator=g)
+            wb0 = torch.randn(16, cin, 3, 3, device="cuda", generator=g) * 0.05
+            wb0[n_used:] = 0
+            wb = wb0.requires_grad_()
+            bb = torch.randn(16, device="cuda", generator=g).requires_grad_()
+            R3 = torch.randn(M, 16, device="cuda", generator=g)
+            R3[:, n_used:] = 0
+            ys = leaf(yh)
+            out = Fn.HeadFinalConvFn.apply(ys, wb, bb, B, H, W, None, n_used)
+            (out * R3).sum().backward()
+            yd = nchw(yh, B, H, W, cin).requires_grad_()
+            wbd, bbd = wb.detach().double().requires_grad_(), bb.detach().double().requires_grad_()
+            od = F.conv2d(yd, wbd, bbd, padding=1)
+            (od * nchw(R3, B, H, W, 16)).sum().backward()
+            for name, a, b in (("out", out[:, :n_used], to_rows(od, 16)[:, :n_used]), ("dy", mgrad(ys, cin), to_rows(yd.grad, cin)),
+                               ("dw", wb.grad, wbd.grad), ("db", bb.grad[:n_used], bbd.grad[:n_used])):
+                assert rel(a, b) < TOL, ("head final conv", n_used, name, rel(a, b))
         # ConvTranspose2d k2 s2 (pixel-shuffle store), BatchNorm statistics of the fp32 output
         cin = cout = 64
         xt = torch.randn(M, cin, device="cuda", generator=g)

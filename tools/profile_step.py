@@ -31,7 +31,7 @@ for e in prof.events():
         agg[n][0] += 1; agg[n][1] += e.device_time
 tot = sum(v[1] for v in agg.values())
 mine = sum(v[1] for k, v in agg.items() if not k.startswith('torch:') and 'Memset' not in k and 'Memcpy' not in k)
-out = ["# torch.profiler (kineto) device-time table of ONE steady-state training step (%d frames x 30k pts), round 1" % frames,
+out = ["# torch.profiler (kineto) device-time table of ONE steady-state training step (%d frames x 30k pts), round 2" % frames,
        "# %d device activities, %.3f ms summed device time; libpnx kernels %.1f%%" % (sum(v[0] for v in agg.values()), tot / 1e3, 100 * mine / tot)]
 for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
     out.append("%9.3f ms %5.1f%% %5d  %s" % (t / 1e3, 100 * t / tot, c, k[:70]))
