@@ -192,15 +192,23 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    nccl_log = None
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own log (ring/tree/NVLS setup, nranks) goes to stderr so stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's own log (communicator init: nranks, rings/trees, NVLS) goes to a per-process file so stdout stays the one
+        # JSON line; rank 0 echoes the communicator lines to stderr at the end
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            logdir = os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "/tmp"
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(logdir, "nccl.%h.%p.log")
+            nccl_log = os.environ["NCCL_DEBUG_FILE"].replace("%h", os.uname().nodename).replace("%p", str(os.getpid()))
+        else:
+            nccl_log = None
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 5)     # >= one untimed step per distinct synthetic batch (4): the caching allocator has seen every size
     sel = synth.BENCH_CONFIGS[args.config]
@@ -382,6 +390,11 @@ def main():
                                     "and a 4-byte loss read-back (async copy to pinned memory + event, consumed one step late)"},
                 "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof, "voxelize": vox, "cpu_baseline": cpu}
         print(json.dumps(line))
+        if world > 1 and nccl_log and os.path.exists(nccl_log):
+            with open(nccl_log) as fh:
+                comm = [ln.strip() for ln in fh if "nranks" in ln or "NVLS" in ln][:6]
+            for ln in comm:
+                print(ln, file=sys.stderr)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

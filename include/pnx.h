@@ -144,7 +144,8 @@ int pnx_scatter_dense(const void* feat, const int* coords, const int* n_ptr, int
 
 /* ---------------------------------------------------------------- tcgen05 gather implicit GEMM
  * out[m, n] = sum_{t<taps} sum_{c<Cin} A[nbr(m,t), c] * W[t, n, c]  (+ bias[n]) (relu)
- *   A       [rows, lda] bf16        W  [taps, Cout, Cin] bf16 (packed, K-major)
+ *   A       [a_rows, lda] bf16 (a_rows = rows really allocated: the TMA map carries the true extent)
+ *   W       [taps, Cout, Cin] bf16 (packed, K-major)
  *   nbr(m,t): nbr[m*taps+t] if nbr != NULL; computed from the dense geometry if dense != 0
  *             (m -> (b, y, x) over Hout x Wout; source pixel (y*mul + r*dil - pad, x*mul + s*dil - pad)
  *             in an Hin x Win image, t = r*kw + s; out of range = zero);  m itself otherwise (taps==1).
@@ -154,7 +155,7 @@ int pnx_scatter_dense(const void* feat, const int* coords, const int* n_ptr, int
  *           (channel = n % stats_mod), for the BatchNorm that follows the convolution.
  * Replaces spconv SparseConv2d/SubMConv2d (sparse_conv.py:25-29,50-51), F.conv2d/nn.Conv2d
  * (aspp.py:19-32, conv.py:9-10, centerhead.py:35-46,108-114), nn.ConvTranspose2d (centerhead.py:26-27). */
-int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void* Wpacked, int Cout,
+int pnx_igemm(const void* A, long long lda, long long a_rows, int M, int taps, int Cin, const void* Wpacked, int Cout,
               int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
               int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
               double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
@@ -192,8 +193,8 @@ int pnx_conv3x3_win(const void* A, long long lda, int B, int H, int W, int Cin, 
  * the neighbour map: nbr[m*taps+t] if nbr != NULL, else the dense geometry (as pnx_igemm), else row m (taps==1,
  * gathered=0).  x_channels: 64 or a multiple of 128; y_channels: multiple of 64.  Backward of the layers
  * pnx_igemm replaces (autograd in the reference: trainer/trainer/trainer.py:94-108). */
-int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long long ldy, int y_channels,
-              int gathered, int M, int taps, const int* nbr, int Hout, int Wout, int Hin, int Win, int kw,
+int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long long ldy, long long y_rows,
+              int y_channels, int gathered, int M, int taps, const int* nbr, int Hout, int Wout, int Hin, int Win, int kw,
               int mul, int dil, int pad, int shuffle, float* dW, int sm_count, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- row-wise bf16 kernels

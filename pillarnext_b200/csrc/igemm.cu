@@ -657,7 +657,7 @@ int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmPa
 }  // namespace
 
 // Contract: include/pnx.h (pnx_igemm).
-extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin, const void* Wpacked, int Cout,
+extern "C" int pnx_igemm(const void* A, long long lda, long long a_rows, int M, int taps, int Cin, const void* Wpacked, int Cout,
                          int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
                          int mul, int dil, int pad, void* out, long long ldc, int out_fp32, const float* bias,
                          double* stats, int stats_C, int stats_mod, int shuffle, int relu, const void* addend,
@@ -717,10 +717,13 @@ extern "C" int pnx_igemm(const void* A, long long lda, int M, int taps, int Cin,
   int rc = pnx_encode_tmap_2d_bf16(&wmap, Wpacked, (uint64_t)taps * Cout, (uint64_t)wcols, (uint64_t)wcols * 2,
                                    (uint32_t)block_n, 64);
   if (rc) return rc;
-  // A as a 2-D tensor [rows, Cin] for tile::gather4 (box = one 64-channel row).  The row count only bounds the
-  // out-of-range test of the gather (index -1 = absent neighbour = zero fill); valid indices come from the caller.
+  // A as a 2-D tensor [a_rows, Cin] for tile::gather4 (box = one 64-channel row); index -1 = absent neighbour = out of
+  // range = zero fill.  The map carries the TRUE row count: a map that claims 2^31 rows (256 GB) makes the gather
+  // instruction fault ("warp illegal address") for some placements of A near the end of a mapping -- measured with
+  // tools/tma_tail_probe.py; with the exact extent it never does.
   CUtensorMap amap;
-  rc = pnx_encode_tmap_gather_bf16(&amap, A, (uint64_t)0x7fffffff, (uint64_t)((a_pieces - 1) * a_lo_off + Cin), (uint64_t)lda * 2);
+  PNX_CHECK_ARG(a_rows >= 1 && a_rows < 0x7fffffffLL, "a_rows = number of rows of A");
+  rc = pnx_encode_tmap_gather_bf16(&amap, A, (uint64_t)a_rows, (uint64_t)((a_pieces - 1) * a_lo_off + Cin), (uint64_t)lda * 2);
   if (rc) return rc;
   const int n_blocks = Cout / block_n;
   switch (block_n) {

@@ -314,8 +314,8 @@ int launch_wgrad(const CUtensorMap& xmap, const CUtensorMap& ymap, WgradParams p
 }  // namespace
 
 // Contract: include/pnx.h (pnx_wgrad).  dW must be zeroed (or hold the value to accumulate into).
-extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long long ldy, int y_channels,
-                         int gathered, int M, int taps, const int* nbr, int Hout, int Wout, int Hin, int Win, int kw,
+extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long long ldy, long long y_rows,
+                         int y_channels, int gathered, int M, int taps, const int* nbr, int Hout, int Wout, int Hin, int Win, int kw,
                          int mul, int dil, int pad, int shuffle, float* dW, int sm_count, cudaStream_t stream) {
   PNX_CHECK_ARG(M >= 0, "M");
   if (M == 0) return PNX_OK;
@@ -343,7 +343,8 @@ extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, const voi
   CUtensorMap xmap, ymap;
   int rc = pnx_encode_tmap_2d_bf16(&xmap, X, (uint64_t)M, (uint64_t)x_channels, (uint64_t)ldx * 2, kKS, 64);
   if (rc) return rc;
-  rc = pnx_encode_tmap_gather_bf16(&ymap, Y, (uint64_t)0x7fffffff, (uint64_t)y_channels, (uint64_t)ldy * 2);
+  PNX_CHECK_ARG(y_rows >= 1 && y_rows < 0x7fffffffLL, "y_rows = number of rows of Y");
+  rc = pnx_encode_tmap_gather_bf16(&ymap, Y, (uint64_t)y_rows, (uint64_t)y_channels, (uint64_t)ldy * 2);   // true extent: see pnx_igemm
   if (rc) return rc;
   // Y chunk: the largest of 256/192/128/64 dividing y_channels; taps per group bounded by 512 TMEM columns
   if (y_channels % 256 == 0) {

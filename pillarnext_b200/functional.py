@@ -114,6 +114,26 @@ class WLayout:
 
 
 _pack_cache = {}
+# Cache validity = (parameter version, optimizer generation).  The version counter alone is NOT enough: torch's fused
+# optimizers (AdamW(fused=True), the reference-scale default here) update the parameters through kernels that do not bump
+# `p._version` (measured on torch 2.11: version 0 -> 0 across step()), so a version-keyed cache would keep serving the
+# initial bf16 weights for the whole training run.  A global post-step hook on every torch optimizer advances the
+# generation; load_state_dict / manual in-place edits advance the version.
+_OPT_GENERATION = [0]
+
+
+def _on_optimizer_step(*_args, **_kwargs):
+    _OPT_GENERATION[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_step  # noqa: E402
+_register_post_step(_on_optimizer_step)
+
+
+def weights_changed():
+    """For optimizers that bypass torch.optim (none in this repo): invalidate every packed weight."""
+    _OPT_GENERATION[0] += 1
+
 
 
 def packed(w, layout, which, flip=False, split=False):
@@ -125,7 +145,7 @@ def packed(w, layout, which, flip=False, split=False):
             return layout.pack_fwd(w, split) if which == "fwd" else layout.pack_dgrad(w, flip, split)
     key = (id(w), which, flip, layout.kind, _P() if split else 0)
     ent = _pack_cache.get(key)
-    ver = w._version
+    ver = (w._version, _OPT_GENERATION[0])
     if ent is not None and ent[0] == ver and ent[1]() is w and ent[3] == w.data_ptr():
         return ent[2]
     with torch.no_grad():

@@ -199,22 +199,50 @@ class SparseResNet(nn.Module):
         self.out_channels = out_channels
 
     def _pyramid_from_plain(self, feat, coors, input_shape):
-        raise NotImplementedError(
-            "SparseResNet needs the rulebook built by pillarnext_b200's PillarFeatureNet (feat._pnx_vox); "
-            "feeding hand-made (features, coords) tensors is not supported yet")
+        """The reference's own calling convention, `backbone(features [P, C], coors [P, 3] int (b, y, x), (H, W))`
+        (sparse_resnet.py:61-64), for callers that do not come through this package's reader: the active-site bitmap,
+        its rank structure and the rulebook are built from the coordinates (any row order, rows must be unique sites).
+        Returns (voxel-like object, features in sorted-site order as bf16 rows (differentiable), row permutation).
+        Batch size = max(b) + 1 (the reference uses len(unique(b)), which breaks on an empty frame)."""
+        assert coors.dim() == 2 and coors.shape[1] == 3 and feat.shape[0] == coors.shape[0]
+        H, W = int(input_shape[0]), int(input_shape[1])
+        dev = feat.device
+        c = coors.to(dev).long()
+        batch = int(c[:, 0].max().item()) + 1 if c.shape[0] else 1
+        L = ops.lib()
+        vwords = (H + 31) // 32
+        key = (c[:, 0] * W + c[:, 2]) * (vwords * 32) + c[:, 1]          # bit index: (b, x, y) order = the reader's sort order
+        order = torch.argsort(key)
+        key = key[order]
+        if key.numel() > 1 and bool((key[1:] == key[:-1]).any()):
+            raise ValueError("SparseResNet: duplicate (b, y, x) coordinates")
+        words = L.pnx_voxelize_bitmap_words(batch, W, H)
+        bm = torch.zeros(words, dtype=torch.int32, device=dev)
+        bits = torch.ones_like(key, dtype=torch.int32) << (key & 31).to(torch.int32)
+        bm.index_add_(0, key >> 5, bits)                                   # distinct bits: the sum is the OR
+        lv = ops.level_from_mask_words(bm, batch, W, H)
+        vox = ops.Voxels()
+        vox.bitmap, vox.blockpref, vox.inblk = lv.bm, lv.blockpref, lv.inblk
+        vox.batch, vox.gx, vox.gy = batch, W, H
+        vox.counts = torch.cat([lv.count, lv.count]).contiguous()
+        rows = feat.index_select(0, order)
+        return vox, rows, order
 
     def forward(self, pillar_features, coors, input_shape):
         """-> dense [B, 256, H/8, W/8] (bf16, channels-last memory) like sparse_resnet.py:61-68.
         NOTE (Appendix A): B is the collated batch size, not len(unique(coors[:,0]))."""
         _require_cuda(pillar_features, "SparseResNet")
         vox = getattr(pillar_features, "_pnx_vox", None)
-        if vox is None:
-            return self._pyramid_from_plain(pillar_features, coors, input_shape)
-        pyr = getattr(vox, "pyramid", None)
-        if pyr is None:
-            pyr = vox.pyramid = build_pyramid(vox, self._layer_strides)
         split = Fn.get_precision() == "split"
-        x = Fn.SplitFn.apply(pillar_features) if split else Fn.ToBF16RowsFn.apply(pillar_features, vox.feat_bf16)
+        if vox is None:
+            vox, rows, _ = self._pyramid_from_plain(pillar_features, coors, input_shape)
+            pyr = vox.pyramid = build_pyramid(vox, self._layer_strides)
+            x = Fn.SplitFn.apply(rows.float()) if split else rows.to(torch.bfloat16)
+        else:
+            pyr = getattr(vox, "pyramid", None)
+            if pyr is None:
+                pyr = vox.pyramid = build_pyramid(vox, self._layer_strides)
+            x = Fn.SplitFn.apply(pillar_features) if split else Fn.ToBF16RowsFn.apply(pillar_features, vox.feat_bf16)
         for s, stage in enumerate(self.blocks):
             x = stage[0].run(x, pyr.entry[s])
             for blk in list(stage)[1:]:

@@ -418,7 +418,7 @@ def igemm(A, M, w_packed, taps, cin, cout, out, *, lda=None, ldc=None, nbr=None,
     add_f32 = 1 if (addend is not None and addend.dtype == torch.float32) else 0
     with _Timed("igemm", 2.0 * M * taps * cin * cout * nseg, 2.0 * M * (cin * min(taps, 2) + cout) + 2.0 * taps * cin * cout,
                 "M%d_T%d_K%d_N%d_bn%d%s" % (M, taps, cin, cout, bn, "_tbl" if nbr is not None else ("_dense" if dense else ""))):
-      check(lib().pnx_igemm(ptr(A), lda, M, taps, cin, ptr(w_packed), cout, bn, ptr(nbr) if nbr is not None else None,
+      check(lib().pnx_igemm(ptr(A), lda, A.shape[0], M, taps, cin, ptr(w_packed), cout, bn, ptr(nbr) if nbr is not None else None,
                           1 if dense else 0, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], ptr(out), ldc, out_fp32,
                           ptr(bias) if bias is not None else None, ptr(stats) if stats is not None else None, sC,
                           stats_mod or (sC if sC else 1), 1 if shuffle else 0, 1 if relu else 0,
@@ -483,7 +483,7 @@ def wgrad(X, x_channels, Y, y_channels, M, taps, dW, *, nbr=None, dense=None, sh
     _count(1)
     with _Timed("wgrad", 2.0 * M * taps * x_channels * y_channels, 2.0 * M * (x_channels + taps * y_channels),
                 "M%d_T%d_X%d_Y%d" % (M, taps, x_channels, y_channels)):
-      check(lib().pnx_wgrad(ptr(X), X.stride(0), x_channels, ptr(Y), Y.stride(0), y_channels, 1 if gathered else 0, M,
+      check(lib().pnx_wgrad(ptr(X), X.stride(0), x_channels, ptr(Y), Y.stride(0), Y.shape[0], y_channels, 1 if gathered else 0, M,
                           taps, ptr(nbr) if nbr is not None else None, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7],
                           1 if shuffle else 0, ptr(dW), sm_count(), stream()))
     return dW

@@ -213,3 +213,23 @@ def test_full_size_frame_independence_and_point_order():
         f1, c1, _ = model.reader(pts[perm].cuda())
     assert torch.equal(c0, c1)
     assert (f0 - f1).abs().max().item() < 1e-4
+
+
+def test_packed_weight_cache_follows_fused_optimizer_steps():
+    """torch's fused AdamW updates parameters without bumping `_version`: the packed bf16 weight cache must still be
+    refreshed after every optimizer step (it is keyed on an optimizer-step generation as well), otherwise the forward
+    keeps using the initial weights for the whole run."""
+    from pillarnext_b200 import functional as Fn
+    w = torch.nn.Parameter(torch.randn(64, 64, 3, 3, device="cuda") * 0.05)
+    lay = Fn.WLayout("dense")
+    p0 = Fn.packed(w, lay, "fwd")
+    assert Fn.packed(w, lay, "fwd") is p0                                   # cached while nothing changed
+    opt = torch.optim.AdamW([w], lr=1e-1, fused=True)
+    w.grad = torch.ones_like(w)
+    opt.step()
+    p1 = Fn.packed(w, lay, "fwd")
+    assert p1 is not p0 and not torch.equal(p1, p0)
+    assert torch.equal(p1, lay.pack_fwd(w.detach()))
+    with torch.no_grad():
+        w.mul_(2.0)                                                          # plain in-place edit: version counter
+    assert torch.equal(Fn.packed(w, lay, "fwd"), lay.pack_fwd(w.detach()))
