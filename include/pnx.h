@@ -175,6 +175,14 @@ int pnx_igemm(const void* A, long long lda, long long a_rows, int M, int taps, i
  * addend_fp32 = 1: `addend` is fp32 [M, ld_add] (requires out_fp32).  nseg = 1, seg_code = 0, a_lo_off = 0,
  * addend_fp32 = 0: the production bf16 path. */
 
+/* ---------------------------------------------------------------- weight repacking (one launch for the whole model)
+ * table = device array of n (<= 256) descriptors { const float* src; bf16* dst; int64 start; int64 base; int64 stride[4];
+ * int32 dim[4]; } (96 bytes): dst[((a*d1 + b)*d2 + c)*d3 + d] = bf16(src[base + a*s0 + b*s1 + c*s2 + d*s3]); `start` =
+ * running element offset of the entry, total = sum of element counts.  Converts the fp32 parameters (reference layouts:
+ * nn.Conv2d, spconv [Cout,kH,kW,Cin], nn.ConvTranspose2d) into the [tap, Cout, Cin] / [tap, Cin, Cout] bf16 operands of
+ * pnx_igemm / pnx_conv3x3_win after an optimizer step. */
+int pnx_pack_weights(const void* table, int n, long long total, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- dense 3x3 conv with TMA-folded im2col
  * out[(b,y,x), n] = sum_{r,s<3} sum_c A[(b, y+r-1, x+s-1), c] * W[r*3+s, n, c] (+bias)(relu), zero padding,
  * on a B x H x W channels-last image (A rows = pixels, row stride lda; W packed [9, Cout, Cin] like pnx_igemm).

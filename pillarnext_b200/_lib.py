@@ -66,6 +66,7 @@ _SIGS = {
     "pnx_bn_bwd_apply_split": [P, L, L, P, L, L, P, L, L, I, P, P, P, P, ctypes.c_double, I, P, P, P, L, L, P, L, L, P],
     "pnx_add_relu_split": [P, L, L, P, L, L, L, I, P, L, L, P],
     "pnx_relu_bwd_split": [P, L, P, L, L, L, I, P, L, L, P],
+    "pnx_pack_weights": [P, I, L, P],
     "pnx_assign_labels": [P, P, I, I, P, P, I, I, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, I,
                           ctypes.c_double, I, I, I, I, I, P, P, P, P, P, P, P, P],
     # F1: decode + rotated NMS.  common prefix = out, ld, B, H, W, C, offs, osf, vs_x, vs_y, pc_x, pc_y, score_thr, range6, rect

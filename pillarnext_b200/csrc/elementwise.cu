@@ -72,40 +72,45 @@ __global__ void __launch_bounds__(256)
 }
 
 // g = dy * (y > 0 if relu);  red[0:C] += sum g ; red[C:2C] += sum g * xhat,  xhat = (x - mean) * invstd
-template <int kThreads, int U>
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
-                                     const __nv_bfloat16* __restrict__ y, long long ldy,
-                                     const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-                                     const float* __restrict__ fscale, const float* __restrict__ fshift,
-                                     double* __restrict__ red) {
+// Register diet (round 2, ncu: 128 registers -> 24 % occupancy -> 4.7 TB/s): the threads accumulate the RAW moments
+// sum g and sum g*x; mean / invstd enter once per block in the fp64 tail (sum g*xhat = invstd * (sum g*x - mean * sum g)),
+// and the affine of the recomputed ReLU mask is only resident in the kMask == 2 instantiation.
+// kMask: 0 no ReLU | 1 mask from the stored output y | 2 mask recomputed from x (y = x*fscale + fshift)
+template <int kThreads, int U, int kMask>
+__global__ void __launch_bounds__(kThreads, 2048 / kThreads >= 3 ? 3 : 1)
+    bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                         const __nv_bfloat16* __restrict__ y, long long ldy,
+                         const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ fscale, const float* __restrict__ fshift,
+                         double* __restrict__ red) {
   extern __shared__ float sred[];  // [kThreads][16]
   const int cg = C >> 3;
   const int my_cg = threadIdx.x % cg;
   const int rows_per_block = kThreads / cg;
   const int my_row = threadIdx.x / cg;
   const int c0 = my_cg << 3;
-  float sg[8], sgx[8], mu[8], is[8], fs[8], fh[8];
+  float sg[8], sgx[8], fs[8], fh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     sg[k] = sgx[k] = 0.f;
-    mu[k] = mean[c0 + k];
-    is[k] = invstd[c0 + k];
-    fs[k] = y ? 0.f : fscale[c0 + k];   // y == nullptr: the ReLU mask is recomputed from x (saves one row-matrix read)
-    fh[k] = y ? 0.f : fshift[c0 + k];
+    if (kMask == 2) {
+      fs[k] = fscale[c0 + k];
+      fh[k] = fshift[c0 + k];
+    }
   }
   if (my_row < rows_per_block) {
     const long long step = rows_per_block;
     for (long long m0 = (long long)blockIdx.x * rows_per_block * U + my_row; m0 < M;
          m0 += (long long)gridDim.x * rows_per_block * U) {
-      uint4 gin[U], xin[U], yin[U];
+      uint4 gin[U], xin[U], yin[kMask == 1 ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long m = m0 + u * step;
         if (m < M) {
           gin[u] = *reinterpret_cast<const uint4*>(dy + m * lddy + c0);
           xin[u] = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
-          if (relu && y) yin[u] = *reinterpret_cast<const uint4*>(y + m * ldy + c0);
+          if (kMask == 1) yin[u] = *reinterpret_cast<const uint4*>(y + m * ldy + c0);
         }
       }
 #pragma unroll
@@ -114,18 +119,16 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long 
         float g[8], yy[8], xx[8];
         unpack8(gin[u], g);
         unpack8(xin[u], xx);
-        if (relu) {
-          if (y) unpack8(yin[u], yy);
-          else {
+        if (kMask == 1) unpack8(yin[u], yy);
+        if (kMask == 2) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
-          }
+          for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
+          const float gg = (kMask != 0 && !(yy[k] > 0.f)) ? 0.f : g[k];
           sg[k] += gg;
-          sgx[k] += gg * (xx[k] - mu[k]) * is[k];
+          sgx[k] = fmaf(gg, xx[k], sgx[k]);
         }
       }
     }
@@ -136,24 +139,29 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long 
     sred[threadIdx.x * 16 + 8 + k] = sgx[k];
   }
   __syncthreads();
-  // thread j < 2*C reduces one (which, channel) over the block's rows
-  for (int j = threadIdx.x; j < 2 * C; j += kThreads) {
-    const int which = j / C, c = j - which * C;
+  // thread c < C reduces both moments of one channel over the block's rows (fp64) and centres the second one
+  for (int c = threadIdx.x; c < C; c += kThreads) {
     const int g_ = c >> 3, k = c & 7;
-    double acc = 0.0;
-    for (int r = 0; r < rows_per_block; ++r) acc += (double)sred[(r * cg + g_) * 16 + which * 8 + k];
-    atomicAdd(&red[which * C + c], acc);
+    double ag = 0.0, agx = 0.0;
+    for (int r = 0; r < rows_per_block; ++r) {
+      ag += (double)sred[(r * cg + g_) * 16 + k];
+      agx += (double)sred[(r * cg + g_) * 16 + 8 + k];
+    }
+    atomicAdd(&red[c], ag);
+    atomicAdd(&red[C + c], (double)invstd[c] * (agx - (double)mean[c] * ag));
   }
 }
 
 // dx = gamma*invstd * (g - sum_g/n - xhat * sum_gx/n) ; optional dres (+)= g        (same thread layout as bn_apply)
-template <int U>
-__global__ void __launch_bounds__(256)
+// Folded to three per-channel coefficients, dx = A*g + B*x + D with A = gamma*invstd, B = -A*invstd*sum_gx/n,
+// D = -A*sum_g/n - B*mean (round 2: 125 registers / 24 % occupancy / 3.7 TB/s before).  kMask as above.
+template <int U, int kMask>
+__global__ void __launch_bounds__(256, 3)
     bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ y,
                         long long ldy, const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gamma, const double* __restrict__ red, float inv_n,
-                        const int* __restrict__ count_dev, int relu,
+                        const int* __restrict__ count_dev,
                         const float* __restrict__ fscale, const float* __restrict__ fshift,
                         __nv_bfloat16* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dres,
                         long long lddres, int dres_accumulate) {
@@ -162,29 +170,32 @@ __global__ void __launch_bounds__(256)
   const int my_cg = threadIdx.x % cg, my_row = threadIdx.x / cg;
   if (my_row >= rpb) return;
   const int c0 = my_cg << 3;
-  float ca[8], cb[8], cc[8], mu[8], is[8], fs[8], fh[8];
+  float cA[8], cB[8], cD[8], fs[8], fh[8];
   if (count_dev) inv_n = 1.f / (float)max(*count_dev, 1);   // SyncBatchNorm: population of all ranks, known on the device only
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = c0 + k;
-    fs[k] = y ? 0.f : fscale[c];
-    fh[k] = y ? 0.f : fshift[c];
-    is[k] = invstd[c];
-    mu[k] = mean[c];
-    ca[k] = gamma[c] * is[k];
-    cb[k] = (float)red[c] * inv_n;
-    cc[k] = (float)red[C + c] * inv_n;
+    if (kMask == 2) {
+      fs[k] = fscale[c];
+      fh[k] = fshift[c];
+    }
+    const float is = invstd[c], mu = mean[c];
+    const float a = gamma[c] * is;
+    const float sgn = (float)red[c] * inv_n, sgxn = (float)red[C + c] * inv_n;
+    cA[k] = a;
+    cB[k] = -a * is * sgxn;
+    cD[k] = -a * sgn - cB[k] * mu;
   }
   const long long step = rpb;
   for (long long mm = (long long)blockIdx.x * rpb * U + my_row; mm < M; mm += (long long)gridDim.x * rpb * U) {
-    uint4 gin[U], xin[U], yin[U];
+    uint4 gin[U], xin[U], yin[kMask == 1 ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long m = mm + u * step;
       if (m < M) {
         gin[u] = *reinterpret_cast<const uint4*>(dy + m * lddy + c0);
         xin[u] = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
-        if (relu && y) yin[u] = *reinterpret_cast<const uint4*>(y + m * ldy + c0);
+        if (kMask == 1) yin[u] = *reinterpret_cast<const uint4*>(y + m * ldy + c0);
       }
     }
 #pragma unroll
@@ -194,19 +205,16 @@ __global__ void __launch_bounds__(256)
     float g[8], yy[8], xx[8], o[8];
     unpack8(gin[u], g);
     unpack8(xin[u], xx);
-    if (relu) {
-      if (y) unpack8(yin[u], yy);
-      else {
+    if (kMask == 1) unpack8(yin[u], yy);
+    if (kMask == 2) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
-      }
+      for (int k = 0; k < 8; ++k) yy[k] = fmaf(xx[k], fs[k], fh[k]);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float gg = (relu && !(yy[k] > 0.f)) ? 0.f : g[k];
+      const float gg = (kMask != 0 && !(yy[k] > 0.f)) ? 0.f : g[k];
       g[k] = gg;
-      const float xh = (xx[k] - mu[k]) * is[k];
-      o[k] = ca[k] * (gg - cb[k] - xh * cc[k]);
+      o[k] = fmaf(cA[k], gg, fmaf(cB[k], xx[k], cD[k]));
     }
     *reinterpret_cast<uint4*>(dx + m * lddx + c0) = pack8(o);
     if (dres) {
@@ -281,8 +289,11 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long 
 }
 
 // grid for the (rows x channel-group) layout: enough blocks for ~16 waves, each thread streaming >= 4 rows
-inline int row_blocks(long long M, int C) {
-  constexpr int waves = 16;
+inline int tune_env(const char* name, int dflt) {   // developer knob (tools/bench_ew.py sweeps); unset in production
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+inline int row_blocks(long long M, int C, int waves) {
   const int rpb = 256 / (C / 8);
   long long b = (M + (long long)rpb * 4 - 1) / ((long long)rpb * 4);
   const long long cap = 148LL * waves;
@@ -295,6 +306,13 @@ inline int row_blocks(long long M, int C) {
     default: { constexpr int U = 4; __VA_ARGS__; } break; \
   }
 
+// kMask dispatch of the BatchNorm backward kernels (0 none | 1 stored y | 2 recomputed from x)
+#define PNX_DISPATCH_MASK(mask, ...)      \
+  switch (mask) {                         \
+    case 0: { constexpr int K = 0; __VA_ARGS__; } break; \
+    case 1: { constexpr int K = 1; __VA_ARGS__; } break; \
+    default: { constexpr int K = 2; __VA_ARGS__; } break; \
+  }
 inline int ew_blocks(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   long long cap = 148LL * 16;
@@ -309,7 +327,7 @@ extern "C" int pnx_bn_apply(const void* x, long long ldx, long long M, int C, co
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(C <= 2048, "C <= 2048");
   constexpr int u = 1;  // rows in flight per thread; measured (tools/bench_ew.py): 6.2 TB/s at U=1, slower unrolled
-  PNX_DISPATCH_U(u, bn_apply_kernel<U><<<row_blocks(M, C), 256, 0, stream>>>(
+  PNX_DISPATCH_U(u, bn_apply_kernel<U><<<row_blocks(M, C, 16), 256, 0, stream>>>(
                         (const __nv_bfloat16*)x, ldx, M, C, scale, shift, (const __nv_bfloat16*)res, ldr, relu,
                         (__nv_bfloat16*)y, ldy));
   PNX_CHECK_LAUNCH();
@@ -326,13 +344,14 @@ extern "C" int pnx_bn_bwd_reduce(const void* dy, long long lddy, const void* y, 
   PNX_CHECK_ARG(C / 8 <= kT, "C <= 2048");
   const int rows_per_block = kT / (C / 8);
   long long nb = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
-  constexpr int rw = 4;
+  static const int rw = tune_env("PNX_BN_BWD_REDUCE_WAVES", 3);
   if (nb > 148 * rw) nb = 148 * rw;
   if (nb < 1) nb = 1;
-  constexpr int u = 4;  // measured best (tools/bench_ew.py)
-  PNX_DISPATCH_U(u, bn_bwd_reduce_kernel<kT, U><<<(int)nb, kT, kT * 16 * sizeof(float), stream>>>(
+  static const int u = tune_env("PNX_BN_BWD_REDUCE_U", 4);
+  const int mask = !relu ? 0 : (y ? 1 : 2);
+  PNX_DISPATCH_MASK(mask, PNX_DISPATCH_U(u, bn_bwd_reduce_kernel<kT, U, K><<<(int)nb, kT, kT * 16 * sizeof(float), stream>>>(
                         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M,
-                        C, mean, invstd, relu, fscale, fshift, red));
+                        C, mean, invstd, fscale, fshift, red)));
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }
@@ -346,11 +365,15 @@ extern "C" int pnx_bn_bwd_apply(const void* dy, long long lddy, const void* y, l
   PNX_CHECK_ARG(C % 8 == 0, "C % 8");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(C <= 2048, "C <= 2048");
-  constexpr int u = 2;  // measured best: 4 rows in flight costs occupancy (161 registers)
-  PNX_DISPATCH_U(u, bn_bwd_apply_kernel<U><<<row_blocks(M, C), 256, 0, stream>>>(
+  static const int u = tune_env("PNX_BN_BWD_APPLY_U", 2);
+  // 3 resident CTAs per SM (80 registers): one full wave of long-lived CTAs beats 16 waves of short ones here, the
+  // per-CTA coefficient set-up (6 per-channel vectors, two of them fp64) is not free (3.49 -> 3.01 ms per step)
+  static const int waves = tune_env("PNX_BN_BWD_APPLY_WAVES", 3);
+  const int mask = !relu ? 0 : (y ? 1 : 2);
+  PNX_DISPATCH_MASK(mask, PNX_DISPATCH_U(u, bn_bwd_apply_kernel<U, K><<<row_blocks(M, C, waves), 256, 0, stream>>>(
                         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)y, ldy, (const __nv_bfloat16*)x, ldx, M,
-                        C, mean, invstd, gamma, red, (float)(1.0 / count), count_dev, relu, fscale, fshift, (__nv_bfloat16*)dx,
-                        lddx, (__nv_bfloat16*)dres, lddres, dres_accumulate));
+                        C, mean, invstd, gamma, red, (float)(1.0 / count), count_dev, fscale, fshift, (__nv_bfloat16*)dx,
+                        lddx, (__nv_bfloat16*)dres, lddres, dres_accumulate)));
   PNX_CHECK_LAUNCH();
   return PNX_OK;
 }

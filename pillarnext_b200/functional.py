@@ -98,6 +98,27 @@ class WLayout:
             p = p.transpose(1, 2)
         return _to_hilo(p.float()) if split else p.to(torch.bfloat16).contiguous()
 
+    def gather_desc(self, shape, which, flip):
+        """The bf16 packed operand as a 4-D gather-copy of the fp32 parameter (pnx_pack_weights, csrc/pack.cu):
+        (dims, element strides into the parameter, base offset) with dst contiguous over dims."""
+        if self.kind == "sp":
+            co, kh, kw, ci = shape
+            if which == "fwd":
+                return (kw, kh, co, ci), (ci, kw * ci, kh * kw * ci, 1), 0
+            sg = -1 if flip else 1
+            return (kw, kh, ci, co), (sg * ci, sg * kw * ci, 1, kh * kw * ci), ((kw - 1) * ci + (kh - 1) * kw * ci) if flip else 0
+        if self.kind == "dense":
+            co, ci, kh, kw = shape
+            T = kh * kw
+            if which == "fwd":
+                return (1, T, co, ci), (0, 1, ci * T, T), 0
+            return (1, T, ci, co), (0, -1 if flip else 1, T, ci * T), (T - 1) if flip else 0
+        ci, co, kh, kw = shape
+        T = kh * kw
+        if which == "fwd":
+            return (1, T, co, ci), (0, 1, T, co * T), 0
+        return (1, T, ci, co), (0, 1, co * T, T), 0
+
     def unpack_grad(self, g, shape):
         """g fp32 [taps, Cout, Cin] (convT: [4, Cin, Cout]) -> gradient in the parameter's layout (always a fresh
         tensor: the accumulator may live in the per-step zero arena)."""
@@ -146,14 +167,63 @@ def packed(w, layout, which, flip=False, split=False):
     key = (id(w), which, flip, layout.kind, _P() if split else 0)
     ent = _pack_cache.get(key)
     ver = (w._version, _OPT_GENERATION[0])
-    if ent is not None and ent[0] == ver and ent[1]() is w and ent[3] == w.data_ptr():
-        return ent[2]
+    if ent is not None and ent[1]() is w and ent[3] == w.data_ptr():
+        if ent[0] == ver:
+            return ent[2]
+        if not split and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous():
+            _repack_all(w.device)                      # every stale bf16 operand of the model in one launch
+            ent = _pack_cache.get(key)
+            if ent is not None and ent[0] == ver:
+                return ent[2]
     with torch.no_grad():
         p = layout.pack_fwd(w, split) if which == "fwd" else layout.pack_dgrad(w, flip, split)
     if len(_pack_cache) > 4096:      # ids of dead tensors: drop everything rather than grow without bound
         _pack_cache.clear()
     _pack_cache[key] = (ver, weakref.ref(w), p, w.data_ptr())
+    if not split:
+        _pack_table["dirty"] = True
     return p
+
+
+# One descriptor table for all cached bf16 operands (rebuilt when the set of entries changes -- the first two steps).
+_pack_table = {"dirty": True, "chunks": [], "keys": [], "rebuilds": 0}
+
+
+def _repack_all(device):
+    """After an optimizer step (or any in-place parameter edit) rewrite EVERY cached bf16 operand on `device` in place with
+    one pnx_pack_weights launch per 256 entries -- instead of ~2 torch kernels per (weight, layout) request."""
+    import struct
+    tb = _pack_table
+    alive = all((e := _pack_cache.get(k)) is not None and (w := e[1]()) is not None and w.data_ptr() == e[3] for k in tb["keys"])
+    if tb["dirty"] or not alive or tb.get("device") != device:
+        keys, chunks, blob, start = [], [], bytearray(), 0
+        for k, e in list(_pack_cache.items()):
+            w = e[1]()
+            if w is None or w.data_ptr() != e[3]:
+                del _pack_cache[k]
+                continue
+            if k[4] != 0 or w.device != device or w.dtype != torch.float32 or not w.is_contiguous():
+                continue
+            dims, strides, base = WLayout(k[3]).gather_desc(tuple(w.shape), k[1], k[2])
+            blob += struct.pack("<QQqq4q4i", w.data_ptr(), e[2].data_ptr(), start, base, *strides, *dims)
+            start += e[2].numel()
+            keys.append(k)
+            if len(keys) % 256 == 0:
+                chunks.append((blob, 256, start))
+                blob, start = bytearray(), 0
+        if len(keys) % 256:
+            chunks.append((blob, len(keys) % 256, start))
+        # pinned staging + async copy: a pageable .to(device) would block the host until the stream drains
+        tb["host"] = [torch.frombuffer(b, dtype=torch.uint8).clone().pin_memory() for b, _, _ in chunks]
+        tb["chunks"] = [(h.to(device, non_blocking=True), n, tot) for h, (_, n, tot) in zip(tb["host"], chunks)]
+        tb["keys"], tb["dirty"], tb["device"] = keys, False, device
+        tb["rebuilds"] += 1
+    for table, n, tot in tb["chunks"]:
+        ops.pack_weights(table, n, tot)
+    gen = _OPT_GENERATION[0]
+    for k in tb["keys"]:
+        e = _pack_cache[k]
+        _pack_cache[k] = ((e[1]()._version, gen), e[1], e[2], e[3])
 
 
 class ConvSpec:

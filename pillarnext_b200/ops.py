@@ -651,6 +651,12 @@ def wgrad_split(X, x_lo, x_channels, Y, y_lo, y_channels, M, taps, dW, **kw):
 _cls_tables = {}
 
 
+def pack_weights(table, n, total):
+    """pnx_pack_weights: rewrite all bf16 packed operands described by the device table (functional._repack_all)."""
+    _count(1)
+    check(lib().pnx_pack_weights(ptr(table), int(n), int(total), stream()))
+
+
 def assign_labels(gt_boxes, gt_cls, tasks, voxel_size, pc_range, out_size_factor, max_objs=500, gaussian_overlap=0.1,
                   min_radius=2):
     """AssignLabel + collate on the GPU (pnx_assign_labels): gt_boxes [B, N, 9] fp32 cuda, gt_cls [B, N] int32 cuda

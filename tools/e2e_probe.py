@@ -122,3 +122,4 @@ for name, kw in (("bench e2e loop (prefetch on side stream + wait_stream)", {}),
     bench_loop(3, **kw)
     print("%-60s %.2f ms" % (name, bench_loop(10, **kw)))
     print("%-60s %.2f ms (20 steps)" % (name, bench_loop(20, **kw)))
+from pillarnext_b200 import functional as _F; print("pack table rebuilds:", _F._pack_table["rebuilds"], "entries:", len(_F._pack_table["keys"]))
