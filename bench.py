@@ -443,17 +443,18 @@ def voxelize_roofline(dev, sel, pk):
     for total in (480000, 1920000, 7680000):
         frames = max(1, total // n)
         pts = synth.collate_points([base[i % nbase] for i in range(frames)]).to(dev)
-        v = ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False)
+        v = ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False, frame_sorted=True)
+        v.check_order()
         P = int(v.counts[0].item())
         Nv = int((v.pillar_of_point[:pts.shape[0]] >= 0).sum().item())
         for _ in range(3):
-            ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False)
+            ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False, frame_sorted=True)
         torch.cuda.synchronize()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
         t0.record()
         for _ in range(reps):
-            ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False)
+            ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False, frame_sorted=True)
         t1.record()
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / reps

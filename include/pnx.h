@@ -68,6 +68,20 @@ int pnx_voxelize(const float* points, int n_points, int batch, float min_x, floa
                  float vs_y, int gx, int gy, uint32_t* bitmap, uint16_t* inblk, int* blockcnt, int* blockpref,
                  int* cell_of_point, int* pillar_of_point, int* coords, int cap_pillars,
                  uint32_t* bucket_cnt, int* counts, cudaStream_t stream);
+/* Frame-tiled variant for points GROUPED BY FRAME in ascending batch index (the collate order, loader/collate.py:17-21):
+ * same arguments and bit-identical outputs as pnx_voxelize, but the occupancy bitmap of a frame lives in the shared memory
+ * of a thread-block cluster (marking and ranking are shared-memory / DSMEM operations instead of random L2 transactions)
+ * and HBM only sees streaming traffic.  Kernels: bounds (1024-ary search of the frame offsets) | mark (cluster per frame)
+ * | scan | rank (+ coords, blockpref).  scratch = pnx_voxelize_frames_scratch(batch) int32; the input order is verified on
+ * the device: scratch[0] != 0 after the call means the points were not grouped and every output is invalid (use
+ * pnx_voxelize).  pnx_voxelize_frames_supported: 1 when the geometry qualifies (whole 32-word blocks per frame, slices
+ * that fit shared memory with clusters of at most 8 CTAs). n_points must be > 0. */
+int pnx_voxelize_frames_scratch(int batch);
+int pnx_voxelize_frames_supported(int batch, int gx, int gy);
+int pnx_voxelize_frames(const float* points, int n_points, int batch, float min_x, float min_y, float vs_x,
+                        float vs_y, int gx, int gy, uint32_t* bitmap, uint16_t* inblk, int* blockcnt, int* blockpref,
+                        int* cell_of_point, int* pillar_of_point, int* coords, int cap_pillars,
+                        uint32_t* bucket_cnt, int* counts, int* scratch, cudaStream_t stream);
 /* CSR grouping of the kept points by pillar (input of the per-pillar mean / max, pillar_encoder.py:113-114,43):
  * bucket_off [cap_pillars+1], bucket_pts [n_points] (ascending point id inside a pillar), bucket_tmp scratch,
  * scan_scratch [cap_pillars/2048 + 4]; counts[1] receives the number of kept points. */

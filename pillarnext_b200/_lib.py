@@ -27,6 +27,9 @@ _SIGS = {
     "pnx_scan_blocks": [P, I, P, P, P],
     "pnx_blockcnt_size": [I],
     "pnx_voxelize": [P, I, I, F, F, F, F, I, I, P, P, P, P, P, P, P, I, P, P, P],
+    "pnx_voxelize_frames": [P, I, I, F, F, F, F, I, I, P, P, P, P, P, P, P, I, P, P, P, P],
+    "pnx_voxelize_frames_scratch": [I],
+    "pnx_voxelize_frames_supported": [I, I, I],
     "pnx_bucketize": [P, I, I, P, P, P, P, P, P, P],
     "pnx_bn_finalize": [P, I, P, L, P, P, F, F, P, P, P, P, P, P, P],
     "pnx_bn_eval_affine": [I, P, P, P, P, F, P, P, P],

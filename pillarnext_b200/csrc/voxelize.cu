@@ -381,7 +381,442 @@ __global__ void vox_sort_kernel(const int* __restrict__ bucket_tmp, const int* _
   bucket_pts[lo + rank] = i;
 }
 
+// =====================================================================================================================
+// Frame-tiled index generation (round 2).  The global-bitmap pipeline above issues one random RED.OR per point into HBM/L2
+// and three random L2 reads per point in the rank pass; both are bounded by the L2 transaction rate (measured ~100 G
+// RED/s, ~350 G random reads/s), which caps it near 0.2 of the HBM roofline whatever the streaming side does.  Here the
+// occupancy bitmap of ONE frame lives in the shared memory of a thread-block cluster (a nuScenes frame is 259 KB: 4 CTAs x
+// 65 KB), so marking and ranking are shared-memory operations -- local, or remote through distributed shared memory
+// (mapa + red/ld.shared::cluster) -- and HBM only sees streaming traffic:
+//   bounds  off[b] = first point of frame b (1024-ary search on the batch column; collate order = grouped by frame)
+//   mark    cluster b streams its frame's points once (cp.async.bulk ring), ORs them into the cluster's bitmap, stores
+//           the cell ids, then writes bitmap / in-block prefixes / block counts with coalesced stores (no memset pass)
+//   scan    exclusive scan of the per-CTA pillar counts (one small CTA)
+//   rank    cluster b reloads its bitmap slice (L2), rebuilds the prefixes in shared memory, emits blockpref and the
+//           sorted-unique coords, and turns every cell id into its pillar id with three shared-memory reads
+// Input order is VERIFIED, not assumed: a point whose batch index disagrees with the frame range it lies in, or bounds
+// that are not monotone, raise scratch[0] (the caller checks it at its next synchronisation and must then use
+// pnx_voxelize, which takes any order).  Outputs are identical to pnx_voxelize (same tests).
+constexpr int kFrThreads = 1024;
+constexpr int kFrStages = 2;
+constexpr int kFrCoordStage = 32;
+constexpr int kFrMaxCluster = 8;
+
+struct FrameCfg {
+  int W;     // bitmap words per frame (multiple of 32)
+  int nblk;  // 32-word blocks per frame
+  int bpc;   // blocks per CTA of the cluster
+  int cs;    // cluster size
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void red_or_cluster(uint32_t addr, uint32_t v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_cluster_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// point sub-range of cluster rank k: the frame's (extended) range cut in cs parts at EVEN point indices, so that every
+// bulk copy starts 16-byte aligned (a point is 24 bytes)
+__device__ __forceinline__ long long frame_cut(long long p0, long long p1, int k, int cs) {
+  if (k <= 0) return p0;
+  if (k >= cs) return p1;
+  const long long c = (p0 + (p1 - p0) * k / cs + 1) & ~1LL;
+  return c < p1 ? c : p1;
+}
+__device__ __forceinline__ void frame_range(const int* __restrict__ off, int b, int batch, int n, long long* p0, long long* p1) {
+  // frame 0 also owns the points in front of it, the last frame those behind it (batch index outside [0, batch): dropped)
+  long long a = b == 0 ? 0 : off[b], e = b == batch - 1 ? n : off[b + 1];
+  a = a < 0 ? 0 : (a > n ? n : a);
+  e = e < a ? a : (e > n ? n : e);
+  *p0 = a;
+  *p1 = e;
+}
+
+__global__ void __launch_bounds__(1024) vox_frame_bounds_kernel(const float* __restrict__ points, int n, int* __restrict__ off,
+                                                               int* __restrict__ status) {
+  __shared__ int s_first;
+  const int b = blockIdx.x;
+  int lo = 0, hi = n;  // the answer lies in [lo, hi]
+  while (lo < hi) {
+    const int span = hi - lo;
+    const int step = (span + 1023) / 1024;
+    const int nsamp = (span + step - 1) / step;
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    if ((int)threadIdx.x < nsamp && (int)__ldg(points + ((long long)lo + (long long)threadIdx.x * step) * 6) >= b)
+      atomicMin(&s_first, (int)threadIdx.x);
+    __syncthreads();
+    const int t = s_first;
+    __syncthreads();
+    if (t == 0x7fffffff) {
+      lo = lo + (nsamp - 1) * step + 1;
+    } else {
+      hi = lo + t * step;
+      lo = t > 0 ? hi - step + 1 : hi;
+    }
+  }
+  if (threadIdx.x == 0) {
+    off[b] = lo;
+    if (b == 0) *status = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kFrThreads) vox_frame_mark_kernel(const float* __restrict__ points, int n, VoxGeom g, FrameCfg f,
+                                                                    const int* __restrict__ off, uint32_t* __restrict__ bitmap,
+                                                                    uint16_t* __restrict__ inblk, int* __restrict__ blockcnt,
+                                                                    int* __restrict__ cell_of_point, int* __restrict__ cta_cnt,
+                                                                    int* __restrict__ status) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  const int words = f.bpc * 32;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(fsm);
+  float* ring = reinterpret_cast<float*>(fsm + (size_t)words * 4);
+  uint64_t* full = reinterpret_cast<uint64_t*>(fsm + (size_t)words * 4 + kFrStages * kVoxStageBytes);
+  __shared__ int s_warp_cnt[kFrThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = (int)cluster_ctarank(), b = blockIdx.x / f.cs;
+  for (int i = tid; i < words / 4; i += kFrThreads) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    for (int s = 0; s < kFrStages; ++s) pnx::mbar_init(&full[s], 1);
+    pnx::fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();  // every CTA's slice is zeroed before anybody marks
+  long long f0, f1;
+  frame_range(off, b, g.batch, n, &f0, &f1);
+  long long p0 = frame_cut(f0, f1, r, f.cs);
+  const long long p1 = frame_cut(f0, f1, r + 1, f.cs);
+  const uint32_t bits_addr = pnx::smem_u32(bits);
+  auto process = [&](const float* p, long long i) {
+    const float cx = __fdiv_rn(__fsub_rn(p[1], g.min_x), g.vs_x);
+    const float cy = __fdiv_rn(__fsub_rn(p[2], g.min_y), g.vs_y);
+    const bool inside = (cx >= 0.f) && (cx < (float)g.gx) && (cy >= 0.f) && (cy < (float)g.gy);
+    const int pb = (int)p[0];
+    int cell = -1;
+    if (pb != b) {
+      if (pb >= 0 && pb < g.batch) atomicAdd(status, 1);  // a point of another frame inside this frame's range: input not grouped
+    } else if (inside) {
+      const int xi = (int)cx, yi = (int)cy;
+      const int lw = xi * g.vwords + (yi >> 5);
+      const int owner = lw / words, loc = lw - owner * words;
+      red_or_cluster(mapa_u32(bits_addr + (uint32_t)loc * 4u, (uint32_t)owner), 1u << (yi & 31));
+      cell = ((b * g.gx + xi) * g.vwords + (yi >> 5)) * 32 + (yi & 31);
+    }
+    cell_of_point[i] = cell;
+  };
+  if ((p0 & 1) && p0 < p1) {  // odd start (only the frame's own first point can be): one plain load, then 16-byte aligned stages
+    if (tid == 0) {
+      float q[3];
+      for (int k = 0; k < 3; ++k) q[k] = __ldg(points + p0 * 6 + k);
+      process(q, p0);
+    }
+    ++p0;
+  }
+  const int n_stage = p1 > p0 ? (int)((p1 - p0 + kVoxStagePts - 1) / kVoxStagePts) : 0;
+  auto stage_pts = [&](int it) { return (int)min((long long)kVoxStagePts, p1 - (p0 + (long long)it * kVoxStagePts)); };
+  auto issue = [&](int it) {
+    const int s = it % kFrStages;
+    pnx::mbar_arrive_expect_tx(&full[s], kVoxStageBytes);
+    bulk_g2s(ring + (size_t)s * kVoxStagePts * 6, points + (p0 + (long long)it * kVoxStagePts) * 6, kVoxStageBytes, &full[s]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < min(n_stage, kFrStages); ++it)
+      if (stage_pts(it) == kVoxStagePts) issue(it);
+  for (int it = 0; it < n_stage; ++it) {
+    const int s = it % kFrStages;
+    const int np = stage_pts(it);
+    float* st = ring + (size_t)s * kVoxStagePts * 6;
+    if (np == kVoxStagePts) {
+      pnx::mbar_wait(&full[s], (uint32_t)((it / kFrStages) & 1));
+    } else {  // ragged last stage of this CTA's range: plain coalesced loads
+      const float* src = points + (p0 + (long long)it * kVoxStagePts) * 6;
+      for (int q = tid; q < np * 6; q += kFrThreads) st[q] = __ldg(src + q);
+      __syncthreads();
+    }
+    if (tid < np) process(st + tid * 6, p0 + (long long)it * kVoxStagePts + tid);
+    __syncthreads();
+    if (tid == 0 && it + kFrStages < n_stage && stage_pts(it + kFrStages) == kVoxStagePts) issue(it + kFrStages);
+  }
+  cluster_sync_all();  // all marks of the cluster have landed (release / acquire at cluster scope)
+  // ---- block popcounts + in-block prefixes, bitmap written once, coalesced
+  int mine = 0;
+  for (int lb = warp; lb < f.bpc; lb += kFrThreads / 32) {
+    const int fb = r * f.bpc + lb;
+    if (fb >= f.nblk) break;
+    const uint32_t w = bits[lb * 32 + lane];
+    const int c = __popc(w);
+    const int incl = warp_incl_scan(c);
+    const size_t gw = ((size_t)b * f.nblk + fb) * 32 + lane;
+    bitmap[gw] = w;
+    inblk[gw] = (uint16_t)(incl - c);
+    if (lane == 31) {
+      blockcnt[(size_t)b * f.nblk + fb] = incl;
+      mine += incl;
+    }
+  }
+  if (lane == 31) s_warp_cnt[warp] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_warp_cnt[lane];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) cta_cnt[blockIdx.x] = v;
+  }
+}
+
+// exclusive scan of the per-CTA pillar counts (n_cta = batch * cluster size values) + the monotonicity check of the bounds
+__global__ void __launch_bounds__(1024) vox_frame_scan_kernel(const int* __restrict__ cta_cnt, int n_cta, int* __restrict__ cta_base,
+                                                             const int* __restrict__ off, int batch, int n, int* __restrict__ status,
+                                                             int* __restrict__ blockpref_total, int* __restrict__ total_out) {
+  int carry = 0;
+  for (int base = 0; base < n_cta; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_cta ? cta_cnt[i] : 0;
+    int tot;
+    const int ex = block_excl_scan<1024>(v, &tot);
+    if (i < n_cta) cta_base[i] = ex + carry;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) {
+    *blockpref_total = carry;
+    if (total_out) *total_out = carry;
+  }
+  int bad = 0;
+  for (int b = threadIdx.x; b < batch; b += 1024) bad += (off[b] > off[b + 1]) || off[b] < 0 || off[b + 1] > n;
+  if (bad) atomicAdd(status, bad);
+}
+
+__global__ void __launch_bounds__(kFrThreads) vox_frame_rank_kernel(int n, VoxGeom g, FrameCfg f, const int* __restrict__ off,
+                                                                    const uint32_t* __restrict__ bitmap, const int* __restrict__ cta_base,
+                                                                    const int* __restrict__ cell_of_point, int* __restrict__ blockpref,
+                                                                    int* __restrict__ pillar_of_point, int* __restrict__ coords, int cap,
+                                                                    uint32_t* __restrict__ bucket_cnt) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  const int words = f.bpc * 32;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(fsm);
+  uint16_t* inb = reinterpret_cast<uint16_t*>(fsm + (size_t)words * 4);
+  int* bpref = reinterpret_cast<int*>(fsm + (size_t)words * 6);                       // [bpc + 1]
+  int* stage = reinterpret_cast<int*>(fsm + (size_t)words * 6 + ((size_t)f.bpc + 4) / 4 * 16);  // [32 warps][kFrCoordStage * 3]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = (int)cluster_ctarank(), b = blockIdx.x / f.cs;
+  const int my_blocks = max(0, min(f.bpc, f.nblk - r * f.bpc));
+  // A: slice of the bitmap -> shared memory, in-block prefixes, block counts
+  for (int lb = warp; lb < f.bpc; lb += kFrThreads / 32) {
+    uint32_t w = 0u;
+    if (lb < my_blocks) w = __ldg(bitmap + ((size_t)b * f.nblk + r * f.bpc + lb) * 32 + lane);
+    const int c = __popc(w);
+    const int incl = warp_incl_scan(c);
+    bits[lb * 32 + lane] = w;
+    inb[lb * 32 + lane] = (uint16_t)(incl - c);
+    if (lane == 31) bpref[lb] = incl;
+  }
+  __syncthreads();
+  // B: exclusive scan of the block counts, offset by the pillars in front of this CTA
+  {
+    int carry = __ldg(cta_base + blockIdx.x);
+    for (int base = 0; base < f.bpc; base += kFrThreads) {
+      const int i = base + tid;
+      const int v = i < f.bpc ? bpref[i] : 0;
+      int tot;
+      const int ex = block_excl_scan<kFrThreads>(v, &tot);
+      if (i < f.bpc) {
+        bpref[i] = ex + carry;
+        if (i < my_blocks) blockpref[(size_t)b * f.nblk + r * f.bpc + i] = ex + carry;
+      }
+      carry += tot;
+    }
+    if (tid == 0) bpref[f.bpc] = carry;
+  }
+  __syncthreads();
+  // C: coords (b, yi, xi) of this slice's pillars, rows in sorted-unique order
+  for (int lb = warp; lb < my_blocks; lb += kFrThreads / 32) {
+    const int base_idx = bpref[lb], total = bpref[lb + 1] - base_idx;
+    if (total == 0) continue;
+    uint32_t w = bits[lb * 32 + lane];
+    const int pre = (int)inb[lb * 32 + lane];
+    const int lw = (r * f.bpc + lb) * 32 + lane;
+    const int xi = lw / g.vwords, vw = lw - xi * g.vwords;
+    if (total <= kFrCoordStage && base_idx + total <= cap) {
+      int* cs = stage + warp * (kFrCoordStage * 3);
+      int k = pre;
+      while (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        cs[k * 3 + 0] = b;
+        cs[k * 3 + 1] = vw * 32 + bit;
+        cs[k * 3 + 2] = xi;
+        ++k;
+      }
+      __syncwarp();
+      int* dst = coords + (size_t)base_idx * 3;
+      for (int q = lane; q < total * 3; q += 32) dst[q] = cs[q];
+      __syncwarp();
+    } else {
+      int idx = base_idx + pre;
+      while (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        if (idx < cap) {
+          coords[(size_t)idx * 3 + 0] = b;
+          coords[(size_t)idx * 3 + 1] = vw * 32 + bit;
+          coords[(size_t)idx * 3 + 2] = xi;
+        }
+        ++idx;
+      }
+    }
+  }
+  cluster_sync_all();  // the tables of every CTA of the cluster are complete
+  // D: pillar id of every point of this CTA's share of the frame
+  long long f0, f1;
+  frame_range(off, b, g.batch, n, &f0, &f1);
+  const long long p0 = frame_cut(f0, f1, r, f.cs), p1 = frame_cut(f0, f1, r + 1, f.cs);
+  const uint32_t bits_addr = pnx::smem_u32(bits), inb_addr = pnx::smem_u32(inb), bpref_addr = pnx::smem_u32(bpref);
+  const int frame_word0 = b * f.W;
+  constexpr int kU = 4;
+  for (long long i0 = p0 + tid; i0 < p1; i0 += (long long)kFrThreads * kU) {
+    int cell[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = i0 + (long long)u * kFrThreads;
+      cell[u] = i < p1 ? __ldg(cell_of_point + i) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = i0 + (long long)u * kFrThreads;
+      if (i >= p1) break;
+      int pid = -1;
+      if (cell[u] >= 0) {
+        const int lw = (cell[u] >> 5) - frame_word0, bit = cell[u] & 31;
+        const uint32_t owner = (uint32_t)(lw / words);
+        const uint32_t loc = (uint32_t)lw - owner * (uint32_t)words;
+        const uint32_t wbits = ld_cluster_u32(mapa_u32(bits_addr + loc * 4u, owner));
+        const uint32_t pre = ld_cluster_u16(mapa_u32(inb_addr + loc * 2u, owner));
+        const uint32_t base = ld_cluster_u32(mapa_u32(bpref_addr + (loc >> 5) * 4u, owner));
+        pid = (int)(base + pre) + __popc(wbits & ((1u << bit) - 1u));
+        if (bucket_cnt) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bucket_cnt + pid) : "memory");
+      }
+      pillar_of_point[i] = pid;
+    }
+  }
+  cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
+}
+
+inline size_t frame_mark_smem(int bpc) { return (size_t)bpc * 128 + (size_t)kFrStages * kVoxStageBytes + kFrStages * 8 + 64; }
+inline size_t frame_rank_smem(int bpc) { return (size_t)bpc * 192 + ((size_t)bpc + 4) / 4 * 16 + (size_t)(kFrThreads / 32) * kFrCoordStage * 12 + 64; }
+
+// cluster size for a frame of nblk blocks: the smallest power of two whose slices fit two CTAs per SM (one if they must),
+// then widened until the grid covers the SMs
+inline int frame_cluster_size(int batch, int nblk, int sm_count) {
+  constexpr size_t two_per_sm = 113 * 1024, one_per_sm = 226 * 1024;
+  int cs = 0;
+  for (int c = 1; c <= kFrMaxCluster && !cs; c *= 2) {
+    const int bpc = (nblk + c - 1) / c;
+    if (frame_mark_smem(bpc) <= two_per_sm && frame_rank_smem(bpc) <= two_per_sm) cs = c;
+  }
+  for (int c = 1; c <= kFrMaxCluster && !cs; c *= 2) {
+    const int bpc = (nblk + c - 1) / c;
+    if (frame_mark_smem(bpc) <= one_per_sm && frame_rank_smem(bpc) <= one_per_sm) cs = c;
+  }
+  if (!cs) return 0;
+  while (cs < kFrMaxCluster && (long long)batch * cs < sm_count) cs *= 2;
+  return cs;
+}
+
+template <typename... Args>
+int launch_cluster(void (*kernel)(Args...), int grid, int cs, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kFrThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PNX_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+  return PNX_OK;
+}
+
 }  // namespace
+
+// Scratch (int32 elements) of pnx_voxelize_frames: [0] status, then bounds, per-CTA counts and bases.
+extern "C" int pnx_voxelize_frames_scratch(int batch) { return 8 + (batch + 1) + 2 * (batch * kFrMaxCluster + 1); }
+
+// 1 when pnx_voxelize_frames can run this geometry (whole 32-word blocks per frame, slices that fit shared memory).
+extern "C" int pnx_voxelize_frames_supported(int batch, int gx, int gy) {
+  if (batch <= 0 || gx <= 0 || gy <= 0) return 0;
+  const long long W = (long long)gx * ((gy + 31) / 32);
+  if (W % 32 != 0 || W * batch * 32 >= 2147483647LL) return 0;
+  return frame_cluster_size(batch, (int)(W / 32), 148) > 0 ? 1 : 0;
+}
+
+// Same outputs as pnx_voxelize for points grouped by frame (ascending batch index, the collate order); see the block
+// comment above.  scratch = pnx_voxelize_frames_scratch(batch) ints; scratch[0] != 0 after the call (read it at the next
+// synchronisation) means the input was not grouped and the outputs are invalid: call pnx_voxelize instead.
+extern "C" int pnx_voxelize_frames(const float* points, int n_points, int batch, float min_x, float min_y, float vs_x,
+                                   float vs_y, int gx, int gy, uint32_t* bitmap, uint16_t* inblk, int* blockcnt, int* blockpref,
+                                   int* cell_of_point, int* pillar_of_point, int* coords, int cap_pillars,
+                                   uint32_t* bucket_cnt, int* counts /* [0]=P */, int* scratch, cudaStream_t stream) {
+  PNX_CHECK_ARG(n_points > 0 && batch > 0 && gx > 0 && gy > 0, "bad sizes (n_points must be > 0: use pnx_voxelize for empty input)");
+  PNX_CHECK_ARG(vs_x > 0.f && vs_y > 0.f, "voxel size must be positive");
+  PNX_CHECK_ARG(pnx_voxelize_frames_supported(batch, gx, gy), "geometry not supported by the frame-tiled voxelizer");
+  PNX_CHECK_ARG((reinterpret_cast<uintptr_t>(points) & 15) == 0, "points must be 16-byte aligned");
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    PNX_CUDA(cudaGetDevice(&dev));
+    PNX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    PNX_CUDA(cudaFuncSetAttribute(vox_frame_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PNX_CUDA(cudaFuncSetAttribute(vox_frame_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  }
+  VoxGeom g{min_x, min_y, vs_x, vs_y, gx, gy, (gy + 31) / 32, batch};
+  FrameCfg f;
+  f.W = gx * g.vwords;
+  f.nblk = f.W / 32;
+  f.cs = frame_cluster_size(batch, f.nblk, sm_count);
+  f.bpc = (f.nblk + f.cs - 1) / f.cs;
+  int* status = scratch;
+  int* off = scratch + 8;
+  int* cta_cnt = off + batch + 1;
+  int* cta_base = cta_cnt + batch * kFrMaxCluster + 1;
+  const int n_cta = batch * f.cs;
+  if (bucket_cnt) PNX_CUDA(cudaMemsetAsync(bucket_cnt, 0, (size_t)(cap_pillars + 1) * 4 * 2, stream));
+  vox_frame_bounds_kernel<<<batch + 1, 1024, 0, stream>>>(points, n_points, off, status);
+  PNX_CHECK_LAUNCH();
+  int rc = launch_cluster(vox_frame_mark_kernel, n_cta, f.cs, frame_mark_smem(f.bpc), stream, points, n_points, g, f,
+                          (const int*)off, bitmap, inblk, blockcnt, cell_of_point, cta_cnt, status);
+  if (rc) return rc;
+  vox_frame_scan_kernel<<<1, 1024, 0, stream>>>(cta_cnt, n_cta, cta_base, off, batch, n_points, status,
+                                                blockpref + (size_t)batch * f.nblk, counts);
+  PNX_CHECK_LAUNCH();
+  rc = launch_cluster(vox_frame_rank_kernel, n_cta, f.cs, frame_rank_smem(f.bpc), stream, n_points, g, f, (const int*)off,
+                      (const uint32_t*)bitmap, (const int*)cta_base, (const int*)cell_of_point, blockpref, pillar_of_point,
+                      coords, cap_pillars, bucket_cnt);
+  return rc;
+}
 
 extern "C" size_t pnx_voxelize_bitmap_words(int batch, int gx, int gy) {
   size_t w = (size_t)batch * gx * ((gy + 31) / 32);

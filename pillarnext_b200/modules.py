@@ -51,11 +51,11 @@ class PillarNet(nn.Module):
         self.voxel_size = np.array(voxel_size)
         self.pc_range = np.array(pc_range)
 
-    def forward(self, points, batch_size=None):
+    def forward(self, points, batch_size=None, frame_sorted=False):
         _require_cuda(points, "PillarNet")
         if batch_size is None:
             batch_size = int(points[:, 0].max().item()) + 1 if points.shape[0] else 1
-        return ops.voxelize(points, batch_size, self.voxel_size, self.pc_range)
+        return ops.voxelize(points, batch_size, self.voxel_size, self.pc_range, frame_sorted=frame_sorted)
 
 
 class Pyramid:
@@ -70,7 +70,10 @@ def build_pyramid(vox, strides):
     levels = [lv0]
     for s in strides:
         levels.append(ops.level_dilate(levels[-1], int(s)))
-    counts = torch.cat([vox.counts] + [lv.count for lv in levels[1:]]).cpu().tolist()   # the one sync
+    status = getattr(vox, "status", None)
+    counts = torch.cat([vox.counts] + [lv.count for lv in levels[1:]] + ([status] if status is not None else [])).cpu().tolist()   # the one sync
+    if status is not None:
+        vox.check_order(counts.pop())          # frame-tiled voxelizer: the points must have been grouped by frame
     vox.P, vox.Nv = int(counts[0]), int(counts[1])
     ns = [vox.P] + [int(c) for c in counts[2:]]
     for lv, n in zip(levels, ns):
@@ -107,6 +110,10 @@ class PillarFeatureNet(nn.Module):
         self.voxelization = PillarNet(num_input_features, voxel_size, pc_range)
         self.pyramid_strides = None      # set by SingleStageDetector: build the backbone rulebook in the same sync
         self.batch_size = None           # frames per batch when known by the caller (else read from the points)
+        # collate_kitti (loader/collate.py:17-21) concatenates the frames in order, so the points arrive grouped by frame:
+        # the frame-tiled voxelizer applies (the order is verified on the device; a violation raises at the step's one
+        # host synchronisation).  Set False for point tensors in arbitrary order.
+        self.frame_sorted = False      # TODO(verify on GPU) -> True
 
     def forward(self, points):
         """points [N, 6] (batch_idx, x, y, z, intensity, time) -> (feat_max [P,64] fp32, coords [P,3] int32 (b,y,x),
@@ -116,7 +123,7 @@ class PillarFeatureNet(nn.Module):
         B = self.batch_size
         if B is None:
             B = int(points[:, 0].max().item()) + 1 if points.shape[0] else 1
-        vox = ops.voxelize(points, B, self.voxel_size, self.pc_range)
+        vox = ops.voxelize(points, B, self.voxel_size, self.pc_range, frame_sorted=self.frame_sorted)
         if self.pyramid_strides is not None:
             vox.pyramid = build_pyramid(vox, self.pyramid_strides)
         l0, l1 = self.pfn_layers[0], self.pfn_layers[1]

@@ -96,14 +96,32 @@ class Voxels:
 
     def sync_counts(self):
         if self.P is None:
-            c = self.counts.cpu()
+            if getattr(self, "status", None) is not None:
+                c = torch.cat([self.counts, self.status]).cpu()
+                self.check_order(c[2])
+            else:
+                c = self.counts.cpu()
             self.P, self.Nv = int(c[0]), int(c[1])
         return self.P, self.Nv
 
+    def check_order(self, status_value=None):
+        """Raise if the frame-tiled voxelizer found the points not grouped by frame (status_value: the already fetched
+        host copy of self.status; fetched here, with a synchronisation, when omitted)."""
+        if getattr(self, "status", None) is None:
+            return
+        bad = int(self.status.item()) if status_value is None else int(status_value)
+        if bad:
+            raise RuntimeError("pnx_voxelize_frames: %d point(s) lie outside their frame's range -- the points are not grouped "
+                               "by ascending batch index; use voxelize(..., frame_sorted=False)" % bad)
 
-def voxelize(points, batch, voxel_size, pc_range, buckets=True):
+
+def voxelize(points, batch, voxel_size, pc_range, buckets=True, frame_sorted=False):
     """V1-V2 index generation (pnx_voxelize) and, with buckets=True, the CSR grouping the PFN needs
-    (pnx_bucketize). points [N,6] fp32 cuda (b,x,y,z,i,t)."""
+    (pnx_bucketize). points [N,6] fp32 cuda (b,x,y,z,i,t).
+    frame_sorted=True: the points are grouped by frame in ascending batch index (what collate produces) -> the
+    frame-tiled kernels (pnx_voxelize_frames: occupancy bitmap in cluster shared memory).  The order is verified on the
+    device: `v.status` (int32 [1]) is non-zero when it did not hold and the outputs must be discarded -- check it at the
+    next host synchronisation (Voxels.check_order(), modules.build_pyramid does) and re-run with frame_sorted=False."""
     assert points.is_cuda and points.dtype == torch.float32 and points.dim() == 2 and points.shape[1] == 6, \
         "points must be a CUDA float32 [N, 6] tensor (batch_idx, x, y, z, intensity, time)"
     points = points.contiguous()
@@ -130,10 +148,19 @@ def voxelize(points, batch, voxel_size, pc_range, buckets=True):
     v.coords = torch.empty(max(cap_p, 1), 3, **i32)
     bucket_cnt = torch.empty(2 * (cap_p + 1), **i32) if buckets else None
     v.counts = torch.zeros(2, **i32)
-    _count(5 if n > 0 else 3)
-    check(L.pnx_voxelize(ptr(points), n, batch, v.min_x, v.min_y, v.vs_x, v.vs_y, gx, gy, ptr(v.bitmap), ptr(v.inblk),
-                         ptr(v.blockcnt), ptr(v.blockpref), ptr(cell), ptr(v.pillar_of_point), ptr(v.coords), cap_p,
-                         ptr(bucket_cnt) if buckets else None, ptr(v.counts), stream()))
+    v.status = None
+    if frame_sorted and n > 0 and L.pnx_voxelize_frames_supported(batch, gx, gy):
+        scratch = torch.empty(L.pnx_voxelize_frames_scratch(batch), **i32)
+        v.status = scratch[0:1]
+        _count(4)
+        check(L.pnx_voxelize_frames(ptr(points), n, batch, v.min_x, v.min_y, v.vs_x, v.vs_y, gx, gy, ptr(v.bitmap), ptr(v.inblk),
+                                    ptr(v.blockcnt), ptr(v.blockpref), ptr(cell), ptr(v.pillar_of_point), ptr(v.coords), cap_p,
+                                    ptr(bucket_cnt) if buckets else None, ptr(v.counts), ptr(scratch), stream()))
+    else:
+        _count(5 if n > 0 else 3)
+        check(L.pnx_voxelize(ptr(points), n, batch, v.min_x, v.min_y, v.vs_x, v.vs_y, gx, gy, ptr(v.bitmap), ptr(v.inblk),
+                             ptr(v.blockcnt), ptr(v.blockpref), ptr(cell), ptr(v.pillar_of_point), ptr(v.coords), cap_p,
+                             ptr(bucket_cnt) if buckets else None, ptr(v.counts), stream()))
     if buckets:
         scratch = torch.empty(cap_p // 2048 + 4, **i32)
         v.bucket_off = torch.empty(cap_p + 1, **i32)

@@ -10,9 +10,11 @@ from pillarnext_b200 import ops, synth
 pytestmark = pytest.mark.gpu
 
 
-def run_case(points, batch, cfg):
-    v = ops.voxelize(points.cuda(), batch, cfg["voxel_size"], cfg["pc_range"])
+def run_case(points, batch, cfg, frame_sorted=False):
+    v = ops.voxelize(points.cuda(), batch, cfg["voxel_size"], cfg["pc_range"], frame_sorted=frame_sorted)
     P, Nv = v.sync_counts()
+    if frame_sorted and points.shape[0]:
+        assert v.status is not None, "the frame-tiled kernels must be the ones that ran"
     ref = O.voxelize(points, cfg["voxel_size"], cfg["pc_range"])
     assert P == ref["coords"].shape[0]
     assert Nv == int(ref["keep"].sum())
@@ -66,6 +68,85 @@ def test_voxelize_waymo_shape_and_tiny():
     cfg = synth.tiny_config(40)  # V not a multiple of 32
     pts = synth.collate_points([synth.make_frame(s, 500, cfg) for s in range(2)])
     run_case(pts, 2, cfg)
+
+
+def frames_supported(batch, cfg):
+    g = ops.grid_size_xy(cfg["voxel_size"], cfg["pc_range"])
+    return bool(ops.lib().pnx_voxelize_frames_supported(batch, int(g[0]), int(g[1])))
+
+
+@pytest.mark.parametrize("n,batch,kind", [(30000, 1, "uniform"), (30001, 2, "lidar"), (1001, 3, "uniform"), (257, 1, "uniform"),
+                                          (30000, 6, "lidar"), (2999, 40, "lidar")])
+def test_frame_tiled_voxelizer_matches_oracle(n, batch, kind):
+    """pnx_voxelize_frames (cluster shared-memory bitmap) = same bit-exact contract as pnx_voxelize, for every cluster
+    size the scheduler picks (1 frame -> 8 CTAs, 40 frames -> 4), odd frame lengths (bulk copies start at even points)."""
+    cfg = synth.NUSC
+    assert frames_supported(batch, cfg)
+    pts = synth.collate_points([synth.make_frame(s, n + 7 * s, cfg, kind, sweeps=10) for s in range(batch)])
+    v, ref = run_case(pts, batch, cfg, frame_sorted=True)
+    # the occupancy bitmap / block prefixes feed the rulebook: identical to the general path's
+    w = ops.voxelize(pts.cuda(), batch, cfg["voxel_size"], cfg["pc_range"], frame_sorted=False)
+    assert torch.equal(v.bitmap, w.bitmap) and torch.equal(v.inblk, w.inblk) and torch.equal(v.blockpref, w.blockpref)
+
+
+def test_frame_tiled_voxelizer_edge_cases():
+    cfg = synth.NUSC
+    g = torch.Generator().manual_seed(5)
+    # an empty frame in the middle, a frame of one point, points outside the range, NaN / inf coordinates
+    f0 = torch.tensor(synth.make_frame(0, 5001, cfg, "lidar", sweeps=10))
+    f2 = torch.tensor(synth.make_frame(2, 1, cfg, "uniform"))
+    f3 = torch.tensor(synth.make_frame(3, 4000, cfg, "uniform"))
+    f3[:50, 0] = float("nan")
+    f3[50:60, 1] = float("inf")
+    f3[60:90, 0] = 1e6
+    pts = torch.cat([torch.nn.functional.pad(f, (1, 0), value=float(b)) for b, f in ((0, f0), (2, f2), (3, f3))])
+    run_case(pts, 4, cfg, frame_sorted=True)
+    # batch indices outside [0, batch) sit in front of / behind the frames in sorted order: dropped like everywhere else
+    lead = torch.nn.functional.pad(torch.tensor(synth.make_frame(9, 33, cfg, "uniform")), (1, 0), value=-1.0)
+    tail = torch.nn.functional.pad(torch.tensor(synth.make_frame(8, 77, cfg, "uniform")), (1, 0), value=4.0)
+    v = ops.voxelize(torch.cat([lead, pts, tail]).cuda(), 4, cfg["voxel_size"], cfg["pc_range"], frame_sorted=True)
+    w = ops.voxelize(torch.cat([lead, pts, tail]).cuda(), 4, cfg["voxel_size"], cfg["pc_range"], frame_sorted=False)
+    assert v.sync_counts() == w.sync_counts()
+    assert torch.equal(v.pillar_of_point, w.pillar_of_point) and torch.equal(v.coords[:v.P], w.coords[:w.P])
+    assert torch.equal(v.bucket_pts[:v.Nv], w.bucket_pts[:w.Nv]) and torch.equal(v.bucket_off[:v.P + 1], w.bucket_off[:w.P + 1])
+    # one hot pillar (5000 points in one cell): every mark hits the same shared-memory word
+    q = torch.zeros(5000, 6)
+    q[:, 1:3] = torch.rand(5000, 2, generator=g) * 0.07 + 1.0
+    run_case(q, 1, cfg, frame_sorted=True)
+
+
+def test_frame_tiled_voxelizer_rejects_ungrouped_points():
+    """The order is verified on the device: interleaved frames raise at the next synchronisation instead of producing
+    wrong indices."""
+    cfg = synth.NUSC
+    pts = synth.collate_points([synth.make_frame(s, 4000, cfg, "lidar", sweeps=10) for s in range(3)])
+    perm = torch.randperm(pts.shape[0], generator=torch.Generator().manual_seed(1))
+    v = ops.voxelize(pts[perm].cuda(), 3, cfg["voxel_size"], cfg["pc_range"], frame_sorted=True)
+    with pytest.raises(RuntimeError, match="not grouped"):
+        v.sync_counts()
+    # a single misplaced point is enough
+    one = pts.clone()
+    one[[10, 9000]] = one[[9000, 10]]
+    v = ops.voxelize(one.cuda(), 3, cfg["voxel_size"], cfg["pc_range"], frame_sorted=True)
+    with pytest.raises(RuntimeError, match="not grouped"):
+        v.sync_counts()
+    run_case(pts[perm], 3, cfg, frame_sorted=False)      # the general path takes any order
+
+
+def test_frame_tiled_voxelizer_waymo_and_fallback_geometry():
+    cfg = synth.WAYMO_BENCH
+    assert frames_supported(2, cfg)
+    pts = synth.collate_points([synth.make_frame(7 + s, 90000 + s, cfg, "uniform") for s in range(2)])
+    run_case(pts, 2, cfg, frame_sorted=True)
+    cfg = synth.tiny_config(40)  # 40 x 2 words per frame: not whole 32-word blocks -> the general kernels run
+    assert not frames_supported(2, cfg)
+    pts = synth.collate_points([synth.make_frame(s, 500, cfg) for s in range(2)])
+    v = ops.voxelize(pts.cuda(), 2, cfg["voxel_size"], cfg["pc_range"], frame_sorted=True)
+    assert v.status is None
+    cfg = synth.tiny_config(128)
+    assert frames_supported(2, cfg)
+    pts = synth.collate_points([synth.make_frame(s, 3000, cfg) for s in range(2)])
+    run_case(pts, 2, cfg, frame_sorted=True)
 
 
 def test_pfn_forward_matches_oracle():

@@ -32,6 +32,6 @@ for n in win_fwd win_dgrad igemm_256 wgrad_head wgrad_256 vox_mark vox_rank bn_b
   python tools/ncu_keys.py $O/r2_$n.ncu-rep "" >> $O/ncu_r2_kernels.txt 2>&1
   echo >> $O/ncu_r2_kernels.txt
 done
-cuobjdump -sass pillarnext_b200/libpnx.so | grep -oE "^\s+/\*[0-9a-f]+\*/\s+[A-Z0-9_.]+" | awk '{print $2}' | \
+cuobjdump -sass pillarnext_b200/libpnx.so | grep -oE "^\s+/\*[0-9a-f]+\*/\s+[A-Za-z0-9_.]+" | awk '{print $2}' | \
   grep -E "^(UTCHMMA|UTCMMA|UTMALDG|UTMASTG|UTCBAR|UTCCP|SYNCS|UBLKCP|LDTM|STTM|REDG|RED|ATOMG|UTMAPF|UTMACCTL)" | sort | uniq -c | sort -rn > $O/sass_mnemonics_r2.txt
 echo done
