@@ -387,12 +387,20 @@ def main():
     ig[1] = max(ig[1], 1e-9)
     roof = {"bound": "tensor", "kernel": "igemm_kernel + igemm_win_kernel (tcgen05 implicit GEMM: TMA gather4 / TMA window producers; fwd+dgrad)",
             "achieved": ig[0] / (ig[1] * 1e-3) / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-            "frac": ig[0] / (ig[1] * 1e-3) / 1e12 / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+            "frac": ig[0] / (ig[1] * 1e-3) / 1e12 / pk["tf_sust"], "traffic": None, "traffic_detail": None, "peak_source": pk["src"] + " (sustained bf16)",
             "launches": ig[2], "flops_per_step": ig[0], "share_of_step": ig[1] / (ms / args.steps),
             "wgrad": {"achieved": agg["wgrad"][0] / (agg["wgrad"][1] * 1e-3) / 1e12, "launches": agg["wgrad"][2],
                       "share_of_step": agg["wgrad"][1] / (ms / args.steps)} if "wgrad" in agg else None,
             "note": "executed MMA flops (zero-filled absent neighbours included); per-launch CUDA events in a probe step"}
 
+    if args.config == "nusc" and args.frames == 6:
+        tr = traffic_from_profile(("igemm_kernel", "igemm_win_kernel"))
+        if tr:
+            roof["traffic"] = tr["bytes_per_launch"]
+            roof["traffic_detail"] = dict(tr, unit="bytes of DRAM traffic per launch, averaged over the %d igemm launches of one step "
+                                                   "(ncu launch list, same workload)" % tr["launches"],
+                                          algorithmic_note="bound is tensor: DRAM traffic is reported for completeness, "
+                                                           "flops per launch = flops_per_step / launches")
     # ---- voxelizer HBM roofline (second half of the BASELINE metric): many frames per launch so bytes >= 64 MB
     vox = None
     if rank == 0:
@@ -431,6 +439,26 @@ def main():
         dist.destroy_process_group()
 
 
+def traffic_from_profile(kernel_prefixes, path=None):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel family, from the committed ncu
+    launch list of one training step of the nuScenes bench config (profiles/launches_r2_summary.txt, produced by
+    tools/ncu_round2.sh + tools/launch_summary.py).  None when the file is absent."""
+    path = path or os.path.join(ROOT, "profiles", "launches_r2_summary.txt")
+    if not os.path.exists(path):
+        return None
+    tot, n = 0.0, 0
+    with open(path) as fh:
+        for ln in fh:
+            f = ln.split()
+            if ln.startswith("#") or len(f) < 7:
+                continue
+            name = " ".join(f[6:])
+            if any(k in name for k in kernel_prefixes):
+                tot += (float(f[3]) + float(f[4])) * 1e6
+                n += int(f[2])
+    return {"bytes_per_launch": tot / n, "launches": n, "source": os.path.relpath(path, ROOT)} if n else None
+
+
 def voxelize_roofline(dev, sel, pk):
     """Index-generation voxelizer (pnx_voxelize: V1-V2) swept over frames per launch on the selected config's point
     clouds.  Algorithmic bytes: 24*N + 4*Nv + 12*P; the headline entry is the largest launch (>= 64 MB of
@@ -440,27 +468,41 @@ def voxelize_roofline(dev, sel, pk):
     nbase = 16 if n <= 60000 else 4
     base = [synth.make_frame(5000 + i, n, cfg, "lidar", sweeps=sel["sweeps"], rings=sel["rings"]) for i in range(nbase)]
     sweep = []
+    tiled = None
     for total in (480000, 1920000, 7680000):
         frames = max(1, total // n)
         pts = synth.collate_points([base[i % nbase] for i in range(frames)]).to(dev)
-        v = ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False, frame_sorted=True)
-        v.check_order()
+        v = ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False)
+        tiled = v.status is not None
         P = int(v.counts[0].item())
         Nv = int((v.pillar_of_point[:pts.shape[0]] >= 0).sum().item())
         for _ in range(3):
-            ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False, frame_sorted=True)
+            ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False)
         torch.cuda.synchronize()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
         t0.record()
         for _ in range(reps):
-            ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False, frame_sorted=True)
+            ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False)
         t1.record()
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / reps
         alg = 24.0 * pts.shape[0] + 4.0 * Nv + 12.0 * P
-        sweep.append({"frames_per_launch": frames, "points": int(pts.shape[0]), "pillars": P, "algorithmic_bytes": alg, "ms": ms,
+        sweep.append({"frames_per_launch": frames, "points": int(pts.shape[0]), "pillars": P, "algorithmic_bytes": alg, "ms": ms, "kernels": "frame-tiled" if tiled else "global-bitmap",
                       "achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm"]})
+        if total == 7680000 and ops.lib().pnx_voxelize_frames_supported(frames, *[int(x) for x in ops.grid_size_xy(cfg["voxel_size"], cfg["pc_range"])]):
+            # the alternative design (bitmap slices in shared memory), for the record: bit-exact, measured slower
+            f = lambda: ops.voxelize(pts, frames, cfg["voxel_size"], cfg["pc_range"], buckets=False, frame_sorted="force")
+            f().check_order()
+            for _ in range(2):
+                f()
+            torch.cuda.synchronize()
+            t0.record()
+            for _ in range(reps):
+                f()
+            t1.record()
+            torch.cuda.synchronize()
+            sweep[-1]["frame_tiled_ms"] = t0.elapsed_time(t1) / reps
         del pts, v
     best = sweep[-1]
     return {"bound": "hbm", "kernel": "pnx_voxelize", "achieved": best["achieved"], "peak": pk["hbm"],

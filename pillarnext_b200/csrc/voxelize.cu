@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(kVoxThreads, 1) vox_mark_kernel(const float* _
     if (tid < np) {
       const int cell = vox_cell(st + tid * 6, g);
       // fire-and-forget reduction: `atomicOr` with an unused result still compiles to ATOMG (a round trip per point,
-      // measured 3x slower for this pass); red.* is the REDG instruction
+      // measured 3x slower for this pass); red.* is the REDG instruction.  Warp-level aggregation of same-word marks
+      // (__match_any_sync + __reduce_or_sync, one RED per distinct word) was measured too: 78 -> 188 us -- MATCH.ANY costs
+      // more than the REDs it saves, L2 absorbs the duplicates.
       if (cell >= 0) asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(bitmap + (cell >> 5)), "r"(1u << (cell & 31)) : "memory");
       cell_of_point[p0 + (long long)it * kVoxStagePts + tid] = cell;
     }
@@ -310,49 +312,65 @@ __global__ void vox_rank_kernel(const int* __restrict__ cell_of_point, int n, co
   pillar_of_point[i] = pid;
 }
 
-// V2c: coords (b, yi, xi) of every pillar in sorted-unique order.  One warp per 32-word block (one coalesced 128-byte
-// read); empty blocks (known from blockpref) are skipped without touching the bitmap.  The pillars of a block are
-// consecutive rows of `coords`: they are staged in shared memory and written with coalesced stores.
+// V2c: coords (b, yi, xi) of every pillar in sorted-unique order.  One warp per kCoU 32-word blocks (coalesced 128-byte
+// reads, issued together with the block prefixes).  The pillars of a block are consecutive rows of `coords`: they are
+// staged in shared memory and written with coalesced stores.
 constexpr int kCoordStage = 128;   // pillars of one block staged per warp (3 ints each); denser blocks take the direct path
+constexpr int kCoU = 4;            // blocks per warp, all their loads in flight together (the kernel was load-latency bound:
+                                   // blockpref -> bitmap/inblk -> store, one block per warp: 98 us for 518 k blocks)
 __global__ void __launch_bounds__(256) vox_coords_kernel(const uint32_t* __restrict__ bitmap, const int* __restrict__ blockpref,
                                                          int n_blocks, VoxGeom g, int* __restrict__ coords, int cap,
                                                          const uint16_t* __restrict__ inblk) {
   __shared__ int s_stage[8 * kCoordStage * 3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int blk = (int)(((long long)blockIdx.x * 256 + threadIdx.x) >> 5);
-  if (blk >= n_blocks) return;
-  const int base_idx = __ldg(blockpref + blk), total = __ldg(blockpref + blk + 1) - base_idx;
-  if (total == 0) return;
-  const int w = blk * 32 + lane;
-  uint32_t bits = __ldg(bitmap + w);
-  const int pre = (int)__ldg(inblk + w);
-  const int row = w / g.vwords, vw = w - row * g.vwords;
-  const int b = row / g.gx, xi = row - b * g.gx;
-  if (total <= kCoordStage && base_idx + total <= cap) {
-    int* cs = s_stage + warp * (kCoordStage * 3);
-    int k = pre;
-    while (bits) {
-      const int bit = __ffs(bits) - 1;
-      bits &= bits - 1;
-      cs[k * 3 + 0] = b;
-      cs[k * 3 + 1] = vw * 32 + bit;  // yi
-      cs[k * 3 + 2] = xi;
-      ++k;
-    }
-    __syncwarp();
-    int* dst = coords + (size_t)base_idx * 3;
-    for (int q = lane; q < total * 3; q += 32) dst[q] = cs[q];
-  } else {
-    int idx = base_idx + pre;
-    while (bits) {
-      const int bit = __ffs(bits) - 1;
-      bits &= bits - 1;
-      if (idx < cap) {
-        coords[idx * 3 + 0] = b;
-        coords[idx * 3 + 1] = vw * 32 + bit;  // yi
-        coords[idx * 3 + 2] = xi;
+  const long long blk0 = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * kCoU;
+  if (blk0 >= n_blocks) return;
+  int base_idx[kCoU], total[kCoU], pre[kCoU];
+  uint32_t bits[kCoU];
+#pragma unroll
+  for (int u = 0; u < kCoU; ++u) {
+    const bool ok = blk0 + u < n_blocks;
+    const long long blk = ok ? blk0 + u : blk0;
+    base_idx[u] = __ldg(blockpref + blk);
+    total[u] = ok ? __ldg(blockpref + blk + 1) : 0;
+    bits[u] = __ldg(bitmap + blk * 32 + lane);
+    pre[u] = (int)__ldg(inblk + blk * 32 + lane);
+  }
+#pragma unroll
+  for (int u = 0; u < kCoU; ++u) {
+    const int tot = total[u] - (blk0 + u < n_blocks ? base_idx[u] : 0);
+    if (blk0 + u >= n_blocks || tot <= 0) continue;
+    const int w = (int)(blk0 + u) * 32 + lane;
+    uint32_t bw = bits[u];
+    const int row = w / g.vwords, vw = w - row * g.vwords;
+    const int b = row / g.gx, xi = row - b * g.gx;
+    if (tot <= kCoordStage && base_idx[u] + tot <= cap) {
+      int* cs = s_stage + warp * (kCoordStage * 3);
+      int k = pre[u];
+      while (bw) {
+        const int bit = __ffs(bw) - 1;
+        bw &= bw - 1;
+        cs[k * 3 + 0] = b;
+        cs[k * 3 + 1] = vw * 32 + bit;  // yi
+        cs[k * 3 + 2] = xi;
+        ++k;
       }
-      ++idx;
+      __syncwarp();
+      int* dst = coords + (size_t)base_idx[u] * 3;
+      for (int q = lane; q < tot * 3; q += 32) dst[q] = cs[q];
+      __syncwarp();
+    } else {
+      int idx = base_idx[u] + pre[u];
+      while (bw) {
+        const int bit = __ffs(bw) - 1;
+        bw &= bw - 1;
+        if (idx < cap) {
+          coords[(size_t)idx * 3 + 0] = b;
+          coords[(size_t)idx * 3 + 1] = vw * 32 + bit;  // yi
+          coords[(size_t)idx * 3 + 2] = xi;
+        }
+        ++idx;
+      }
     }
   }
 }
@@ -382,68 +400,45 @@ __global__ void vox_sort_kernel(const int* __restrict__ bucket_tmp, const int* _
 }
 
 // =====================================================================================================================
-// Frame-tiled index generation (round 2).  The global-bitmap pipeline above issues one random RED.OR per point into HBM/L2
-// and three random L2 reads per point in the rank pass; both are bounded by the L2 transaction rate (measured ~100 G
-// RED/s, ~350 G random reads/s), which caps it near 0.2 of the HBM roofline whatever the streaming side does.  Here the
-// occupancy bitmap of ONE frame lives in the shared memory of a thread-block cluster (a nuScenes frame is 259 KB: 4 CTAs x
-// 65 KB), so marking and ranking are shared-memory operations -- local, or remote through distributed shared memory
-// (mapa + red/ld.shared::cluster) -- and HBM only sees streaming traffic:
+// Frame-tiled index generation (round 2).  The global-bitmap pipeline above issues one random RED.OR per point into L2 and
+// three random L2 reads per point in the rank pass; both are bounded by the L2 transaction rate (measured ~100 G RED/s,
+// ~350 G random reads/s), which caps it near 0.2 of the HBM roofline whatever the streaming side does.  Here a SLICE of one
+// frame's occupancy bitmap lives in the shared memory of a CTA (a nuScenes frame is 259 KB = 2 slices of 130 KB), so marking
+// and ranking are LOCAL shared-memory operations and HBM/L2 only see streaming traffic:
 //   bounds  off[b] = first point of frame b (1024-ary search on the batch column; collate order = grouped by frame)
-//   mark    cluster b streams its frame's points once (cp.async.bulk ring), ORs them into the cluster's bitmap, stores
-//           the cell ids, then writes bitmap / in-block prefixes / block counts with coalesced stores (no memset pass)
+//   mark    CTA (b, s) streams ALL points of frame b (cp.async.bulk ring; the second slice's read is an L2 hit), ORs the
+//           ones that fall into slice s into its bitmap, stores their cell ids, then writes bitmap / in-block prefixes /
+//           block counts with coalesced stores (no memset pass, no re-read)
 //   scan    exclusive scan of the per-CTA pillar counts (one small CTA)
-//   rank    cluster b reloads its bitmap slice (L2), rebuilds the prefixes in shared memory, emits blockpref and the
-//           sorted-unique coords, and turns every cell id into its pillar id with three shared-memory reads
+//   rank    CTA (b, s) reloads its slice (L2), rebuilds the prefixes in shared memory, emits blockpref and the sorted-unique
+//           coords, streams the frame's cell ids and turns the ones of its slice into pillar ids with three shared-memory reads
+// A first version kept ONE copy of the frame's points per cluster and marked / ranked through distributed shared memory
+// (red / ld.shared::cluster): bit-exact, but remote 4-byte transactions retire at only ~50-60 G/s chip-wide -- slower than
+// the L2 atomics they were meant to replace (rank 379 us, mark 153 us for 7.68 M points) -- so the slices read the points
+// redundantly from L2 instead and every fine-grained access is local.
 // Input order is VERIFIED, not assumed: a point whose batch index disagrees with the frame range it lies in, or bounds
 // that are not monotone, raise scratch[0] (the caller checks it at its next synchronisation and must then use
 // pnx_voxelize, which takes any order).  Outputs are identical to pnx_voxelize (same tests).
 constexpr int kFrThreads = 1024;
-constexpr int kFrStages = 2;
-constexpr int kFrCoordStage = 32;
-constexpr int kFrMaxCluster = 8;
+constexpr int kFrStagePts = 512;                      // points per ring stage (12 KB bulk copy)
+constexpr int kFrStageBytes = kFrStagePts * 24;
+constexpr int kFrMaxStages = 8;                       // the ring takes what the bitmap slice leaves of the shared memory
+constexpr int kFrMinStages = 4;
+constexpr int kFrMaxSlices = 8;
 
 struct FrameCfg {
-  int W;     // bitmap words per frame (multiple of 32)
-  int nblk;  // 32-word blocks per frame
-  int bpc;   // blocks per CTA of the cluster
-  int cs;    // cluster size
+  int W;       // bitmap words per frame (multiple of 32)
+  int nblk;    // 32-word blocks per frame
+  int bpc;     // blocks per slice
+  int cs;      // slices per frame
+  int cstage;  // pillars of one block staged per warp for the coords store
+  int stages;  // ring depth of the mark kernel
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void red_or_cluster(uint32_t addr, uint32_t v) {
-  asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t ld_cluster_u16(uint32_t addr) {
-  uint16_t v;
-  asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
-  return v;
+__device__ __forceinline__ void red_or_shared(uint32_t* addr, uint32_t v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(pnx::smem_u32(addr)), "r"(v) : "memory");
 }
 
-// point sub-range of cluster rank k: the frame's (extended) range cut in cs parts at EVEN point indices, so that every
-// bulk copy starts 16-byte aligned (a point is 24 bytes)
-__device__ __forceinline__ long long frame_cut(long long p0, long long p1, int k, int cs) {
-  if (k <= 0) return p0;
-  if (k >= cs) return p1;
-  const long long c = (p0 + (p1 - p0) * k / cs + 1) & ~1LL;
-  return c < p1 ? c : p1;
-}
 __device__ __forceinline__ void frame_range(const int* __restrict__ off, int b, int batch, int n, long long* p0, long long* p1) {
   // frame 0 also owns the points in front of it, the last frame those behind it (batch index outside [0, batch): dropped)
   long long a = b == 0 ? 0 : off[b], e = b == batch - 1 ? n : off[b + 1];
@@ -482,49 +477,51 @@ __global__ void __launch_bounds__(1024) vox_frame_bounds_kernel(const float* __r
   }
 }
 
-__global__ void __launch_bounds__(kFrThreads) vox_frame_mark_kernel(const float* __restrict__ points, int n, VoxGeom g, FrameCfg f,
-                                                                    const int* __restrict__ off, uint32_t* __restrict__ bitmap,
-                                                                    uint16_t* __restrict__ inblk, int* __restrict__ blockcnt,
-                                                                    int* __restrict__ cell_of_point, int* __restrict__ cta_cnt,
-                                                                    int* __restrict__ status) {
+__global__ void __launch_bounds__(kFrThreads, 1) vox_frame_mark_kernel(const float* __restrict__ points, int n, VoxGeom g, FrameCfg f,
+                                                                       const int* __restrict__ off, uint32_t* __restrict__ bitmap,
+                                                                       uint16_t* __restrict__ inblk, int* __restrict__ blockcnt,
+                                                                       int* __restrict__ cell_of_point, int* __restrict__ cta_cnt,
+                                                                       int* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t fsm[];
   const int words = f.bpc * 32;
   uint32_t* bits = reinterpret_cast<uint32_t*>(fsm);
   float* ring = reinterpret_cast<float*>(fsm + (size_t)words * 4);
-  uint64_t* full = reinterpret_cast<uint64_t*>(fsm + (size_t)words * 4 + kFrStages * kVoxStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(fsm + (size_t)words * 4 + (size_t)f.stages * kFrStageBytes);
+  const int S = f.stages;
   __shared__ int s_warp_cnt[kFrThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = (int)cluster_ctarank(), b = blockIdx.x / f.cs;
+  const int b = blockIdx.x / f.cs, r = blockIdx.x - b * f.cs;
   for (int i = tid; i < words / 4; i += kFrThreads) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
-    for (int s = 0; s < kFrStages; ++s) pnx::mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) pnx::mbar_init(&full[s], 1);
     pnx::fence_barrier_init();
   }
   __syncthreads();
-  cluster_sync_all();  // every CTA's slice is zeroed before anybody marks
-  long long f0, f1;
-  frame_range(off, b, g.batch, n, &f0, &f1);
-  long long p0 = frame_cut(f0, f1, r, f.cs);
-  const long long p1 = frame_cut(f0, f1, r + 1, f.cs);
-  const uint32_t bits_addr = pnx::smem_u32(bits);
+  long long p0, p1;
+  frame_range(off, b, g.batch, n, &p0, &p1);
+  const int w_lo = r * words;
   auto process = [&](const float* p, long long i) {
     const float cx = __fdiv_rn(__fsub_rn(p[1], g.min_x), g.vs_x);
     const float cy = __fdiv_rn(__fsub_rn(p[2], g.min_y), g.vs_y);
     const bool inside = (cx >= 0.f) && (cx < (float)g.gx) && (cy >= 0.f) && (cy < (float)g.gy);
     const int pb = (int)p[0];
-    int cell = -1;
-    if (pb != b) {
-      if (pb >= 0 && pb < g.batch) atomicAdd(status, 1);  // a point of another frame inside this frame's range: input not grouped
-    } else if (inside) {
+    if (pb != b) {  // a point of another frame inside this frame's range: the input is not grouped
+      if (r == 0) {
+        if (pb >= 0 && pb < g.batch) atomicAdd(status, 1);
+        cell_of_point[i] = -1;
+      }
+    } else if (!inside) {
+      if (r == 0) cell_of_point[i] = -1;
+    } else {
       const int xi = (int)cx, yi = (int)cy;
-      const int lw = xi * g.vwords + (yi >> 5);
-      const int owner = lw / words, loc = lw - owner * words;
-      red_or_cluster(mapa_u32(bits_addr + (uint32_t)loc * 4u, (uint32_t)owner), 1u << (yi & 31));
-      cell = ((b * g.gx + xi) * g.vwords + (yi >> 5)) * 32 + (yi & 31);
+      const int loc = xi * g.vwords + (yi >> 5) - w_lo;
+      if (loc >= 0 && loc < words) {  // this slice owns the cell: mark it and publish the cell id
+        red_or_shared(bits + loc, 1u << (yi & 31));
+        cell_of_point[i] = ((b * g.gx + xi) * g.vwords + (yi >> 5)) * 32 + (yi & 31);
+      }
     }
-    cell_of_point[i] = cell;
   };
-  if ((p0 & 1) && p0 < p1) {  // odd start (only the frame's own first point can be): one plain load, then 16-byte aligned stages
+  if ((p0 & 1) && p0 < p1) {  // odd first point: one plain load, then every stage starts 16-byte aligned (a point is 24 B)
     if (tid == 0) {
       float q[3];
       for (int k = 0; k < 3; ++k) q[k] = __ldg(points + p0 * 6 + k);
@@ -532,32 +529,34 @@ __global__ void __launch_bounds__(kFrThreads) vox_frame_mark_kernel(const float*
     }
     ++p0;
   }
-  const int n_stage = p1 > p0 ? (int)((p1 - p0 + kVoxStagePts - 1) / kVoxStagePts) : 0;
-  auto stage_pts = [&](int it) { return (int)min((long long)kVoxStagePts, p1 - (p0 + (long long)it * kVoxStagePts)); };
+  // ring of S stages of 512 points: S - 1 bulk copies stay in flight while one stage is processed (the loop is otherwise
+  // latency-bound: one 1024-point stage per ~1.3 us with a 2-deep ring, measured)
+  const int n_stage = p1 > p0 ? (int)((p1 - p0 + kFrStagePts - 1) / kFrStagePts) : 0;
+  auto stage_pts = [&](int it) { return (int)min((long long)kFrStagePts, p1 - (p0 + (long long)it * kFrStagePts)); };
   auto issue = [&](int it) {
-    const int s = it % kFrStages;
-    pnx::mbar_arrive_expect_tx(&full[s], kVoxStageBytes);
-    bulk_g2s(ring + (size_t)s * kVoxStagePts * 6, points + (p0 + (long long)it * kVoxStagePts) * 6, kVoxStageBytes, &full[s]);
+    const int s = it % S;
+    pnx::mbar_arrive_expect_tx(&full[s], kFrStageBytes);
+    bulk_g2s(ring + (size_t)s * kFrStagePts * 6, points + (p0 + (long long)it * kFrStagePts) * 6, kFrStageBytes, &full[s]);
   };
   if (tid == 0)
-    for (int it = 0; it < min(n_stage, kFrStages); ++it)
-      if (stage_pts(it) == kVoxStagePts) issue(it);
+    for (int it = 0; it < min(n_stage, S); ++it)
+      if (stage_pts(it) == kFrStagePts) issue(it);
   for (int it = 0; it < n_stage; ++it) {
-    const int s = it % kFrStages;
+    const int s = it % S;
     const int np = stage_pts(it);
-    float* st = ring + (size_t)s * kVoxStagePts * 6;
-    if (np == kVoxStagePts) {
-      pnx::mbar_wait(&full[s], (uint32_t)((it / kFrStages) & 1));
-    } else {  // ragged last stage of this CTA's range: plain coalesced loads
-      const float* src = points + (p0 + (long long)it * kVoxStagePts) * 6;
+    float* st = ring + (size_t)s * kFrStagePts * 6;
+    if (np == kFrStagePts) {
+      pnx::mbar_wait(&full[s], (uint32_t)((it / S) & 1));
+    } else {  // ragged last stage of the frame: plain coalesced loads
+      const float* src = points + (p0 + (long long)it * kFrStagePts) * 6;
       for (int q = tid; q < np * 6; q += kFrThreads) st[q] = __ldg(src + q);
       __syncthreads();
     }
-    if (tid < np) process(st + tid * 6, p0 + (long long)it * kVoxStagePts + tid);
+    if (tid < np) process(st + tid * 6, p0 + (long long)it * kFrStagePts + tid);
     __syncthreads();
-    if (tid == 0 && it + kFrStages < n_stage && stage_pts(it + kFrStages) == kVoxStagePts) issue(it + kFrStages);
+    if (tid == 0 && it + S < n_stage && stage_pts(it + S) == kFrStagePts) issue(it + S);
   }
-  cluster_sync_all();  // all marks of the cluster have landed (release / acquire at cluster scope)
+  __syncthreads();
   // ---- block popcounts + in-block prefixes, bitmap written once, coalesced
   int mine = 0;
   for (int lb = warp; lb < f.bpc; lb += kFrThreads / 32) {
@@ -584,7 +583,7 @@ __global__ void __launch_bounds__(kFrThreads) vox_frame_mark_kernel(const float*
   }
 }
 
-// exclusive scan of the per-CTA pillar counts (n_cta = batch * cluster size values) + the monotonicity check of the bounds
+// exclusive scan of the per-CTA pillar counts (n_cta = batch * slices values) + the monotonicity check of the bounds
 __global__ void __launch_bounds__(1024) vox_frame_scan_kernel(const int* __restrict__ cta_cnt, int n_cta, int* __restrict__ cta_base,
                                                              const int* __restrict__ off, int batch, int n, int* __restrict__ status,
                                                              int* __restrict__ blockpref_total, int* __restrict__ total_out) {
@@ -606,32 +605,41 @@ __global__ void __launch_bounds__(1024) vox_frame_scan_kernel(const int* __restr
   if (bad) atomicAdd(status, bad);
 }
 
-__global__ void __launch_bounds__(kFrThreads) vox_frame_rank_kernel(int n, VoxGeom g, FrameCfg f, const int* __restrict__ off,
-                                                                    const uint32_t* __restrict__ bitmap, const int* __restrict__ cta_base,
-                                                                    const int* __restrict__ cell_of_point, int* __restrict__ blockpref,
-                                                                    int* __restrict__ pillar_of_point, int* __restrict__ coords, int cap,
-                                                                    uint32_t* __restrict__ bucket_cnt) {
+__global__ void __launch_bounds__(kFrThreads, 1) vox_frame_rank_kernel(int n, VoxGeom g, FrameCfg f, const int* __restrict__ off,
+                                                                       const uint32_t* __restrict__ bitmap, const int* __restrict__ cta_base,
+                                                                       const int* __restrict__ cell_of_point, int* __restrict__ blockpref,
+                                                                       int* __restrict__ pillar_of_point, int* __restrict__ coords, int cap,
+                                                                       uint32_t* __restrict__ bucket_cnt) {
   extern __shared__ __align__(128) uint8_t fsm[];
   const int words = f.bpc * 32;
   uint32_t* bits = reinterpret_cast<uint32_t*>(fsm);
   uint16_t* inb = reinterpret_cast<uint16_t*>(fsm + (size_t)words * 4);
-  int* bpref = reinterpret_cast<int*>(fsm + (size_t)words * 6);                       // [bpc + 1]
-  int* stage = reinterpret_cast<int*>(fsm + (size_t)words * 6 + ((size_t)f.bpc + 4) / 4 * 16);  // [32 warps][kFrCoordStage * 3]
+  int* bpref = reinterpret_cast<int*>(fsm + (size_t)words * 6);                                   // [bpc + 1]
+  int* stage = reinterpret_cast<int*>(fsm + (size_t)words * 6 + ((size_t)f.bpc + 4) / 4 * 16);  // [32 warps][cstage * 3]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = (int)cluster_ctarank(), b = blockIdx.x / f.cs;
+  const int b = blockIdx.x / f.cs, r = blockIdx.x - b * f.cs;
   const int my_blocks = max(0, min(f.bpc, f.nblk - r * f.bpc));
-  // A: slice of the bitmap -> shared memory, in-block prefixes, block counts
-  for (int lb = warp; lb < f.bpc; lb += kFrThreads / 32) {
-    uint32_t w = 0u;
-    if (lb < my_blocks) w = __ldg(bitmap + ((size_t)b * f.nblk + r * f.bpc + lb) * 32 + lane);
-    const int c = __popc(w);
-    const int incl = warp_incl_scan(c);
-    bits[lb * 32 + lane] = w;
-    inb[lb * 32 + lane] = (uint16_t)(incl - c);
-    if (lane == 31) bpref[lb] = incl;
+  // A: slice of the bitmap -> shared memory, in-block prefixes, block counts (kA blocks per warp in flight: the loop
+  //    is load-latency bound otherwise)
+  constexpr int kA = 8;
+  for (int lb0 = warp * kA; lb0 < f.bpc; lb0 += (kFrThreads / 32) * kA) {
+    uint32_t w[kA];
+#pragma unroll
+    for (int u = 0; u < kA; ++u)
+      w[u] = (lb0 + u < my_blocks) ? __ldg(bitmap + ((size_t)b * f.nblk + r * f.bpc + lb0 + u) * 32 + lane) : 0u;
+#pragma unroll
+    for (int u = 0; u < kA; ++u) {
+      const int lb = lb0 + u;
+      if (lb >= f.bpc) break;
+      const int c = __popc(w[u]);
+      const int incl = warp_incl_scan(c);
+      bits[lb * 32 + lane] = w[u];
+      inb[lb * 32 + lane] = (uint16_t)(incl - c);
+      if (lane == 31) bpref[lb] = incl;
+    }
   }
   __syncthreads();
-  // B: exclusive scan of the block counts, offset by the pillars in front of this CTA
+  // B: exclusive scan of the block counts, offset by the pillars in front of this slice
   {
     int carry = __ldg(cta_base + blockIdx.x);
     for (int base = 0; base < f.bpc; base += kFrThreads) {
@@ -656,8 +664,8 @@ __global__ void __launch_bounds__(kFrThreads) vox_frame_rank_kernel(int n, VoxGe
     const int pre = (int)inb[lb * 32 + lane];
     const int lw = (r * f.bpc + lb) * 32 + lane;
     const int xi = lw / g.vwords, vw = lw - xi * g.vwords;
-    if (total <= kFrCoordStage && base_idx + total <= cap) {
-      int* cs = stage + warp * (kFrCoordStage * 3);
+    if (total <= f.cstage && base_idx + total <= cap) {
+      int* cs = stage + warp * (f.cstage * 3);
       int k = pre;
       while (w) {
         const int bit = __ffs(w) - 1;
@@ -685,92 +693,64 @@ __global__ void __launch_bounds__(kFrThreads) vox_frame_rank_kernel(int n, VoxGe
       }
     }
   }
-  cluster_sync_all();  // the tables of every CTA of the cluster are complete
-  // D: pillar id of every point of this CTA's share of the frame
-  long long f0, f1;
-  frame_range(off, b, g.batch, n, &f0, &f1);
-  const long long p0 = frame_cut(f0, f1, r, f.cs), p1 = frame_cut(f0, f1, r + 1, f.cs);
-  const uint32_t bits_addr = pnx::smem_u32(bits), inb_addr = pnx::smem_u32(inb), bpref_addr = pnx::smem_u32(bpref);
-  const int frame_word0 = b * f.W;
-  constexpr int kU = 4;
+  // D: pillar ids of the frame's points whose cell lies in this slice (slice 0 also writes the -1 of dropped points)
+  long long p0, p1;
+  frame_range(off, b, g.batch, n, &p0, &p1);
+  const int word0 = b * f.W + r * words;
+  constexpr int kU = 8;
   for (long long i0 = p0 + tid; i0 < p1; i0 += (long long)kFrThreads * kU) {
     int cell[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long i = i0 + (long long)u * kFrThreads;
-      cell[u] = i < p1 ? __ldg(cell_of_point + i) : -1;
+      cell[u] = i < p1 ? __ldg(cell_of_point + i) : -2;
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long i = i0 + (long long)u * kFrThreads;
-      if (i >= p1) break;
-      int pid = -1;
-      if (cell[u] >= 0) {
-        const int lw = (cell[u] >> 5) - frame_word0, bit = cell[u] & 31;
-        const uint32_t owner = (uint32_t)(lw / words);
-        const uint32_t loc = (uint32_t)lw - owner * (uint32_t)words;
-        const uint32_t wbits = ld_cluster_u32(mapa_u32(bits_addr + loc * 4u, owner));
-        const uint32_t pre = ld_cluster_u16(mapa_u32(inb_addr + loc * 2u, owner));
-        const uint32_t base = ld_cluster_u32(mapa_u32(bpref_addr + (loc >> 5) * 4u, owner));
-        pid = (int)(base + pre) + __popc(wbits & ((1u << bit) - 1u));
-        if (bucket_cnt) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bucket_cnt + pid) : "memory");
+      if (cell[u] == -2) break;
+      if (cell[u] < 0) {
+        if (r == 0) pillar_of_point[i] = -1;
+        continue;
       }
+      const int loc = (cell[u] >> 5) - word0, bit = cell[u] & 31;
+      if (loc < 0 || loc >= words) continue;
+      const int pid = bpref[loc >> 5] + (int)inb[loc] + __popc(bits[loc] & ((1u << bit) - 1u));
+      if (bucket_cnt) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bucket_cnt + pid) : "memory");
       pillar_of_point[i] = pid;
     }
   }
-  cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
 }
 
-inline size_t frame_mark_smem(int bpc) { return (size_t)bpc * 128 + (size_t)kFrStages * kVoxStageBytes + kFrStages * 8 + 64; }
-inline size_t frame_rank_smem(int bpc) { return (size_t)bpc * 192 + ((size_t)bpc + 4) / 4 * 16 + (size_t)(kFrThreads / 32) * kFrCoordStage * 12 + 64; }
-
-// cluster size for a frame of nblk blocks: the smallest power of two whose slices fit two CTAs per SM (one if they must),
-// then widened until the grid covers the SMs
-inline int frame_cluster_size(int batch, int nblk, int sm_count) {
-  constexpr size_t two_per_sm = 113 * 1024, one_per_sm = 226 * 1024;
-  int cs = 0;
-  for (int c = 1; c <= kFrMaxCluster && !cs; c *= 2) {
-    const int bpc = (nblk + c - 1) / c;
-    if (frame_mark_smem(bpc) <= two_per_sm && frame_rank_smem(bpc) <= two_per_sm) cs = c;
-  }
-  for (int c = 1; c <= kFrMaxCluster && !cs; c *= 2) {
-    const int bpc = (nblk + c - 1) / c;
-    if (frame_mark_smem(bpc) <= one_per_sm && frame_rank_smem(bpc) <= one_per_sm) cs = c;
-  }
-  if (!cs) return 0;
-  while (cs < kFrMaxCluster && (long long)batch * cs < sm_count) cs *= 2;
-  return cs;
+constexpr size_t kFrSmemMax = 226 * 1024;
+inline size_t frame_mark_smem(int bpc, int stages) { return (size_t)bpc * 128 + (size_t)stages * kFrStageBytes + stages * 8 + 64; }
+inline size_t frame_rank_smem(int bpc, int cstage) {
+  return (size_t)bpc * 192 + ((size_t)bpc + 4) / 4 * 16 + (size_t)(kFrThreads / 32) * cstage * 12 + 64;
 }
 
-template <typename... Args>
-int launch_cluster(void (*kernel)(Args...), int grid, int cs, size_t smem, cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kFrThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PNX_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
-  return PNX_OK;
+// slices per frame: the fewest whose tables fit the shared memory of one CTA per SM (every slice re-reads the frame's
+// points from L2, so fewer is better); 0 = the frame does not fit
+inline int frame_slices(int nblk) {
+  for (int c = 1; c <= kFrMaxSlices; ++c) {
+    const int bpc = (nblk + c - 1) / c;
+    if (frame_mark_smem(bpc, kFrMinStages) <= kFrSmemMax && frame_rank_smem(bpc, 8) <= kFrSmemMax) return c;
+  }
+  return 0;
 }
 
 }  // namespace
 
 // Scratch (int32 elements) of pnx_voxelize_frames: [0] status, then bounds, per-CTA counts and bases.
-extern "C" int pnx_voxelize_frames_scratch(int batch) { return 8 + (batch + 1) + 2 * (batch * kFrMaxCluster + 1); }
+extern "C" int pnx_voxelize_frames_scratch(int batch) { return 8 + (batch + 1) + 2 * (batch * kFrMaxSlices + 1); }
 
-// 1 when pnx_voxelize_frames can run this geometry (whole 32-word blocks per frame, slices that fit shared memory).
+// 0: pnx_voxelize_frames cannot run this geometry (a frame must be whole 32-word blocks and its slices must fit shared
+// memory); otherwise the number of CTAs it launches (batch * slices) -- the caller compares it with the SM count: with few
+// large frames (e.g. 14 frames of 540 k points) the global-bitmap kernels keep more of the machine busy.
 extern "C" int pnx_voxelize_frames_supported(int batch, int gx, int gy) {
   if (batch <= 0 || gx <= 0 || gy <= 0) return 0;
   const long long W = (long long)gx * ((gy + 31) / 32);
   if (W % 32 != 0 || W * batch * 32 >= 2147483647LL) return 0;
-  return frame_cluster_size(batch, (int)(W / 32), 148) > 0 ? 1 : 0;
+  return batch * frame_slices((int)(W / 32));
 }
 
 // Same outputs as pnx_voxelize for points grouped by frame (ascending batch index, the collate order); see the block
@@ -782,40 +762,43 @@ extern "C" int pnx_voxelize_frames(const float* points, int n_points, int batch,
                                    uint32_t* bucket_cnt, int* counts /* [0]=P */, int* scratch, cudaStream_t stream) {
   PNX_CHECK_ARG(n_points > 0 && batch > 0 && gx > 0 && gy > 0, "bad sizes (n_points must be > 0: use pnx_voxelize for empty input)");
   PNX_CHECK_ARG(vs_x > 0.f && vs_y > 0.f, "voxel size must be positive");
-  PNX_CHECK_ARG(pnx_voxelize_frames_supported(batch, gx, gy), "geometry not supported by the frame-tiled voxelizer");
+  PNX_CHECK_ARG(pnx_voxelize_frames_supported(batch, gx, gy) > 0, "geometry not supported by the frame-tiled voxelizer");
   PNX_CHECK_ARG((reinterpret_cast<uintptr_t>(points) & 15) == 0, "points must be 16-byte aligned");
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    PNX_CUDA(cudaGetDevice(&dev));
-    PNX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    PNX_CUDA(cudaFuncSetAttribute(vox_frame_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    PNX_CUDA(cudaFuncSetAttribute(vox_frame_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  static bool attr_set = false;
+  if (!attr_set) {
+    PNX_CUDA(cudaFuncSetAttribute(vox_frame_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrSmemMax));
+    PNX_CUDA(cudaFuncSetAttribute(vox_frame_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrSmemMax));
+    attr_set = true;
   }
   VoxGeom g{min_x, min_y, vs_x, vs_y, gx, gy, (gy + 31) / 32, batch};
   FrameCfg f;
   f.W = gx * g.vwords;
   f.nblk = f.W / 32;
-  f.cs = frame_cluster_size(batch, f.nblk, sm_count);
+  f.cs = frame_slices(f.nblk);
   f.bpc = (f.nblk + f.cs - 1) / f.cs;
+  f.cstage = 64;  // coords staging per warp: as much as the slice tables leave
+  while (f.cstage > 8 && frame_rank_smem(f.bpc, f.cstage) > kFrSmemMax) f.cstage -= 8;
+  f.stages = kFrMaxStages;
+  while (f.stages > kFrMinStages && frame_mark_smem(f.bpc, f.stages) > kFrSmemMax) --f.stages;
   int* status = scratch;
   int* off = scratch + 8;
   int* cta_cnt = off + batch + 1;
-  int* cta_base = cta_cnt + batch * kFrMaxCluster + 1;
+  int* cta_base = cta_cnt + batch * kFrMaxSlices + 1;
   const int n_cta = batch * f.cs;
   if (bucket_cnt) PNX_CUDA(cudaMemsetAsync(bucket_cnt, 0, (size_t)(cap_pillars + 1) * 4 * 2, stream));
   vox_frame_bounds_kernel<<<batch + 1, 1024, 0, stream>>>(points, n_points, off, status);
   PNX_CHECK_LAUNCH();
-  int rc = launch_cluster(vox_frame_mark_kernel, n_cta, f.cs, frame_mark_smem(f.bpc), stream, points, n_points, g, f,
-                          (const int*)off, bitmap, inblk, blockcnt, cell_of_point, cta_cnt, status);
-  if (rc) return rc;
+  vox_frame_mark_kernel<<<n_cta, kFrThreads, frame_mark_smem(f.bpc, f.stages), stream>>>(points, n_points, g, f, off, bitmap, inblk, blockcnt,
+                                                                               cell_of_point, cta_cnt, status);
+  PNX_CHECK_LAUNCH();
   vox_frame_scan_kernel<<<1, 1024, 0, stream>>>(cta_cnt, n_cta, cta_base, off, batch, n_points, status,
                                                 blockpref + (size_t)batch * f.nblk, counts);
   PNX_CHECK_LAUNCH();
-  rc = launch_cluster(vox_frame_rank_kernel, n_cta, f.cs, frame_rank_smem(f.bpc), stream, n_points, g, f, (const int*)off,
-                      (const uint32_t*)bitmap, (const int*)cta_base, (const int*)cell_of_point, blockpref, pillar_of_point,
-                      coords, cap_pillars, bucket_cnt);
-  return rc;
+  vox_frame_rank_kernel<<<n_cta, kFrThreads, frame_rank_smem(f.bpc, f.cstage), stream>>>(n_points, g, f, off, bitmap, cta_base, cell_of_point,
+                                                                                         blockpref, pillar_of_point, coords, cap_pillars,
+                                                                                         bucket_cnt);
+  PNX_CHECK_LAUNCH();
+  return PNX_OK;
 }
 
 extern "C" size_t pnx_voxelize_bitmap_words(int batch, int gx, int gy) {
@@ -863,7 +846,7 @@ extern "C" int pnx_voxelize(const float* points, int n_points, int batch, float 
   int rc = pnx_scan_blocks(blockcnt, n_blocks, blockpref, counts, stream);
   if (rc) return rc;
   if (n_points > 0) {
-    vox_coords_kernel<<<pnx_cdiv((long long)n_blocks * 32, 256), 256, 0, stream>>>(bitmap, blockpref, n_blocks, g, coords,
+    vox_coords_kernel<<<pnx_cdiv((long long)pnx_cdiv(n_blocks, kCoU) * 32, 256), 256, 0, stream>>>(bitmap, blockpref, n_blocks, g, coords,
                                                                                   cap_pillars, inblk);
   } else {
     PNX_CUDA(cudaMemsetAsync(inblk, 0, (size_t)n_words * 2, stream));

@@ -110,10 +110,10 @@ class PillarFeatureNet(nn.Module):
         self.voxelization = PillarNet(num_input_features, voxel_size, pc_range)
         self.pyramid_strides = None      # set by SingleStageDetector: build the backbone rulebook in the same sync
         self.batch_size = None           # frames per batch when known by the caller (else read from the points)
-        # collate_kitti (loader/collate.py:17-21) concatenates the frames in order, so the points arrive grouped by frame:
-        # the frame-tiled voxelizer applies (the order is verified on the device; a violation raises at the step's one
-        # host synchronisation).  Set False for point tensors in arbitrary order.
-        self.frame_sorted = False      # TODO(verify on GPU) -> True
+        # collate_kitti (loader/collate.py:17-21) concatenates the frames in order, so the points arrive grouped by frame and
+        # ops.voxelize MAY pick the frame-tiled kernels (ops.FRAME_TILED_MIN_CTAS; the order is then verified on the device
+        # and a violation raises at the step's one host synchronisation).  Set False for point tensors in arbitrary order.
+        self.frame_sorted = True
 
     def forward(self, points):
         """points [N, 6] (batch_idx, x, y, z, intensity, time) -> (feat_max [P,64] fp32, coords [P,3] int32 (b,y,x),

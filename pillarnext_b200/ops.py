@@ -115,13 +115,21 @@ class Voxels:
                                "by ascending batch index; use voxelize(..., frame_sorted=False)" % bad)
 
 
+# The frame-tiled kernels (pnx_voxelize_frames) are bit-exact but, measured on the B200, NOT faster than the global-bitmap
+# ones at any batch size (256 nuScenes frames: 416 us vs 290 us; ncu: instruction-issue bound, 139 M + 96 M warp
+# instructions -- every slice re-processes all points of its frame and the bitmap sweeps cost as much as the points), so
+# they only run on request (frame_sorted="force"); None = never chosen automatically.
+FRAME_TILED_MIN_CTAS = None
+
+
 def voxelize(points, batch, voxel_size, pc_range, buckets=True, frame_sorted=False):
     """V1-V2 index generation (pnx_voxelize) and, with buckets=True, the CSR grouping the PFN needs
     (pnx_bucketize). points [N,6] fp32 cuda (b,x,y,z,i,t).
     frame_sorted=True: the points are grouped by frame in ascending batch index (what collate produces) -> the
-    frame-tiled kernels (pnx_voxelize_frames: occupancy bitmap in cluster shared memory).  The order is verified on the
-    device: `v.status` (int32 [1]) is non-zero when it did not hold and the outputs must be discarded -- check it at the
-    next host synchronisation (Voxels.check_order(), modules.build_pyramid does) and re-run with frame_sorted=False."""
+    frame-tiled kernels (pnx_voxelize_frames: bitmap slices in shared memory) MAY be used: "force" = whenever the geometry
+    allows, True = when FRAME_TILED_MIN_CTAS says so (never, today: see there).  The order is verified on the device:
+    `v.status` (int32 [1]) is non-zero when it did not hold and the outputs must be discarded -- check it at the next
+    host synchronisation (Voxels.check_order(), modules.build_pyramid does) and re-run with frame_sorted=False."""
     assert points.is_cuda and points.dtype == torch.float32 and points.dim() == 2 and points.shape[1] == 6, \
         "points must be a CUDA float32 [N, 6] tensor (batch_idx, x, y, z, intensity, time)"
     points = points.contiguous()
@@ -149,7 +157,8 @@ def voxelize(points, batch, voxel_size, pc_range, buckets=True, frame_sorted=Fal
     bucket_cnt = torch.empty(2 * (cap_p + 1), **i32) if buckets else None
     v.counts = torch.zeros(2, **i32)
     v.status = None
-    if frame_sorted and n > 0 and L.pnx_voxelize_frames_supported(batch, gx, gy):
+    n_cta = L.pnx_voxelize_frames_supported(batch, gx, gy) if (frame_sorted and n > 0) else 0
+    if n_cta > 0 and (frame_sorted == "force" or (FRAME_TILED_MIN_CTAS is not None and n_cta >= FRAME_TILED_MIN_CTAS)):
         scratch = torch.empty(L.pnx_voxelize_frames_scratch(batch), **i32)
         v.status = scratch[0:1]
         _count(4)

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def run_case(points, batch, cfg, frame_sorted=False):
-    v = ops.voxelize(points.cuda(), batch, cfg["voxel_size"], cfg["pc_range"], frame_sorted=frame_sorted)
+    v = ops.voxelize(points.cuda(), batch, cfg["voxel_size"], cfg["pc_range"], frame_sorted="force" if frame_sorted else False)
     P, Nv = v.sync_counts()
     if frame_sorted and points.shape[0]:
         assert v.status is not None, "the frame-tiled kernels must be the ones that ran"
@@ -78,8 +78,8 @@ def frames_supported(batch, cfg):
 @pytest.mark.parametrize("n,batch,kind", [(30000, 1, "uniform"), (30001, 2, "lidar"), (1001, 3, "uniform"), (257, 1, "uniform"),
                                           (30000, 6, "lidar"), (2999, 40, "lidar")])
 def test_frame_tiled_voxelizer_matches_oracle(n, batch, kind):
-    """pnx_voxelize_frames (cluster shared-memory bitmap) = same bit-exact contract as pnx_voxelize, for every cluster
-    size the scheduler picks (1 frame -> 8 CTAs, 40 frames -> 4), odd frame lengths (bulk copies start at even points)."""
+    """pnx_voxelize_frames (bitmap slices in shared memory) = same bit-exact contract as pnx_voxelize; odd frame lengths
+    exercise the unaligned first point (bulk copies must start at even points)."""
     cfg = synth.NUSC
     assert frames_supported(batch, cfg)
     pts = synth.collate_points([synth.make_frame(s, n + 7 * s, cfg, kind, sweeps=10) for s in range(batch)])
@@ -104,7 +104,7 @@ def test_frame_tiled_voxelizer_edge_cases():
     # batch indices outside [0, batch) sit in front of / behind the frames in sorted order: dropped like everywhere else
     lead = torch.nn.functional.pad(torch.tensor(synth.make_frame(9, 33, cfg, "uniform")), (1, 0), value=-1.0)
     tail = torch.nn.functional.pad(torch.tensor(synth.make_frame(8, 77, cfg, "uniform")), (1, 0), value=4.0)
-    v = ops.voxelize(torch.cat([lead, pts, tail]).cuda(), 4, cfg["voxel_size"], cfg["pc_range"], frame_sorted=True)
+    v = ops.voxelize(torch.cat([lead, pts, tail]).cuda(), 4, cfg["voxel_size"], cfg["pc_range"], frame_sorted="force")
     w = ops.voxelize(torch.cat([lead, pts, tail]).cuda(), 4, cfg["voxel_size"], cfg["pc_range"], frame_sorted=False)
     assert v.sync_counts() == w.sync_counts()
     assert torch.equal(v.pillar_of_point, w.pillar_of_point) and torch.equal(v.coords[:v.P], w.coords[:w.P])
@@ -121,13 +121,13 @@ def test_frame_tiled_voxelizer_rejects_ungrouped_points():
     cfg = synth.NUSC
     pts = synth.collate_points([synth.make_frame(s, 4000, cfg, "lidar", sweeps=10) for s in range(3)])
     perm = torch.randperm(pts.shape[0], generator=torch.Generator().manual_seed(1))
-    v = ops.voxelize(pts[perm].cuda(), 3, cfg["voxel_size"], cfg["pc_range"], frame_sorted=True)
+    v = ops.voxelize(pts[perm].cuda(), 3, cfg["voxel_size"], cfg["pc_range"], frame_sorted="force")
     with pytest.raises(RuntimeError, match="not grouped"):
         v.sync_counts()
     # a single misplaced point is enough
     one = pts.clone()
     one[[10, 9000]] = one[[9000, 10]]
-    v = ops.voxelize(one.cuda(), 3, cfg["voxel_size"], cfg["pc_range"], frame_sorted=True)
+    v = ops.voxelize(one.cuda(), 3, cfg["voxel_size"], cfg["pc_range"], frame_sorted="force")
     with pytest.raises(RuntimeError, match="not grouped"):
         v.sync_counts()
     run_case(pts[perm], 3, cfg, frame_sorted=False)      # the general path takes any order
@@ -141,7 +141,7 @@ def test_frame_tiled_voxelizer_waymo_and_fallback_geometry():
     cfg = synth.tiny_config(40)  # 40 x 2 words per frame: not whole 32-word blocks -> the general kernels run
     assert not frames_supported(2, cfg)
     pts = synth.collate_points([synth.make_frame(s, 500, cfg) for s in range(2)])
-    v = ops.voxelize(pts.cuda(), 2, cfg["voxel_size"], cfg["pc_range"], frame_sorted=True)
+    v = ops.voxelize(pts.cuda(), 2, cfg["voxel_size"], cfg["pc_range"], frame_sorted="force")
     assert v.status is None
     cfg = synth.tiny_config(128)
     assert frames_supported(2, cfg)
