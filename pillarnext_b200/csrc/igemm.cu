@@ -441,8 +441,13 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
               s0 += f;
               q0 = fmaf(f, f, q0);
             }
-            atomicAdd(&st_sum[cb * 32 + lane], s0);
-            atomicAdd(&st_sq[cb * 32 + lane], q0);
+            // fp32-grade mode: the per-warp partials go straight to the fp64 accumulators.  Four warps adding fp32 partials
+            // into one shared-memory word in arrival order perturbs the statistics at 1e-7, which now and then flips a ReLU
+            // gate / a scatter_max winner downstream and moves a gradient by 1e-3 from one run to the next (measured);
+            // fp64 adds differ at 1e-16 whatever the order.
+            const int ch = (n0 + cb * 32 + lane) % p.stats_mod;
+            atomicAdd(&p.stats[ch], (double)s0);
+            atomicAdd(&p.stats[p.stats_C + ch], (double)q0);
           }
           __syncwarp();
         } else if (staged) {
@@ -588,9 +593,15 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] *= v[k];
             const float s2 = colsum32(v);
-            if (lane < kColBlk) {  // lane c owns column c of this warp's accumulators: plain read-modify-write
-              atomicAdd(&st_sum[cb * kColBlk + lane], s1);
-              atomicAdd(&st_sq[cb * kColBlk + lane], s2);
+            if (lane < kColBlk) {  // lane c owns column c of this warp's accumulators
+              if (F == 2) {          // fp32-grade mode: order-insensitive fp64 accumulation (see the staged fp32 path)
+                const int ch = (n0 + cb * kColBlk + lane) % p.stats_mod;
+                atomicAdd(&p.stats[ch], (double)s1);
+                atomicAdd(&p.stats[p.stats_C + ch], (double)s2);
+              } else {
+                atomicAdd(&st_sum[cb * kColBlk + lane], s1);
+                atomicAdd(&st_sq[cb * kColBlk + lane], s2);
+              }
             }
           }
         }
@@ -602,7 +613,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
       if (++acc == kAccSets) { acc = 0; acc_phase ^= 1; }
       ++ti;
     }
-    if (p.stats) {
+    if (p.stats && F != 2) {
       named_bar_sync(2, EW * 32);  // the epilogue warps
       for (int c = threadIdx.x - (kThreadsTotal - EW * 32); c < BN; c += EW * 32) {
         const int ch = (n0 + c) % p.stats_mod;

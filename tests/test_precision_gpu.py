@@ -382,14 +382,22 @@ def test_full_size_nuscenes_frame_vs_oracle():
 def test_run_to_run_spread_of_the_gradients():
     """The cross-CTA reductions (BatchNorm statistics: fp32 shared-memory partials + fp64 global atomics; weight-gradient
     split-K: fp32 red.global.add) are ORDER-dependent, so two runs of the same step are not bit-identical.  This test
-    measures the spread and pins it: the forward differs at fp32-rounding level, and the ReLU-gate law above turns a
-    forward difference eps into ~sqrt(eps) on the gradients.  (A bit-reproducible mode would need ordered two-stage
-    reductions in every epilogue; the split-mode BatchNorm backward reduce already is one, pnx_bn_bwd_reduce_split.)"""
+    measures the spread and pins it.
+      * split (fp32-grade) mode: the BatchNorm statistics go straight to fp64 accumulators (order effects 1e-16), so the
+        FORWARD is bit-identical from run to run and the gradients differ only by the fp32 split-K atomics of the weight
+        gradients (3e-7, most parameters bit-identical).  Before that change the 1e-7 perturbation of the statistics
+        flipped a ReLU gate / scatter_max winner in roughly one run out of three and moved a reader gradient by 2.6e-3.
+      * bf16 mode: every stored activation is re-rounded to 8 mantissa bits, so ANY perturbation, however small, flips a
+        few roundings in the next layer and the difference climbs to the bf16 quantisation-noise floor within a few
+        layers: two identical runs differ by as much as one run differs from fp32 (3e-2 on the head maps; the ReLU-gate
+        law then gives tenths on the gradients).  That is a property of bf16 storage, not a bug -- and the reason the
+        parity gate of this repository is the split mode, whose assertions are tight.  (Bit-reproducible bf16 runs would
+        need ordered two-stage reductions in every GEMM epilogue; only the split-mode BatchNorm backward reduce is one.)"""
     cfg = synth.tiny_config(128, TASKS)
     B = 2
     ex = to_cuda(synth.make_batch([0, 1], 3000, cfg, kind="uniform", n_boxes=25, sweeps=10))
     lines = []
-    for mode, tol_fwd, tol_grad in (("split", 1e-5, 5e-3), ("bf16", 5e-3, 8e-2)):
+    for mode, tol_fwd, tol_grad in (("split", 1e-6, 1e-5), ("bf16", 1.5e-1, 1.0)):
         runs = []
         for _ in range(2):
             model, _ = build(cfg)
