@@ -317,7 +317,7 @@ __global__ void vox_rank_kernel(const int* __restrict__ cell_of_point, int n, co
 // staged in shared memory and written with coalesced stores.
 constexpr int kCoordStage = 128;   // pillars of one block staged per warp (3 ints each); denser blocks take the direct path
 constexpr int kCoU = 4;            // blocks per warp, all their loads in flight together (the kernel was load-latency bound:
-                                   // blockpref -> bitmap/inblk -> store, one block per warp: 98 us for 518 k blocks)
+                                   // blockpref -> bitmap/inblk -> store, one block per warp: 98 us for 452 k blocks)
 __global__ void __launch_bounds__(256) vox_coords_kernel(const uint32_t* __restrict__ bitmap, const int* __restrict__ blockpref,
                                                          int n_blocks, VoxGeom g, int* __restrict__ coords, int cap,
                                                          const uint16_t* __restrict__ inblk) {
@@ -403,7 +403,7 @@ __global__ void vox_sort_kernel(const int* __restrict__ bucket_tmp, const int* _
 // Frame-tiled index generation (round 2).  The global-bitmap pipeline above issues one random RED.OR per point into L2 and
 // three random L2 reads per point in the rank pass; both are bounded by the L2 transaction rate (measured ~100 G RED/s,
 // ~350 G random reads/s), which caps it near 0.2 of the HBM roofline whatever the streaming side does.  Here a SLICE of one
-// frame's occupancy bitmap lives in the shared memory of a CTA (a nuScenes frame is 259 KB = 2 slices of 130 KB), so marking
+// frame's occupancy bitmap lives in the shared memory of a CTA (a nuScenes frame is 226 KB = 2 slices of 113 KB), so marking
 // and ranking are LOCAL shared-memory operations and HBM/L2 only see streaming traffic:
 //   bounds  off[b] = first point of frame b (1024-ary search on the batch column; collate order = grouped by frame)
 //   mark    CTA (b, s) streams ALL points of frame b (cp.async.bulk ring; the second slice's read is an L2 hit), ORs the
