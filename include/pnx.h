@@ -125,7 +125,7 @@ int pnx_pfn_max1(const float* y1, const int* bucket_off, const int* counts, int 
  * Inputs: the forward's saved buffers (pnx_pfn_* outputs), dfeat [cap_pillars,64] fp32.
  * Scratch: argq1 [cap_pillars,64] int32, d_x0 / dxm_part [cap_points,32] fp32.
  * Outputs (zero them first): red fp64 [64+128] = {dbeta0[32], dgamma0[32], dbeta1[64], dgamma1[64]},
- * dW0 [32,10], dW1 [64,64] fp32. */
+ * dW0 [32,10], dW1 [64,64] fp64 (accumulated by cross-CTA atomics: fp64 makes their order irrelevant at fp32 level). */
 int pnx_pfn_backward(const float* points, const int* bucket_off, const int* bucket_pts,
                      const int* pillar_of_point, const int* coords, const int* counts, int cap_points,
                      int cap_pillars, float min_x, float min_y, float vs_x, float vs_y, const float* pmean,
@@ -133,7 +133,7 @@ int pnx_pfn_backward(const float* points, const int* bucket_off, const int* buck
                      const float* dfeat, const float* w1, const float* scale0, const float* shift0,
                      const float* mean0, const float* invstd0, const float* gamma0, const float* scale1,
                      const float* shift1, const float* mean1, const float* invstd1, const float* gamma1,
-                     int* argq1, float* d_x0, float* dxm_part, double* red, float* dW0, float* dW1,
+                     int* argq1, float* d_x0, float* dxm_part, double* red, double* dW0, double* dW1,
                      int phases, const int* bn_count, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- B1-B4 active sites / rulebook
@@ -217,7 +217,15 @@ int pnx_conv3x3_win(const void* A, long long lda, int B, int H, int W, int Cin, 
  * pnx_igemm replaces (autograd in the reference: trainer/trainer/trainer.py:94-108). */
 int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long long ldy, long long y_rows,
               int y_channels, int gathered, int M, int taps, const int* nbr, int Hout, int Wout, int Hin, int Win, int kw,
-              int mul, int dil, int pad, int shuffle, float* dW, int sm_count, cudaStream_t stream);
+              int mul, int dil, int pad, int shuffle, float* dW, float* partials, int sm_count, cudaStream_t stream);
+/* Deterministic weight gradients: with partials != NULL (pnx_wgrad_splits(...) * taps * x_channels * y_channels floats,
+ * 16-byte aligned) every K split stores its own slab with plain stores and one kernel adds the slabs to dW in split order,
+ * instead of fp32 red.global.add from all splits.  pnx_wgrad_splits = the number of splits pnx_wgrad uses for the shape. */
+int pnx_wgrad_splits(int x_channels, int y_channels, int taps, int M, int sm_count);
+/* Library-wide switch: the BatchNorm statistics of the GEMM epilogues (pnx_igemm / pnx_conv3x3_win `stats`) are
+ * accumulated in fp64 from per-warp partials (order effects 1e-16) instead of through fp32 shared-memory words added in
+ * arrival order (1e-7).  Returns the previous setting. */
+int pnx_set_deterministic(int on);
 
 /* ---------------------------------------------------------------- row-wise bf16 kernels
  * y = relu?(x*scale + shift (+ res))  -- BatchNorm apply (+residual)(+ReLU): sparse_conv.py:33-39,55-63,

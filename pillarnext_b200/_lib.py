@@ -51,7 +51,9 @@ _SIGS = {
     "pnx_scatter_dense": [P, P, P, I, I, I, I, I, P, I, P],
     "pnx_igemm": [P, L, L, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, L, I, P, P, I, I, I, I, P, L, I, L, L, I, P, L, P, P, P, P, P, I, I, P],
     "pnx_conv3x3_win": [P, L, I, I, I, I, P, I, I, P, L, P, P, I, I, I, P, L, P, P, P, P, P, I, I, P],
-    "pnx_wgrad": [P, L, I, P, L, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, P, I, P],
+    "pnx_wgrad": [P, L, I, P, L, L, I, I, I, I, P, I, I, I, I, I, I, I, I, I, P, P, I, P],
+    "pnx_wgrad_splits": [I, I, I, I, I],
+    "pnx_set_deterministic": [I],
     "pnx_bn_apply": [P, L, L, I, P, P, P, L, I, P, L, P],
     "pnx_bn_bwd_reduce": [P, L, P, L, P, L, L, I, P, P, I, P, P, P, P],
     "pnx_bn_bwd_apply": [P, L, P, L, P, L, L, I, P, P, P, P, ctypes.c_double, P, I, P, P, P, L, P, L, I, P],

@@ -32,6 +32,7 @@ struct IgemmParams {
   const float* bias;
   double* stats;
   int stats_C, stats_mod;
+  int stats_direct;  // deterministic mode: per-warp partials go straight to the fp64 accumulators (no fp32 shared-memory stage)
   int shuffle, relu;
   const __nv_bfloat16* addend;  // optional [M, ld_add] bf16 added before the store (gradient accumulation)
   long long ld_add;
@@ -553,8 +554,14 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
                 }
               }
               const int c0 = (cb - 1) * 32 + 2 * lane;  // columns of this pair of blocks owned by this lane
-              atomicAdd(&st_sum[c0], s0); atomicAdd(&st_sum[c0 + 1], s1);
-              atomicAdd(&st_sq[c0], q0); atomicAdd(&st_sq[c0 + 1], q1);
+              if (p.stats_direct) {   // order-insensitive (fp64) accumulation, see pnx_set_deterministic
+                const int ch0 = (n0 + c0) % p.stats_mod, ch1 = (n0 + c0 + 1) % p.stats_mod;
+                atomicAdd(&p.stats[ch0], (double)s0); atomicAdd(&p.stats[ch1], (double)s1);
+                atomicAdd(&p.stats[p.stats_C + ch0], (double)q0); atomicAdd(&p.stats[p.stats_C + ch1], (double)q1);
+              } else {
+                atomicAdd(&st_sum[c0], s0); atomicAdd(&st_sum[c0 + 1], s1);
+                atomicAdd(&st_sq[c0], q0); atomicAdd(&st_sq[c0 + 1], q1);
+              }
             }
             __syncwarp();
           }
@@ -594,7 +601,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
             for (int k = 0; k < 32; ++k) v[k] *= v[k];
             const float s2 = colsum32(v);
             if (lane < kColBlk) {  // lane c owns column c of this warp's accumulators
-              if (F == 2) {          // fp32-grade mode: order-insensitive fp64 accumulation (see the staged fp32 path)
+              if (F == 2 || p.stats_direct) {  // fp32-grade / deterministic mode: order-insensitive fp64 accumulation
                 const int ch = (n0 + cb * kColBlk + lane) % p.stats_mod;
                 atomicAdd(&p.stats[ch], (double)s1);
                 atomicAdd(&p.stats[p.stats_C + ch], (double)s2);
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(64 + PW * 32 + 64 + EW * 32, 1) igemm_kernel(c
       if (++acc == kAccSets) { acc = 0; acc_phase ^= 1; }
       ++ti;
     }
-    if (p.stats && F != 2) {
+    if (p.stats && F != 2 && !p.stats_direct) {
       named_bar_sync(2, EW * 32);  // the epilogue warps
       for (int c = threadIdx.x - (kThreadsTotal - EW * 32); c < BN; c += EW * 32) {
         const int ch = (n0 + c) % p.stats_mod;
@@ -667,6 +674,19 @@ int launch_igemm(const CUtensorMap& wmap, const CUtensorMap& amap, const IgemmPa
 
 }  // namespace
 
+// Deterministic mode (library-wide switch): BatchNorm statistics produced by the GEMM epilogues (pnx_igemm,
+// pnx_conv3x3_win) are accumulated in fp64 from per-warp partials instead of through fp32 shared-memory words that four
+// warps add to in arrival order.  fp64 adds differ at 1e-16 whatever the order, so the statistics -- and with them the
+// whole forward pass -- come out bit-identical from run to run.  Slower (one RED.F64 per warp, tile and channel); meant for
+// debugging and regression hunting.  Returns the previous setting.
+int g_pnx_deterministic = 0;
+extern "C" int pnx_set_deterministic(int on) {
+  const int prev = g_pnx_deterministic;
+  g_pnx_deterministic = on ? 1 : 0;
+  return prev;
+}
+
+
 // Contract: include/pnx.h (pnx_igemm).
 extern "C" int pnx_igemm(const void* A, long long lda, long long a_rows, int M, int taps, int Cin, const void* Wpacked, int Cout,
                          int block_n, const int* nbr, int dense, int Hout, int Wout, int Hin, int Win, int kw,
@@ -699,6 +719,7 @@ extern "C" int pnx_igemm(const void* A, long long lda, long long a_rows, int M, 
   p.kw = kw > 0 ? kw : 1; p.mul = mul; p.dil = dil; p.pad = pad;
   p.out = out; p.ldc = ldc; p.out_fp32 = out_fp32; p.bias = bias;
   p.stats = stats; p.stats_C = stats_C; p.stats_mod = stats_mod > 0 ? stats_mod : 1 << 30;
+  p.stats_direct = g_pnx_deterministic;
   p.shuffle = shuffle; p.relu = relu;
   p.addend = addend_fp32 ? nullptr : (const __nv_bfloat16*)addend;
   p.addend_f32 = addend_fp32 ? (const float*)addend : nullptr;

@@ -12,6 +12,8 @@
 //   warps 2..9: epilogue (bias, ReLU, bf16 coalesced store through a swizzled slab, BatchNorm statistics)
 #include "pnx_common.cuh"
 
+extern int g_pnx_deterministic;  // igemm.cu (pnx_set_deterministic)
+
 namespace {
 
 struct WinParams {
@@ -22,6 +24,7 @@ struct WinParams {
   const float* bias;
   double* stats;
   int stats_C;
+  int stats_direct;
   int relu;
   int base_off_mode;        // 1: descriptor base offset = (start >> 7) & 7 (PTX ISA), 0: leave 0
   // fused BatchNorm-backward reduction (see igemm.cu IgemmParams): this conv produces dy of y = relu(bn(raw))
@@ -310,8 +313,13 @@ __global__ void __launch_bounds__(320, 1) igemm_win_kernel(const __grid_constant
                 }
               }
             const int c0 = (cb - 1) * 32 + 2 * lane;
-            atomicAdd(&s_stat[c0], s0); atomicAdd(&s_stat[c0 + 1], s1);
-            atomicAdd(&s_stat[BN + c0], q0); atomicAdd(&s_stat[BN + c0 + 1], q1);
+            if (p.stats_direct) {   // deterministic mode: order-insensitive fp64 accumulation (pnx_set_deterministic)
+              atomicAdd(&p.stats[n0 + c0], (double)s0); atomicAdd(&p.stats[n0 + c0 + 1], (double)s1);
+              atomicAdd(&p.stats[p.stats_C + n0 + c0], (double)q0); atomicAdd(&p.stats[p.stats_C + n0 + c0 + 1], (double)q1);
+            } else {
+              atomicAdd(&s_stat[c0], s0); atomicAdd(&s_stat[c0 + 1], s1);
+              atomicAdd(&s_stat[BN + c0], q0); atomicAdd(&s_stat[BN + c0 + 1], q1);
+            }
           }
           __syncwarp();
         }
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(320, 1) igemm_win_kernel(const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (p.stats) {
+    if (p.stats && !p.stats_direct) {
       asm volatile("bar.sync 2, 256;" ::: "memory");
       for (int c = threadIdx.x - 64; c < BN; c += 256) {
         atomicAdd(&p.stats[n0 + c], (double)s_stat[c]);
@@ -379,6 +387,7 @@ extern "C" int pnx_conv3x3_win(const void* A, long long lda, int B, int H, int W
   p.B = B; p.H = H; p.W = W; p.XC = (W + 127) / 128;
   p.Cin = Cin; p.Cout_total = Cout;
   p.out = (__nv_bfloat16*)out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.stats_C = stats_C; p.relu = relu;
+  p.stats_direct = g_pnx_deterministic;
   p.base_off_mode = base_off_mode;
   p.bnr_raw = (const __nv_bfloat16*)bnr_raw; p.bnr_ld = bnr_ld; p.bnr_scale = bnr_scale; p.bnr_shift = bnr_shift;
   p.bnr_mean = bnr_mean; p.bnr_invstd = bnr_invstd; p.bnr_red = bnr_red; p.bnr_C = bnr_C;

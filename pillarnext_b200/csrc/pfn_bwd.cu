@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256)
                         const float* __restrict__ shift0, const float* __restrict__ mean1,
                         const float* __restrict__ invstd1, const float* __restrict__ gamma1,
                         const double* __restrict__ red1, const float* __restrict__ w1, float* __restrict__ d_x0,
-                        float* __restrict__ dxm_part, float* __restrict__ dW1, const int* __restrict__ bn_count) {
+                        float* __restrict__ dxm_part, double* __restrict__ dW1, const int* __restrict__ bn_count) {
   extern __shared__ float smem[];
   float* sdy = smem;                  // [64][kLd]
   float* sin_ = smem + 64 * kLd;      // [64][kLd]
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256)
       for (int i = 0; i < 16; ++i) acc[i] = fmaf(sdy[(og + i) * kLd + qq], v, acc[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) atomicAdd(&dW1[(og + i) * 64 + k], acc[i]);
+    for (int i = 0; i < 16; ++i) atomicAdd(&dW1[(og + i) * 64 + k], (double)acc[i]);  // fp64: order-insensitive across CTAs
   }
 }
 
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(320)
                         const float* __restrict__ pmean, const float* __restrict__ y0, const float* __restrict__ g0,
                         const int* __restrict__ counts, int cap_n, PfnGeom geo, const float* __restrict__ mean0,
                         const float* __restrict__ invstd0, const float* __restrict__ gamma0,
-                        const double* __restrict__ red0, float* __restrict__ dW0, const int* __restrict__ bn_count) {
+                        const double* __restrict__ red0, double* __restrict__ dW0, const int* __restrict__ bn_count) {
   __shared__ float sdy[32 * kLd];
   __shared__ float sf[10 * kLd];
   __shared__ float sbn[5 * 32];
@@ -236,13 +236,14 @@ __global__ void __launch_bounds__(320)
     const int o = threadIdx.x / 10, k = threadIdx.x - o * 10;
     float acc = 0.f;
     for (int qq = 0; qq < 256; ++qq) acc = fmaf(sdy[o * kLd + qq], sf[k * kLd + qq], acc);
-    atomicAdd(&dW0[o * 10 + k], acc);
+    atomicAdd(&dW0[o * 10 + k], (double)acc);
   }
 }
 
 }  // namespace
 
-// Contract: include/pnx.h (pnx_pfn_backward).  red [2*32 + 2*64] fp64 and dW0/dW1 must be zeroed.
+// Contract: include/pnx.h (pnx_pfn_backward).  red [2*32 + 2*64] fp64 and dW0 [32,10] / dW1 [64,64] fp64 must be zeroed
+// (fp64 accumulators: the per-CTA partials are summed by global atomics, whose order then does not matter at fp32 level).
 extern "C" int pnx_pfn_backward(const float* points, const int* bucket_off, const int* bucket_pts,
                                 const int* pillar_of_point, const int* coords, const int* counts, int cap_points,
                                 int cap_pillars, float min_x, float min_y, float vs_x, float vs_y, const float* pmean,
@@ -250,7 +251,7 @@ extern "C" int pnx_pfn_backward(const float* points, const int* bucket_off, cons
                                 const float* dfeat, const float* w1, const float* scale0, const float* shift0,
                                 const float* mean0, const float* invstd0, const float* gamma0, const float* scale1,
                                 const float* shift1, const float* mean1, const float* invstd1, const float* gamma1,
-                                int* argq1, float* d_x0, float* dxm_part, double* red, float* dW0, float* dW1,
+                                int* argq1, float* d_x0, float* dxm_part, double* red, double* dW0, double* dW1,
                                 int phases, const int* bn_count, cudaStream_t stream) {
   if (cap_points == 0 || cap_pillars == 0) return PNX_OK;
   static bool attr_set = false;

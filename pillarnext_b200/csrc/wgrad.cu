@@ -30,6 +30,7 @@ struct WgradParams {
   int Hout, Wout, Hin, Win, kw, mul, dil, pad;
   int shuffle;     // ConvTranspose k2s2: tap q selects pixel (2y+q/2, 2x+q%2) of the gathered operand
   float* dW;       // [T, X_total, Y_total]
+  float* partials; // deterministic mode: [splits][T, X_total, Y_total], plain stores, reduced in split order afterwards
   int X_total, Y_total;
   int x_dup;       // X has only 64 channels: second MN atom aliases the first (rows 64..127 ignored)
   int y_chunks;    // Y_total / NYC
@@ -261,15 +262,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       for (int j = 0; j < ntaps; ++j) {
         const int xch = (xb * XB + x2) * 128 + xrow_local;
         const bool ok = xch < p.X_total && !(p.x_dup && xrow_local >= 64);
-        float* dst = p.dW + ((size_t)(t0 + j) * p.X_total + (ok ? xch : 0)) * p.Y_total + yc * NYC;
+        float* out = p.partials ? p.partials + (size_t)blockIdx.z * ((size_t)p.T * p.X_total * p.Y_total) : p.dW;
+        float* dst = out + ((size_t)(t0 + j) * p.X_total + (ok ? xch : 0)) * p.Y_total + yc * NYC;
 #pragma unroll
         for (int cb = 0; cb < NYC / 32; ++cb) {
           uint32_t r[32];
           pnx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + x2 * (NYC * TG) + j * NYC + cb * 32, r);
           pnx::tmem_ld_wait();
           if (ok) {
+            if (p.partials) {  // every (tap, x, y) of a split's slab is written by exactly one CTA
 #pragma unroll
-            for (int k = 0; k < 32; ++k) atomicAdd(dst + cb * 32 + k, __uint_as_float(r[k]));
+              for (int k = 0; k < 32; k += 4)
+                *reinterpret_cast<uint4*>(dst + cb * 32 + k) = make_uint4(r[k], r[k + 1], r[k + 2], r[k + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) atomicAdd(dst + cb * 32 + k, __uint_as_float(r[k]));
+            }
           }
         }
       }
@@ -281,6 +289,44 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   if (warp == 1) pnx::tmem_dealloc<512>(tmem_base);
 }
 
+// dW[i] += sum over the splits, in split order (deterministic mode)
+__global__ void wgrad_reduce_partials_kernel(const float* __restrict__ partials, int splits, long long n, float* __restrict__ dW) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += partials[(size_t)z * n + i];
+    dW[i] += acc;
+  }
+}
+
+// grid plan shared by the launcher and pnx_wgrad_splits
+struct WPlan { int taps_per_group, groups, rows_per_split, splits; };
+inline WPlan wgrad_plan(int TG, int XB, int NYC, int x_blocks, int Y_total, int T, int M, int sm_count) {
+  WPlan w;
+  x_blocks /= XB;
+  const int y_chunks = Y_total / NYC;
+  w.taps_per_group = T < TG ? T : TG;
+  w.groups = (T + w.taps_per_group - 1) / w.taps_per_group;
+  w.taps_per_group = (T + w.groups - 1) / w.groups;  // balance the groups (e.g. 9 taps, TG = 8 -> 5 + 4)
+  w.groups = (T + w.taps_per_group - 1) / w.taps_per_group;
+  const int ctas_xy = x_blocks * y_chunks * w.groups;
+  // two full waves of CTAs (one CTA per SM): round DOWN -- 2*148 + a few CTAs would run a third, nearly empty wave
+  int splits = (2 * sm_count) / ctas_xy;
+  const int max_splits = (M + 8 * kKS - 1) / (8 * kKS);  // at least 8 K-chunks per CTA
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  w.rows_per_split = ((M + splits - 1) / splits + kKS - 1) / kKS * kKS;
+  w.splits = (M + w.rows_per_split - 1) / w.rows_per_split;
+  return w;
+}
+// the (NYC, TG, XB) variant pnx_wgrad picks for a shape
+inline void wgrad_variant(int x_channels, int y_channels, int* NYC, int* TG, int* XB) {
+  const int x_blocks = x_channels == 64 ? 1 : x_channels / 128;
+  if (y_channels % 256 == 0) { *NYC = 256; *TG = 1; *XB = (x_blocks % 2 == 0) ? 2 : 1; }
+  else if (y_channels % 192 == 0) { *NYC = 192; *TG = 2; *XB = 1; }
+  else if (y_channels % 128 == 0) { *NYC = 128; *TG = 3; *XB = 1; }
+  else { *NYC = 64; *TG = 5; *XB = 1; }
+}
+
 template <int NYC, int TG, int XB>
 int launch_wgrad(const CUtensorMap& xmap, const CUtensorMap& ymap, WgradParams p, int x_blocks, int sm_count,
                  cudaStream_t stream) {
@@ -290,33 +336,38 @@ int launch_wgrad(const CUtensorMap& xmap, const CUtensorMap& ymap, WgradParams p
                                   (int)WCfg<NYC, TG, XB>::kSmem));
     attr_set = true;
   }
+  const WPlan w = wgrad_plan(TG, XB, NYC, x_blocks, p.Y_total, p.T, p.M, sm_count);
   x_blocks /= XB;
   p.y_chunks = p.Y_total / NYC;
-  p.taps_per_group = p.T < TG ? p.T : TG;
-  int groups = (p.T + p.taps_per_group - 1) / p.taps_per_group;
-  // balance the groups (e.g. 9 taps, TG = 8 -> 5 + 4)
-  p.taps_per_group = (p.T + groups - 1) / groups;
-  groups = (p.T + p.taps_per_group - 1) / p.taps_per_group;
-  const int ctas_xy = x_blocks * p.y_chunks * groups;
-  // two full waves of CTAs (one CTA per SM): round DOWN -- 2*148 + a few CTAs would run a third, nearly empty wave
-  int splits = (2 * sm_count) / ctas_xy;
-  const int max_splits = (p.M + 8 * kKS - 1) / (8 * kKS);  // at least 8 K-chunks per CTA
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  p.rows_per_split = ((p.M + splits - 1) / splits + kKS - 1) / kKS * kKS;
-  splits = (p.M + p.rows_per_split - 1) / p.rows_per_split;
+  p.taps_per_group = w.taps_per_group;
+  p.rows_per_split = w.rows_per_split;
+  const int groups = w.groups, splits = w.splits;
   dim3 grid(x_blocks * p.y_chunks, groups, splits);
   wgrad_kernel<NYC, TG, XB><<<grid, kThreads, WCfg<NYC, TG, XB>::kSmem, stream>>>(xmap, ymap, p);
   PNX_CHECK_LAUNCH();
+  if (p.partials) {
+    const long long n = (long long)p.T * p.X_total * p.Y_total;
+    wgrad_reduce_partials_kernel<<<(int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), 256, 0, stream>>>(p.partials, splits, n, p.dW);
+    PNX_CHECK_LAUNCH();
+  }
   return PNX_OK;
 }
 
 }  // namespace
 
+// Number of K splits pnx_wgrad uses for a shape (deterministic mode: `partials` holds splits * taps * X * Y floats).
+extern "C" int pnx_wgrad_splits(int x_channels, int y_channels, int taps, int M, int sm_count) {
+  if (M <= 0 || x_channels <= 0 || y_channels <= 0 || taps <= 0) return 0;
+  if (sm_count <= 0) sm_count = 148;
+  int NYC, TG, XB;
+  wgrad_variant(x_channels, y_channels, &NYC, &TG, &XB);
+  return wgrad_plan(TG, XB, NYC, x_channels == 64 ? 1 : x_channels / 128, y_channels, taps, M, sm_count).splits;
+}
+
 // Contract: include/pnx.h (pnx_wgrad).  dW must be zeroed (or hold the value to accumulate into).
 extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, const void* Y, long long ldy, long long y_rows,
                          int y_channels, int gathered, int M, int taps, const int* nbr, int Hout, int Wout, int Hin, int Win, int kw,
-                         int mul, int dil, int pad, int shuffle, float* dW, int sm_count, cudaStream_t stream) {
+                         int mul, int dil, int pad, int shuffle, float* dW, float* partials, int sm_count, cudaStream_t stream) {
   PNX_CHECK_ARG(M >= 0, "M");
   if (M == 0) return PNX_OK;
   PNX_CHECK_ARG(taps >= 1 && taps <= 9, "taps");
@@ -332,7 +383,8 @@ extern "C" int pnx_wgrad(const void* X, long long ldx, int x_channels, const voi
   p.nbr = nbr; p.gathered = gathered;
   p.Hout = Hout > 0 ? Hout : 1; p.Wout = Wout > 0 ? Wout : 1; p.Hin = Hin; p.Win = Win;
   p.kw = kw > 0 ? kw : 1; p.mul = mul; p.dil = dil; p.pad = pad; p.shuffle = shuffle;
-  p.dW = dW; p.X_total = x_channels; p.Y_total = y_channels;
+  p.dW = dW; p.partials = partials; p.X_total = x_channels; p.Y_total = y_channels;
+  PNX_CHECK_ARG(!partials || (reinterpret_cast<uintptr_t>(partials) & 15) == 0, "partials 16-byte aligned");
   p.x_dup = x_channels == 64 ? 1 : 0;
   p.inv_hw = 1.0f / (float)(p.Hout * p.Wout);
   p.inv_w = 1.0f / (float)p.Wout;

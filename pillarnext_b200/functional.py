@@ -53,6 +53,18 @@ def _split():
     return _PRECISION == "split"
 
 
+def set_deterministic(on):
+    """Opt-in reproducible reductions for the bf16 path (debugging / regression hunting; slower):
+      * BatchNorm statistics of the conv epilogues accumulate in fp64 (order effects 1e-16 instead of 1e-7), the fused
+        BatchNorm-backward reduce is switched off in favour of the separate pass (fixed order inside a CTA, fp64 across CTAs);
+      * weight gradients: every K split writes its own slab, the slabs are added in split order (no fp32 atomics).
+    With it two runs of the same step give a bit-identical forward and bit-identical parameter gradients
+    (tests/test_precision_gpu.py::test_run_to_run_spread_of_the_gradients; "bit-identical" up to the 1e-16 order effects
+    of the remaining fp64 atomics, which vanish in the rounding to fp32).  Not covered: three or more positives of one
+    class colliding on one heat-map cell (fp32 atomics in the loss gradient).  Returns the previous setting."""
+    return ops.set_deterministic(on)
+
+
 def _P():
     return ops.split_pieces()
 
@@ -279,6 +291,8 @@ def _claim_bn_reduce(info, M, C, k_total):
     """The BNInfo to hand to the GEMM producing a [M, C] gradient (K = k_total), or None when the fused path does not
     apply.  All consumers of one BatchNorm output must make the same decision: they share the shape, so they do."""
     if info is None or info.raw is None or info.C != C or info.M != M or not ops.bnr_eligible(C) or k_total < FUSE_BN_REDUCE_MIN_K:
+        return None
+    if ops.DETERMINISTIC:          # the fused reduce goes through fp32 shared-memory partials in arrival order
         return None
     if info.red is None:
         info.red = ops.zeros(2 * C, torch.float64, info.raw.device)

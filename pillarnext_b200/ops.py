@@ -284,8 +284,8 @@ def pfn_backward(v, fwd, dfeat, w1, gamma0, gamma1):
     d_x0 = torch.empty(n, 32, dtype=torch.float32, device=dev)
     dxm = torch.empty(n, 32, dtype=torch.float32, device=dev)
     red = torch.zeros(64 + 128, dtype=torch.float64, device=dev)
-    dW0 = torch.zeros(32, 10, dtype=torch.float32, device=dev)
-    dW1 = torch.zeros(64, 64, dtype=torch.float32, device=dev)
+    dW0 = torch.zeros(32, 10, dtype=torch.float64, device=dev)      # fp64 accumulators (cross-CTA atomics, order-insensitive)
+    dW1 = torch.zeros(64, 64, dtype=torch.float64, device=dev)
     _count(4)
     bn_count = fwd.get("bn_count")
 
@@ -314,7 +314,7 @@ def pfn_backward(v, fwd, dfeat, w1, gamma0, gamma1):
         dist.all_reduce(glob[:64])
         run(8, glob)
     r = red.float()
-    return dW0, dW1, r[32:64], r[0:32], r[128:192], r[64:128]
+    return dW0.float(), dW1.float(), r[32:64], r[0:32], r[128:192], r[64:128]
 
 
 # --------------------------------------------------------------------------------- sites / rulebook
@@ -499,6 +499,18 @@ def conv3x3_win(A, B, H, W, w_packed, cin, cout, out, *, bias=None, stats=None, 
     return out
 
 
+DETERMINISTIC = False     # set through functional.set_deterministic
+
+
+def set_deterministic(on):
+    """Library side of functional.set_deterministic: ordered split-K reduction in pnx_wgrad (per-split slabs added in split
+    order) and fp64 accumulation of the BatchNorm statistics in the GEMM epilogues (pnx_set_deterministic)."""
+    global DETERMINISTIC
+    prev, DETERMINISTIC = DETERMINISTIC, bool(on)
+    lib().pnx_set_deterministic(1 if on else 0)
+    return prev
+
+
 def wgrad(X, x_channels, Y, y_channels, M, taps, dW, *, nbr=None, dense=None, shuffle=False, gathered=None):
     """dW[t, x, y] += sum_m X[m, x] * Y[g(m,t), y]; X direct, Y gathered; dW fp32 [taps, x_channels, y_channels]."""
     assert X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16 and dW.dtype == torch.float32
@@ -516,12 +528,16 @@ def wgrad(X, x_channels, Y, y_channels, M, taps, dW, *, nbr=None, dense=None, sh
     d = dense or (0, 0, 0, 0, 1, 1, 1, 0)
     if gathered is None:
         gathered = nbr is not None or dense is not None or shuffle
-    _count(1)
+    partials = None
+    if DETERMINISTIC and M > 0:
+        splits = lib().pnx_wgrad_splits(x_channels, y_channels, taps, M, sm_count())
+        partials = torch.empty(splits * taps * x_channels * y_channels, dtype=torch.float32, device=dW.device)
+    _count(2 if partials is not None else 1)
     with _Timed("wgrad", 2.0 * M * taps * x_channels * y_channels, 2.0 * M * (x_channels + taps * y_channels),
                 "M%d_T%d_X%d_Y%d" % (M, taps, x_channels, y_channels)):
       check(lib().pnx_wgrad(ptr(X), X.stride(0), x_channels, ptr(Y), Y.stride(0), Y.shape[0], y_channels, 1 if gathered else 0, M,
                           taps, ptr(nbr) if nbr is not None else None, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7],
-                          1 if shuffle else 0, ptr(dW), sm_count(), stream()))
+                          1 if shuffle else 0, ptr(dW), ptr(partials) if partials is not None else None, sm_count(), stream()))
     return dW
 
 

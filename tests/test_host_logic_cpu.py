@@ -11,7 +11,7 @@ def test_wgrad_splits_channel_counts_the_kernel_does_not_tile(monkeypatch):
 
     class FakeLib:
         def pnx_wgrad(self, X, ldx, xc, Y, ldy, y_rows, yc, gathered, M, taps, nbr, *rest):
-            dW_ptr = rest[9]
+            dW_ptr = rest[9]   # ..., shuffle, dW, partials, sm_count, stream
             calls.append(dict(x_off=X, ldx=ldx, xc=xc, yc=yc, taps=taps, dW=dW_ptr))
             return 0
 

@@ -88,8 +88,16 @@ def run_oracle(cfg, sd, ex, B, quant):
         O.QUANT = False
 
 
+@pytest.fixture
+def deterministic():
+    from pillarnext_b200 import functional as Fn
+    prev = Fn.set_deterministic(True)
+    yield
+    Fn.set_deterministic(prev)
+
+
 @pytest.mark.parametrize("grid,npts,kind", [(128, 3000, "uniform"), (256, 4000, "lidar")])
-def test_detector_matches_oracle(grid, npts, kind):
+def test_detector_matches_oracle(grid, npts, kind, deterministic):
     cfg = synth.tiny_config(grid, TASKS)
     model, sd = build(cfg)
     model.train()
@@ -151,10 +159,11 @@ def test_detector_matches_oracle(grid, npts, kind):
     cs.sort()
     report += ["surrogate cos %.3f norm-ratio %.3f %s" % c for c in cs[:6]]
     print("\n".join(report[-8:]))
-    # fp32 atomics (weight gradients, BatchNorm sums) make the run-to-run rounding differ, and a different set of ReLU
-    # gates then flips: typical worst values are cos 0.76 / ratio 0.91-1.08, one parameter in ~100 may stray further.
-    assert statistics.median(c for c, _, _ in cs) > 0.85 and cs[0][0] > 0.4, "\n".join(report)
-    assert all(0.5 < r < 2.0 for _, r, _ in cs) and sum(not (0.7 < r < 1.4) for _, r, _ in cs) <= 1, "\n".join(report)
+    # Runs under functional.set_deterministic(True) (fixture): ordered split-K + fp64 statistics make the bf16 run
+    # bit-reproducible, so these are fixed numbers, not draws -- the assertions are the tight ones again (an earlier
+    # revision had to tolerate one stray parameter because a different set of ReLU gates flipped from run to run).
+    assert statistics.median(c for c, _, _ in cs) > 0.85 and cs[0][0] > 0.5, "\n".join(report)
+    assert all(0.7 < r < 1.4 for _, r, _ in cs), "\n".join(report)
     model.zero_grad()
     loss, rets = model.head.loss(exg, [dict(pd) for pd in preds])
     report.append("loss %.6f  bf16-faithful %.6f  fp32 %.6f" % (loss.item(), oq["loss"].item(), of["loss"].item()))

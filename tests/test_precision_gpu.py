@@ -387,6 +387,8 @@ def test_run_to_run_spread_of_the_gradients():
         FORWARD is bit-identical from run to run and the gradients differ only by the fp32 split-K atomics of the weight
         gradients (3e-7, most parameters bit-identical).  Before that change the 1e-7 perturbation of the statistics
         flipped a ReLU gate / scatter_max winner in roughly one run out of three and moved a reader gradient by 2.6e-3.
+      * bf16 + functional.set_deterministic(True): the same treatment for the production kernels (fp64 statistics,
+        split-K slabs added in split order): forward bit-identical, every conv / BatchNorm gradient bit-identical.
       * bf16 mode: every stored activation is re-rounded to 8 mantissa bits, so ANY perturbation, however small, flips a
         few roundings in the next layer and the difference climbs to the bf16 quantisation-noise floor within a few
         layers: two identical runs differ by as much as one run differs from fp32 (3e-2 on the head maps; the ReLU-gate
@@ -397,7 +399,9 @@ def test_run_to_run_spread_of_the_gradients():
     B = 2
     ex = to_cuda(synth.make_batch([0, 1], 3000, cfg, kind="uniform", n_boxes=25, sweeps=10))
     lines = []
-    for mode, tol_fwd, tol_grad in (("split", 1e-6, 1e-5), ("bf16", 1.5e-1, 1.0)):
+    for label, tol_fwd, tol_grad in (("split", 1e-6, 1e-5), ("bf16", 1.5e-1, 1.0), ("bf16+deterministic", 0.0, 1e-5), ("split+deterministic", 0.0, 1e-5)):
+        mode = label.split("+")[0]
+        prev_det = Fn.set_deterministic(label.endswith("deterministic"))
         runs = []
         for _ in range(2):
             model, _ = build(cfg)
@@ -408,11 +412,18 @@ def test_run_to_run_spread_of_the_gradients():
                 loss.backward()
             runs.append((torch.cat([v.detach().float().reshape(-1) for pd in preds for v in pd.values()]),
                          {k: v.grad.detach().clone() for k, v in model.named_parameters()}))
+        Fn.set_deterministic(prev_det)
         fwd = rel(runs[0][0], runs[1][0])
         g = sorted((rel(runs[0][1][k], runs[1][1][k]), k) for k in runs[0][1] if runs[1][1][k].norm() > 1e-6)
         same = sum(1 for k in runs[0][1] if torch.equal(runs[0][1][k], runs[1][1][k]))
-        lines.append("%-5s head maps rel %.2e | parameter gradients rel-L2: median %.2e worst %.2e (%s) | bit-identical %d / %d" %
-                     (mode, fwd, g[len(g) // 2][0], g[-1][0], g[-1][1], same, len(runs[0][1])))
-        assert fwd < tol_fwd and g[-1][0] < tol_grad, "\n".join(lines)
+        lines.append("%-18s head maps rel %.2e | parameter gradients rel-L2: median %.2e worst %.2e (%s) | bit-identical %d / %d" %
+                     (label, fwd, g[len(g) // 2][0], g[-1][0], g[-1][1], same, len(runs[0][1])))
+        assert fwd <= tol_fwd and g[-1][0] < tol_grad, "\n".join(lines)
+        if label.endswith("deterministic"):
+            # functional.set_deterministic: ordered split-K in wgrad + fp64 BatchNorm statistics (+ the fp64 accumulators
+            # the PillarFeatureNet backward always uses) -> the forward and EVERY parameter gradient are bit-identical
+            diff = [k for k in runs[0][1] if not torch.equal(runs[0][1][k], runs[1][1][k])]
+            assert torch.equal(runs[0][0], runs[1][0]), "\n".join(lines)
+            assert not diff, (diff, lines)
     print("\n".join(lines))
     report_to_file("run_to_run_spread.txt", lines)

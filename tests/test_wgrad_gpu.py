@@ -131,3 +131,33 @@ def test_add_relu_roundtrip():
     ops.relu_bwd(dy, y, 1000, 256, g)
     assert torch.equal(g.float(), torch.where(y.float() > 0, dy.float(), torch.zeros(1, device="cuda")))
     ops.add_rows(g, b, 1000, 256)
+
+
+def test_wgrad_deterministic_partials_are_bitwise_reproducible():
+    """pnx_wgrad with a `partials` buffer: per-split slabs + ordered reduction instead of fp32 red.global.add -- equal to
+    the atomic path within accumulation-order noise, and bit-identical between two launches (the atomic path is not)."""
+    from pillarnext_b200 import ops
+    torch.manual_seed(5)
+    B, H, W, cx, cy = 2, 96, 96, 128, 64
+    M = B * H * W
+    X = torch.randn(M, cx, device="cuda").bfloat16()
+    Y = torch.randn(M, cy, device="cuda").bfloat16()
+    geo = (H, W, H, W, 3, 1, 1, 1)
+
+    def run():
+        dW = torch.zeros(9, cx, cy, device="cuda")
+        ops.wgrad(X, cx, Y, cy, M, 9, dW, dense=geo)
+        return dW
+
+    ref = run()
+    prev = ops.set_deterministic(True)
+    try:
+        assert ops.lib().pnx_wgrad_splits(cx, cy, 9, M, ops.sm_count()) > 1, "the case must exercise several K splits"
+        a, b = run(), run()
+        acc = torch.ones(9, cx, cy, device="cuda")          # accumulates into dW like the atomic path
+        ops.wgrad(X, cx, Y, cy, M, 9, acc, dense=geo)
+    finally:
+        ops.set_deterministic(prev)
+    assert torch.equal(a, b)
+    assert ((a - ref).norm() / ref.norm()).item() < 1e-5
+    assert ((acc - 1.0 - a).abs().max() / a.abs().max()).item() < 1e-5
