@@ -12,6 +12,13 @@
 //                       the reference copies the mask to the host and sweeps there).
 //   3. pnx_det_gather : decode the kept candidates into [segments, post_max, 9] boxes / scores / labels.
 // No host synchronisation inside; the caller reads the per-segment counts once.
+// Provenance note: the rotated-rectangle overlap routines below (cross3, rect_cross, in_box2d, seg_intersection,
+// det_box_overlap, det_iou_bev) deliberately follow the ARITHMETIC of the reference's own device code,
+// det3d/core/iou3d_nms/src/iou3d_nms_kernel.cu:39-235 (and its host twin iou3d_cpu.cpp), statement by statement -- same
+// operation order, same 1e-2 margin, same angular ordering of the polygon vertices: the keep / suppress decision of every
+// box pair must come out bit-identical to the reference's NMS, and any algebraically equivalent rewrite flips decisions for
+// IoUs near the threshold.  Everything around them (fused decode, 64-bit sort keys, batched per-(frame, class) mask, the
+// on-GPU sweep with up to 4 slots of 2048 candidates, `__host__ __device__` for the CPU parity leg) is this repository's.
 // Hot loop character: HBM-bound single pass (1) and a few hundred thousand polygon clips (2) -- no tensor-core work.
 #include <math.h>
 
