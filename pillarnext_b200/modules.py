@@ -43,19 +43,41 @@ class PFNLayer(nn.Module):
 
 
 class PillarNet(nn.Module):
-    """Dynamic voxelizer (pillar_encoder.py:53-125). forward(points) -> (features[Nv,10] are NOT materialised
-    here; use PillarFeatureNet) -- kept for API completeness: returns the voxelizer result object."""
+    """Dynamic voxelizer with the reference's interface (pillar_encoder.py:53-125):
+    forward(points) -> (features [Nv, 10], coords [P, 3] int32 (b, y, x), unq_inv [Nv] int64, grid_size (Gy, Gx)).
+    The indices come from the CUDA voxelizer (bit-exact with torch.unique); the decorated point features are materialised
+    here only for callers of THIS module -- PillarFeatureNet never builds them (pnx_pfn_lin0 fuses the decoration into the
+    first linear layer).  The voxelizer result rides along as `features._pnx_vox`."""
 
     def __init__(self, num_input_features, voxel_size, pc_range):
         super().__init__()
         self.voxel_size = np.array(voxel_size)
         self.pc_range = np.array(pc_range)
 
-    def forward(self, points, batch_size=None, frame_sorted=False):
+    def voxelize(self, points, batch_size=None, frame_sorted=False):
         _require_cuda(points, "PillarNet")
         if batch_size is None:
             batch_size = int(points[:, 0].max().item()) + 1 if points.shape[0] else 1
         return ops.voxelize(points, batch_size, self.voxel_size, self.pc_range, frame_sorted=frame_sorted)
+
+    def forward(self, points, batch_size=None):
+        points = points.float()
+        vox = self.voxelize(points, batch_size)
+        P, _ = vox.sync_counts()
+        pop = vox.pillar_of_point[:points.shape[0]]
+        keep = pop >= 0                                                    # :98-103 range mask
+        pts = points[keep]
+        unq_inv = pop[keep].long()
+        coords = vox.coords[:P]                                            # (b, y, x) = unq[:, [0, 2, 1]]
+        vs = torch.tensor(self.voxel_size[:2], dtype=points.dtype, device=points.device)
+        pr = torch.tensor(self.pc_range[:2], dtype=points.dtype, device=points.device)
+        mean = ops.pillar_mean(vox)[:P]                                    # :113-114
+        f_cluster = pts[:, 1:4] - mean[unq_inv]                            # :116
+        cxy = coords[unq_inv][:, [2, 1]].to(points.dtype)                  # (xi, yi) of the point's pillar
+        f_center = pts[:, 1:3] - (cxy * vs.unsqueeze(0) + vs.unsqueeze(0) / 2 + pr.unsqueeze(0))   # :119-120
+        features = torch.cat([pts[:, 1:], f_cluster, f_center], dim=-1)    # :123
+        features._pnx_vox = vox
+        return features, coords, unq_inv, ops.grid_size_xy(self.voxel_size, self.pc_range)[[1, 0]]
 
 
 class Pyramid:

@@ -181,6 +181,15 @@ def voxelize(points, batch, voxel_size, pc_range, buckets=True, frame_sorted=Fal
     return v
 
 
+def pillar_mean(v):
+    """Per-pillar mean of (x, y, z) (pnx_pfn_mean; pillar_encoder.py:113-114 scatter_mean): [cap_p, 3] fp32, rows >= P
+    undefined.  Needs the CSR buckets (voxelize(..., buckets=True))."""
+    mean = torch.empty(max(v.cap_p, 1), 3, dtype=torch.float32, device=v.points.device)
+    _count(1)
+    check(lib().pnx_pfn_mean(ptr(v.points), ptr(v.bucket_off), ptr(v.bucket_pts), ptr(v.counts), v.cap_p, ptr(mean), stream()))
+    return mean
+
+
 # --------------------------------------------------------------------------------- BatchNorm stats
 def bn_finalize(stats, channels, count_ptr, count_mult, gamma, beta, eps, momentum, running_mean, running_var,
                 want_saved=True):

@@ -180,3 +180,19 @@ def test_pfn_forward_matches_oracle():
                     key = "reader.pfn_layers.%d.norm.%s" % (i, k)
                     e = (d[key].cpu() - st[key]).abs().max().item()
                     assert e < 1e-4, (key, e)
+
+
+def test_pillarnet_module_returns_the_reference_tuple():
+    """modules.PillarNet.forward = the reference's (features, coords, unq_inv, grid_size) (pillar_encoder.py:78-125)."""
+    from pillarnext_b200 import modules
+    cfg = synth.NUSC
+    pts = synth.collate_points([synth.make_frame(s, 9000, cfg, "lidar", sweeps=10) for s in range(2)])
+    net = modules.PillarNet(5, cfg["voxel_size"], cfg["pc_range"])
+    feats, coords, inv, grid = net(pts.cuda())
+    ref = O.voxelize(pts, cfg["voxel_size"], cfg["pc_range"])
+    assert torch.equal(coords.cpu(), ref["coords"]) and torch.equal(inv.cpu(), ref["unq_inv"])
+    assert list(grid) == list(ref["grid"])
+    assert feats.shape == ref["features"].shape
+    assert torch.equal(feats[:, :5].cpu(), ref["features"][:, :5])                       # the points themselves
+    assert torch.equal(feats[:, 8:].cpu(), ref["features"][:, 8:])                       # f_center: same fp32 expression
+    assert (feats[:, 5:8].cpu() - ref["features"][:, 5:8]).abs().max().item() < 2e-5     # f_cluster: mean summation order
